@@ -1,0 +1,101 @@
+"""Build libb2a.so (sm_100a) in-tree with nvcc.  No GPU needed: nvcc cross-compiles.
+
+    python -m audio_processor_b200.build            # incremental
+    python -m audio_processor_b200.build --force
+
+The tap-table header csrc/fir_taps_gen.inc is regenerated from tools/gen_fir_taps.cpp
+(the same double-precision design code the runtime uses, csrc/fir_design.h).
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "_build")
+LIB = os.path.join(HERE, "libb2a.so")
+
+SOURCES = [
+    "b2a_host.cu", "logmel.cu", "silence.cu", "resample.cu", "pipeline.cu", "fir_fast_dispatch.cu",
+    "fir_fast_44100_s16x2.cu", "fir_fast_44100_s16x1.cu", "fir_fast_48000_s16x2.cu", "fir_fast_48000_s16x1.cu",
+]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc() -> str:
+    cand = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(cand):
+        raise RuntimeError("nvcc not found: libb2a.so can only be built with the CUDA toolkit")
+    return cand
+
+
+def _deps_mtime() -> float:
+    m = 0.0
+    for d in (CSRC, os.path.join(ROOT, "include")):
+        for f in os.listdir(d):
+            if f.endswith((".cuh", ".h", ".inc")):
+                m = max(m, os.path.getmtime(os.path.join(d, f)))
+    return m
+
+
+def gen_taps(force: bool = False) -> None:
+    out = os.path.join(CSRC, "fir_taps_gen.inc")
+    src = os.path.join(ROOT, "tools", "gen_fir_taps.cpp")
+    dep = max(os.path.getmtime(src), os.path.getmtime(os.path.join(CSRC, "fir_design.h")))
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= dep:
+        return
+    os.makedirs(OBJ, exist_ok=True)
+    exe = os.path.join(OBJ, "gen_fir_taps")
+    subprocess.run(["g++", "-O2", "-o", exe, src], check=True)
+    subprocess.run([exe, out], check=True)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    nvcc = _nvcc()
+    os.makedirs(OBJ, exist_ok=True)
+    gen_taps(force)
+    dep_m = _deps_mtime()
+    jobs = []
+    for s in SOURCES:
+        src = os.path.join(CSRC, s)
+        obj = os.path.join(OBJ, s[:-3] + ".o")
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), dep_m):
+            jobs.append((src, obj))
+
+    def compile_one(job):
+        src, obj = job
+        cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-c", src, "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas")
+            cmd.insert(2, "-v")
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {os.path.basename(src)}:\n{r.stdout}\n{r.stderr}")
+        return r.stderr
+
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+            logs = list(ex.map(compile_one, jobs))
+        if verbose:
+            for (src, _), lg in zip(jobs, logs):
+                print(f"== {os.path.basename(src)}\n{lg}")
+    objs = [os.path.join(OBJ, s[:-3] + ".o") for s in SOURCES]
+    if jobs or not os.path.exists(LIB):
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcudart"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,208 @@
+// b2a_host.cu — host side of libb2a: error slot, table designs (double precision), device table cache.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
+#include <vector>
+
+#include "b2a_tables.cuh"
+#include "fir_design.h"
+
+namespace b2a {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
+    return B2A_ECUDA;
+}
+
+// resampler design lives in fir_design.h (shared with tools/gen_fir_taps.cpp)
+static long long gcd_ll(long long a, long long b) { return b2a_design::gcd_ll(a, b); }
+
+void design_resampler_host(int in_rate, int out_rate, int* L_out, int* M_out, int* taps_out, float** h_taps_out) {
+    b2a_design::design_resampler(in_rate, out_rate, L_out, M_out, taps_out, h_taps_out);
+}
+
+// ---- slaney mel filterbank (librosa.filters.mel(sr=16000, n_fft=400, n_mels), whisper mel_filters.npz)
+static double hz_to_mel(double f) {
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
+    const double logstep = std::log(6.4) / 27.0;
+    return f >= min_log_hz ? min_log_mel + std::log(f / min_log_hz) / logstep : f / f_sp;
+}
+static double mel_to_hz(double m) {
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
+    const double logstep = std::log(6.4) / 27.0;
+    return m >= min_log_mel ? min_log_hz * std::exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+
+void design_mel_host(int n_mels, float* filters) {
+    const int nb = kNBins;
+    const double sr = (double)kSampleRate;
+    std::vector<double> fftf(nb), melf(n_mels + 2);
+    for (int k = 0; k < nb; k++) fftf[k] = (sr / 2.0) * (double)k / (double)(nb - 1);
+    double m0 = hz_to_mel(0.0), m1 = hz_to_mel(sr / 2.0);
+    for (int i = 0; i < n_mels + 2; i++) melf[i] = mel_to_hz(m0 + (m1 - m0) * (double)i / (double)(n_mels + 1));
+    for (int i = 0; i < n_mels; i++) {
+        double fd0 = melf[i + 1] - melf[i], fd1 = melf[i + 2] - melf[i + 1];
+        double enorm = 2.0 / (melf[i + 2] - melf[i]);
+        for (int k = 0; k < nb; k++) {
+            double lower = (fftf[k] - melf[i]) / fd0;
+            double upper = (melf[i + 2] - fftf[k]) / fd1;
+            double w = std::fmax(0.0, std::fmin(lower, upper));
+            filters[(size_t)i * nb + k] = (float)(w * enorm);
+        }
+    }
+}
+
+// ---- device table cache ------------------------------------------------------------------------
+static std::mutex g_mu;
+static std::map<std::pair<int, int>, LogMelTables*> g_logmel;                       // (device, n_mels)
+static std::map<std::pair<int, std::pair<int, int>>, ResampleDesign*> g_resample;   // (device, (in, out))
+
+const LogMelTables* get_logmel_tables(int n_mels) {
+    if (n_mels != 80 && n_mels != 128) { set_error("n_mels must be 80 or 128 (got %d)", n_mels); return nullptr; }
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { cuda_fail(e, "cudaGetDevice"); return nullptr; }
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto key = std::make_pair(dev, n_mels);
+    auto it = g_logmel.find(key);
+    if (it != g_logmel.end()) return it->second;
+
+    LogMelTables* h = (LogMelTables*)calloc(1, sizeof(LogMelTables));
+    const double kPi = 3.14159265358979323846;
+    for (int n = 0; n < kNFFT; n++) h->win[n] = (float)(0.5 - 0.5 * std::cos(2.0 * kPi * n / kNFFT));
+    for (int n2 = 0; n2 < 20; n2++)
+        for (int k1 = 0; k1 < 10; k1++) {
+            double a = -2.0 * kPi * (double)(n2 * k1) / 200.0;
+            h->tw200[n2 * 10 + k1] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+    for (int k = 0; k < kNBins; k++) {
+        double a = 2.0 * kPi * (double)k / 400.0;
+        h->tw400[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+    std::vector<float> filt((size_t)n_mels * kNBins);
+    design_mel_host(n_mels, filt.data());
+    h->n_mels = n_mels;
+    for (int m = 0; m < n_mels; m++) {
+        int first = -1, last = -1;
+        for (int k = 0; k < kNBins; k++)
+            if (filt[(size_t)m * kNBins + k] != 0.0f) { if (first < 0) first = k; last = k; }
+        if (first < 0) { first = 0; last = -1; }
+        int len = last - first + 1;
+        if (len > kMelMaxWidth) { free(h); set_error("mel filter %d wider than %d bins", m, kMelMaxWidth); return nullptr; }
+        h->mel_start[m] = first;
+        h->mel_len[m] = len;
+        for (int j = 0; j < len; j++) h->mel_w[m * kMelMaxWidth + j] = filt[(size_t)m * kNBins + first + j];
+    }
+    LogMelTables* d = nullptr;
+    e = cudaMalloc((void**)&d, sizeof(LogMelTables));
+    if (e == cudaSuccess) e = cudaMemcpy(d, h, sizeof(LogMelTables), cudaMemcpyHostToDevice);
+    free(h);
+    if (e != cudaSuccess) { cuda_fail(e, "log-mel table upload"); return nullptr; }
+    g_logmel[key] = d;
+    return d;
+}
+
+const ResampleDesign* get_resample_design(int in_rate, int out_rate) {
+    if (in_rate <= 0 || out_rate <= 0) { set_error("bad sample rate %d -> %d", in_rate, out_rate); return nullptr; }
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { cuda_fail(e, "cudaGetDevice"); return nullptr; }
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto key = std::make_pair(dev, std::make_pair(in_rate, out_rate));
+    auto it = g_resample.find(key);
+    if (it != g_resample.end()) return it->second;
+    ResampleDesign* r = (ResampleDesign*)calloc(1, sizeof(ResampleDesign));
+    float* h = nullptr;
+    design_resampler_host(in_rate, out_rate, &r->L, &r->M, &r->taps, &h);
+    if ((size_t)r->L * r->taps > (size_t)(1 << 22)) {
+        free(h); free(r);
+        set_error("rate pair %d -> %d needs %d phases: unsupported", in_rate, out_rate, r->L);
+        return nullptr;
+    }
+    r->in_rate = in_rate; r->out_rate = out_rate;
+    r->center = (r->taps - 1) / 2;
+    r->h_taps = h;
+    float* d = nullptr;
+    size_t bytes = sizeof(float) * (size_t)r->L * r->taps;
+    e = cudaMalloc((void**)&d, bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { free(h); free(r); cuda_fail(e, "resampler tap upload"); return nullptr; }
+    r->d_taps = d;
+    g_resample[key] = r;
+    return r;
+}
+
+}  // namespace b2a
+
+extern "C" {
+
+int b2a_version(void) { return 100; }  // 0.1.0
+
+const char* b2a_last_error(void) { return b2a::g_err; }
+
+int64_t b2a_launch_count(void) { return (int64_t)b2a::g_launches.load(std::memory_order_relaxed); }
+
+int b2a_resample_ntaps(int in_rate, int out_rate, int* phases) {
+    if (in_rate <= 0 || out_rate <= 0) { b2a::set_error("bad sample rate"); return B2A_EINVAL; }
+    int L, M, taps; float* h = nullptr;
+    b2a::design_resampler_host(in_rate, out_rate, &L, &M, &taps, &h);
+    free(h);
+    if (phases) *phases = L;
+    return taps;
+}
+
+int b2a_resample_taps(int in_rate, int out_rate, float* h_taps, size_t capacity_floats) {
+    if (in_rate <= 0 || out_rate <= 0 || !h_taps) { b2a::set_error("bad argument"); return B2A_EINVAL; }
+    int L, M, taps; float* h = nullptr;
+    b2a::design_resampler_host(in_rate, out_rate, &L, &M, &taps, &h);
+    size_t n = (size_t)L * taps;
+    if (capacity_floats < n) { free(h); b2a::set_error("capacity %zu < %zu", capacity_floats, n); return B2A_EINVAL; }
+    memcpy(h_taps, h, n * sizeof(float));
+    free(h);
+    return B2A_OK;
+}
+
+int b2a_mel_filters(int n_mels, float* h_filters, size_t capacity_floats) {
+    if ((n_mels != 80 && n_mels != 128) || !h_filters || capacity_floats < (size_t)n_mels * b2a::kNBins) {
+        b2a::set_error("bad argument");
+        return B2A_EINVAL;
+    }
+    b2a::design_mel_host(n_mels, h_filters);
+    return B2A_OK;
+}
+
+int64_t b2a_resample_out_len(int64_t n_in, int in_rate, int out_rate) {
+    if (n_in <= 0 || in_rate <= 0 || out_rate <= 0) return 0;
+    long long g = b2a::gcd_ll(in_rate, out_rate);
+    long long L = out_rate / g, M = in_rate / g;
+    if (L == 1 && M == 1) return n_in;
+    return (int64_t)(((__int128)n_in * L + M - 1) / M);   // ceil: every output whose centre tap is inside the input
+}
+
+int64_t b2a_energy_len(int64_t n_out, int out_rate) {
+    if (n_out <= 0 || out_rate <= 0 || out_rate % 1000) return 0;
+    int spm = out_rate / 1000;
+    return (n_out + spm - 1) / spm;
+}
+
+int64_t b2a_log_mel_frames(int64_t n, int64_t padding) { return (n + padding) / b2a::kHop; }
+
+}  // extern "C"

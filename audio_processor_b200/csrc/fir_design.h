@@ -1,0 +1,58 @@
+// fir_design.h — libswresample's default resampling filter, restated (host, double precision).
+//
+// Reference behaviour: FFmpeg libswresample (resample.c build_filter) as driven by
+//   ffmpeg -ar 16000 -ac 1 -c:a pcm_s16le      (/root/reference/app/services/audio_processor.py:912-920)
+// with no resampler options => filter_size 32, phase_shift 10, exact_rational, cutoff 0.97,
+// Kaiser window beta 9.  See SURVEY.md A.1 and oracle/resample_oracle.py (float64 restatement,
+// pinned against the real library).  Header-only so that the build-time tap-table generator
+// (tools/gen_fir_taps.cpp) and the runtime library produce bit-identical float taps.
+#pragma once
+#include <cmath>
+#include <cstdlib>
+#include <vector>
+
+namespace b2a_design {
+
+static inline long long gcd_ll(long long a, long long b) { while (b) { long long t = a % b; a = b; b = t; } return a; }
+
+static inline double bessel_i0(double x) {
+    // power series sum_k ((x/2)^(2k) / (k!)^2); x <= 9 here, converges in < 40 terms
+    double q = x * x * 0.25, term = 1.0, sum = 1.0;
+    for (int k = 1; k < 200; k++) {
+        term *= q / ((double)k * (double)k);
+        sum += term;
+        if (term < sum * 1e-18) break;
+    }
+    return sum;
+}
+
+// h_taps_out: malloc'ed float[L][taps]; every phase normalised to unit DC gain.
+static inline void design_resampler(int in_rate, int out_rate, int* L_out, int* M_out, int* taps_out, float** h_taps_out) {
+    const double kCutoff = 0.97, kBeta = 9.0;
+    const int kFilterSize = 32;
+    long long g = gcd_ll(in_rate, out_rate);
+    int L = (int)(out_rate / g), M = (int)(in_rate / g);
+    double factor = std::fmin((double)out_rate * kCutoff / (double)in_rate, 1.0);
+    int taps = (int)std::ceil(kFilterSize / factor);
+    taps = (taps + 1) & ~1;
+    int center = (taps - 1) / 2;
+    float* h = (float*)malloc(sizeof(float) * (size_t)L * taps);
+    std::vector<double> row(taps);
+    const double kPi = 3.14159265358979323846;
+    for (int ph = 0; ph < L; ph++) {
+        double norm = 0.0;
+        for (int i = 0; i < taps; i++) {
+            double x = kPi * ((double)(i - center) - (double)ph / (double)L) * factor;
+            double y = (x == 0.0) ? 1.0 : std::sin(x) / x;
+            double w = 2.0 * x / (factor * taps * kPi);
+            double t = 1.0 - w * w;
+            y *= bessel_i0(kBeta * std::sqrt(t > 0.0 ? t : 0.0));
+            row[i] = y;
+            norm += y;
+        }
+        for (int i = 0; i < taps; i++) h[(size_t)ph * taps + i] = (float)(row[i] / norm);
+    }
+    *L_out = L; *M_out = M; *taps_out = taps; *h_taps_out = h;
+}
+
+}  // namespace b2a_design

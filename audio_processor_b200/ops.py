@@ -1,0 +1,304 @@
+"""Tensor-level entry points over the C ABI (include/b2a.h).
+
+PyTorch is plumbing here: it owns device memory (caching allocator), streams and
+torch.distributed.  Every function enqueues on torch's current CUDA stream and returns
+device tensors without synchronising; results whose size is data dependent (kept samples,
+frame count, range tables) are exposed through small result objects that synchronise
+lazily when the host asks for them.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Union
+
+from . import _abi
+from ._lib import check, lib, require_cuda
+
+SAMPLE_RATE = 16000
+DEFAULT_SEG_CAP = 8192
+
+
+def _stream(torch) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t) -> Optional[C.c_void_p]:
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _fmt(torch, t) -> int:
+    if t.dtype == torch.int16:
+        return _abi.FMT_S16
+    if t.dtype == torch.float32:
+        return _abi.FMT_F32
+    raise TypeError(f"PCM must be int16 or float32, got {t.dtype}")
+
+
+def _as_cuda_pcm(torch, pcm, device=None):
+    import numpy as np
+    if isinstance(pcm, np.ndarray):
+        pcm = torch.from_numpy(np.ascontiguousarray(pcm))
+    if not torch.is_tensor(pcm):
+        raise TypeError("expected a torch.Tensor or numpy array")
+    if not pcm.is_cuda:
+        pcm = pcm.to(device if device is not None else "cuda", non_blocking=True)
+    return pcm.contiguous()
+
+
+def launch_count() -> int:
+    """kernels launched by libb2a so far in this process (diagnostics / bench `gpu_launches`)."""
+    return int(lib().b2a_launch_count())
+
+
+def resample_out_len(n_in: int, in_rate: int, out_rate: int = SAMPLE_RATE) -> int:
+    return int(lib().b2a_resample_out_len(int(n_in), int(in_rate), int(out_rate)))
+
+
+def resample(pcm, in_rate: int, out_rate: int = SAMPLE_RATE, *, want_s16: bool = True, want_f32: bool = False,
+             want_energy: bool = False):
+    """[n] or [n, C] int16/float32 PCM -> mono at out_rate.  Returns (s16, f32, energy_ms) with None for
+    outputs not requested.  Equivalent of ``ffmpeg -ar out_rate -ac 1 -c:a pcm_s16le`` on raw PCM
+    (reference: app/services/audio_processor.py:912-923)."""
+    torch = require_cuda()
+    x = _as_cuda_pcm(torch, pcm)
+    ch = 1 if x.dim() == 1 else int(x.shape[1])
+    n_in = int(x.shape[0])
+    with torch.cuda.device(x.device):
+        n_out = resample_out_len(n_in, in_rate, out_rate)
+        s16 = torch.empty(n_out + 16, dtype=torch.int16, device=x.device) if want_s16 else None
+        f32 = torch.empty(n_out + 16, dtype=torch.float32, device=x.device) if want_f32 else None
+        en = None
+        if want_energy:
+            ne = int(lib().b2a_energy_len(n_out, out_rate))
+            en = torch.empty(ne + 2, dtype=torch.int64, device=x.device)
+        check(lib().b2a_resample(_ptr(x), _fmt(torch, x), ch, int(in_rate), n_in, int(out_rate), _ptr(s16), _ptr(f32),
+                                 _ptr(en), _stream(torch)))
+    return (s16[:n_out] if s16 is not None else None, f32[:n_out] if f32 is not None else None,
+            en[:-2] if en is not None else None)
+
+
+def _params(min_silence_len, silence_thresh, keep_silence, seek_step) -> _abi.SilenceParams:
+    if isinstance(keep_silence, bool):
+        keep = -1 if keep_silence else 0
+    else:
+        keep = int(keep_silence)
+        if keep < 0:
+            raise ValueError("keep_silence must be >= 0 or a bool")
+    return _abi.SilenceParams(int(min_silence_len), keep, int(seek_step), 0, float(silence_thresh))
+
+
+@dataclass
+class SilenceResult:
+    """Device-side result of detect(); host views synchronise on first access."""
+    silent_ms: "object"
+    nonsilent_ms: "object"
+    kept_ms: "object"
+    kept_off: "object"
+    info: "object"
+    cap: int
+    _host: Optional[dict] = None
+
+    def _sync(self) -> dict:
+        if self._host is None:
+            info = self.info.cpu().tolist()
+            if info[_abi.INFO_OVERFLOW]:
+                raise RuntimeError(f"more than cap={self.cap} silence ranges; raise `cap`")
+            ns, nn, nk = info[_abi.INFO_N_SILENT], info[_abi.INFO_N_NONSILENT], info[_abi.INFO_N_KEPT]
+            self._host = dict(
+                info=info,
+                silent=self.silent_ms[:ns].cpu().tolist(),
+                nonsilent=self.nonsilent_ms[:nn].cpu().tolist(),
+                kept=self.kept_ms[:nk].cpu().tolist(),
+            )
+        return self._host
+
+    @property
+    def silent(self) -> List[List[int]]:
+        return self._sync()["silent"]
+
+    @property
+    def nonsilent(self) -> List[List[int]]:
+        return self._sync()["nonsilent"]
+
+    @property
+    def kept(self) -> List[List[int]]:
+        return self._sync()["kept"]
+
+    @property
+    def len_ms(self) -> int:
+        return int(self._sync()["info"][_abi.INFO_LEN_MS])
+
+    @property
+    def n_keep(self) -> int:
+        return int(self._sync()["info"][_abi.INFO_N_KEEP])
+
+
+def energy_ms(pcm16, sample_rate: int = SAMPLE_RATE):
+    torch = require_cuda()
+    x = _as_cuda_pcm(torch, pcm16)
+    if x.dtype != torch.int16 or x.dim() != 1:
+        raise TypeError("energy_ms expects mono int16 PCM")
+    n = int(x.shape[0])
+    with torch.cuda.device(x.device):
+        ne = int(lib().b2a_energy_len(n, sample_rate))
+        en = torch.empty(ne + 2, dtype=torch.int64, device=x.device)
+        if n > 0:
+            check(lib().b2a_energy_ms(_ptr(x), n, int(sample_rate), _ptr(en), _stream(torch)))
+    return en[:ne]
+
+
+def detect(pcm16, sample_rate: int = SAMPLE_RATE, min_silence_len: int = 1000, silence_thresh: float = -16,
+           keep_silence: Union[int, bool] = 100, seek_step: int = 1, *, energy=None, cap: int = DEFAULT_SEG_CAP) -> SilenceResult:
+    """pydub detect_silence / detect_nonsilent / split_on_silence ranges for mono int16 PCM, on the GPU."""
+    torch = require_cuda()
+    x = _as_cuda_pcm(torch, pcm16)
+    if x.dtype != torch.int16 or x.dim() != 1:
+        raise TypeError("detect expects mono int16 PCM")
+    n = int(x.shape[0])
+    prm = _params(min_silence_len, silence_thresh, keep_silence, seek_step)
+    with torch.cuda.device(x.device):
+        if energy is None:
+            energy = energy_ms(x, sample_rate)
+        dev = x.device
+        sil = torch.zeros((cap, 2), dtype=torch.int32, device=dev)
+        ns = torch.zeros((cap, 2), dtype=torch.int32, device=dev)
+        kp = torch.zeros((cap, 2), dtype=torch.int32, device=dev)
+        koff = torch.zeros(cap + 2, dtype=torch.int64, device=dev)
+        info = torch.zeros(_abi.INFO_LEN, dtype=torch.int64, device=dev)
+        wsb = int(lib().b2a_silence_workspace_bytes(n, sample_rate))
+        ws = torch.empty(wsb + 256, dtype=torch.uint8, device=dev)
+        if energy.numel() == 0:
+            energy = torch.zeros(2, dtype=torch.int64, device=dev)
+        check(lib().b2a_detect_silence(_ptr(energy), n, int(sample_rate), C.byref(prm), int(cap), _ptr(sil), _ptr(ns),
+                                       _ptr(kp), _ptr(koff), _ptr(info), _ptr(ws), wsb, _stream(torch)))
+    return SilenceResult(sil, ns, kp, koff, info, cap)
+
+
+def compact(pcm16, res: SilenceResult, sample_rate: int = SAMPLE_RATE):
+    """Concatenate the kept ranges (pydub `+`).  Returns (buffer, res.info): the first info[N_KEEP] samples of
+    `buffer` are valid; slicing needs the host value (res.n_keep)."""
+    torch = require_cuda()
+    x = _as_cuda_pcm(torch, pcm16)
+    n = int(x.shape[0])
+    with torch.cuda.device(x.device):
+        out = torch.empty(n + 64, dtype=torch.int16, device=x.device)
+        if n > 0:
+            check(lib().b2a_compact(_ptr(x), n, int(sample_rate), _ptr(res.kept_ms), _ptr(res.kept_off), _ptr(res.info),
+                                    _ptr(out), n + 64, _stream(torch)))
+    return out
+
+
+def log_mel(audio, n_mels: int = 80, padding: int = 0, *, per_clip_max: bool = False):
+    """Whisper log-mel of [n] or [B, n] float32 (+-1.0) or int16 audio -> [n_mels, T] / [B, n_mels, T] float32."""
+    torch = require_cuda()
+    x = _as_cuda_pcm(torch, audio)
+    if x.dim() not in (1, 2):
+        raise ValueError("audio must be 1-D or 2-D")
+    batch = 1 if x.dim() == 1 else int(x.shape[0])
+    n = int(x.shape[-1])
+    with torch.cuda.device(x.device):
+        T = int(lib().b2a_log_mel_frames(n, padding))
+        out = torch.empty((batch, n_mels, T), dtype=torch.float32, device=x.device)
+        wsb = int(lib().b2a_log_mel_workspace_bytes(batch, n, padding))
+        ws = torch.empty(wsb + 256, dtype=torch.uint8, device=x.device)
+        check(lib().b2a_log_mel(_ptr(x), _fmt(torch, x), batch, n, n, None, int(padding), int(n_mels),
+                                _abi.NORM_PER_CLIP if per_clip_max else _abi.NORM_WHISPER, _ptr(out), None, _ptr(ws), wsb,
+                                _stream(torch)))
+    return out[0] if x.dim() == 1 else out
+
+
+class PipelinePlan:
+    """Pre-allocated buffers for running the whole path on clips of one shape (no allocation per call)."""
+
+    def __init__(self, n_in: int, in_rate: int, channels: int, dtype, n_mels: int = 80, padding: int = 0,
+                 cap: int = DEFAULT_SEG_CAP, device=None):
+        torch = require_cuda()
+        self.torch = torch
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.n_in, self.in_rate, self.channels, self.dtype = int(n_in), int(in_rate), int(channels), dtype
+        self.n_mels, self.padding, self.cap = int(n_mels), int(padding), int(cap)
+        self.fmt = _abi.FMT_S16 if dtype == torch.int16 else _abi.FMT_F32
+        with torch.cuda.device(self.device):
+            self.n16 = resample_out_len(self.n_in, self.in_rate, SAMPLE_RATE)
+            self.t_cap = (self.n16 + 16 + self.padding) // 160
+            self.pcm = torch.empty(self.n16 + 64, dtype=torch.int16, device=self.device)
+            self.mel = torch.empty(self.n_mels * max(self.t_cap, 1), dtype=torch.float32, device=self.device)
+            self.nonsilent = torch.zeros((self.cap, 2), dtype=torch.int32, device=self.device)
+            self.kept = torch.zeros((self.cap, 2), dtype=torch.int32, device=self.device)
+            self.info = torch.zeros(_abi.INFO_LEN, dtype=torch.int64, device=self.device)
+            self.ws_bytes = int(lib().b2a_pipeline_workspace_bytes(self.n_in, self.in_rate, self.padding, self.cap))
+            self.ws = torch.empty(self.ws_bytes + 512, dtype=torch.uint8, device=self.device)
+            off = (-self.ws.data_ptr()) % 256
+            self._ws_ptr = C.c_void_p(self.ws.data_ptr() + off)
+
+    def run(self, pcm, *, trim: bool = True, min_silence_len: int = 1000, silence_thresh: float = -40,
+            keep_silence: Union[int, bool] = 200, seek_step: int = 1) -> "PipelineResult":
+        torch = self.torch
+        x = pcm
+        if (not x.is_cuda) or x.dtype != self.dtype or not x.is_contiguous():
+            raise ValueError("PipelinePlan.run expects a contiguous CUDA tensor of the planned dtype")
+        ch = 1 if x.dim() == 1 else int(x.shape[1])
+        if int(x.shape[0]) != self.n_in or ch != self.channels:
+            raise ValueError("clip shape differs from the plan")
+        prm = _params(min_silence_len, silence_thresh, keep_silence, seek_step) if trim else None
+        with torch.cuda.device(self.device):
+            check(lib().b2a_pipeline(_ptr(x), self.fmt, ch, self.in_rate, self.n_in, C.byref(prm) if prm is not None else None,
+                                     self.n_mels, self.padding, self.cap, _ptr(self.pcm), _ptr(self.mel),
+                                     _ptr(self.nonsilent), _ptr(self.kept), _ptr(self.info), self._ws_ptr, self.ws_bytes,
+                                     _stream(torch)))
+        return PipelineResult(self)
+
+
+class PipelineResult:
+    """View over a PipelinePlan's output buffers (valid until the plan runs again)."""
+
+    def __init__(self, plan: PipelinePlan):
+        self.plan = plan
+        self._info = None
+
+    def info(self) -> List[int]:
+        if self._info is None:
+            self._info = self.plan.info.cpu().tolist()       # the one synchronising read of the path
+            if self._info[_abi.INFO_OVERFLOW]:
+                raise RuntimeError(f"more than cap={self.plan.cap} silence ranges; raise `cap`")
+        return self._info
+
+    @property
+    def n_keep(self) -> int:
+        return int(self.info()[_abi.INFO_N_KEEP])
+
+    @property
+    def n_frames(self) -> int:
+        return int(self.info()[_abi.INFO_N_FRAMES])
+
+    @property
+    def pcm(self):
+        """trimmed 16 kHz mono int16 PCM (device)"""
+        return self.plan.pcm[: self.n_keep]
+
+    @property
+    def mel(self):
+        """[n_mels, T] float32 Whisper log-mel (device)"""
+        T = self.n_frames
+        return self.plan.mel[: self.plan.n_mels * T].view(self.plan.n_mels, T)
+
+    @property
+    def nonsilent(self) -> List[List[int]]:
+        return self.plan.nonsilent[: int(self.info()[_abi.INFO_N_NONSILENT])].cpu().tolist()
+
+    @property
+    def kept(self) -> List[List[int]]:
+        return self.plan.kept[: int(self.info()[_abi.INFO_N_KEPT])].cpu().tolist()
+
+
+def pipeline(pcm, in_rate: int, *, n_mels: int = 80, padding: int = 0, trim: bool = True, min_silence_len: int = 1000,
+             silence_thresh: float = -40, keep_silence: Union[int, bool] = 200, seek_step: int = 1,
+             cap: int = DEFAULT_SEG_CAP) -> PipelineResult:
+    """One-shot convenience wrapper: convert -> strip silence -> log-mel for a single clip."""
+    torch = require_cuda()
+    x = _as_cuda_pcm(torch, pcm)
+    ch = 1 if x.dim() == 1 else int(x.shape[1])
+    plan = PipelinePlan(int(x.shape[0]), in_rate, ch, x.dtype, n_mels=n_mels, padding=padding, cap=cap, device=x.device)
+    return plan.run(x, trim=trim, min_silence_len=min_silence_len, silence_thresh=silence_thresh,
+                    keep_silence=keep_silence, seek_step=seek_step)

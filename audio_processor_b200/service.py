@@ -1,0 +1,111 @@
+"""Host-side mirror of the reference's hot-path helpers — same names, arguments and error behaviour as
+``AudioProcessor.convert_to_wav`` / ``AudioProcessor.preprocess_audio``
+(/root/reference/app/services/audio_processor.py:901-930 and :305-314), so the Flask job workers can
+call them unchanged (INTEGRATION.md shows the two-line patch).
+
+    fe = AudioFrontend()
+    wav = fe.convert_to_wav("/tmp/job/meeting.wav")      # -> "/tmp/job/meeting.wav" rewritten as 16 kHz mono s16
+    wav = fe.preprocess_audio(wav)                       # -> silence-stripped WAV (new path)
+    mel = fe.log_mel(wav)                                # what model.transcribe computes first
+"""
+from __future__ import annotations
+
+import logging
+import os
+import subprocess
+from typing import List, Optional, Tuple, Union
+
+import numpy as np
+
+from . import ops, wavio, whisper_audio
+
+
+class AudioFrontend:
+    """GPU implementation of the convert -> strip-silence -> log-mel front-end.
+
+    Silence parameters are pydub's (min_silence_len / silence_thresh / keep_silence / seek_step)."""
+
+    def __init__(self, min_silence_len: int = 1000, silence_thresh: float = -40, keep_silence: Union[int, bool] = 200,
+                 seek_step: int = 1, n_mels: int = 80, strip_silence: bool = True, device: Optional[str] = None):
+        self.min_silence_len = min_silence_len
+        self.silence_thresh = silence_thresh
+        self.keep_silence = keep_silence
+        self.seek_step = seek_step
+        self.n_mels = n_mels
+        self.strip_silence = strip_silence
+        self.device = device
+        self.last_segments: Optional[List[List[int]]] = None   # kept [start_ms, end_ms] of the last preprocess_audio
+
+    # -- convert_to_wav (audio_processor.py:901-930) ----------------------------------------------------
+    def convert_to_wav(self, input_path: str) -> str:
+        """轉換檔案為 WAV 格式 (16kHz 單聲道) — returns ``<dirname>/<stem>.wav`` and overwrites it (`-y`)."""
+        logging.info(f"🔄 轉換檔案格式為 WAV: {os.path.basename(input_path)}")
+        output_dir = os.path.dirname(input_path)
+        output_filename = f"{os.path.splitext(os.path.basename(input_path))[0]}.wav"
+        output_path = os.path.join(output_dir, output_filename)
+        try:
+            pcm, rate = wavio.read_wav(input_path)
+            s16, _, _ = ops.resample(self._to_device(pcm), rate, ops.SAMPLE_RATE)
+            wavio.write_wav_s16(output_path, s16.cpu().numpy(), ops.SAMPLE_RATE)
+            logging.info(f"✅ 檔案轉換完成: {output_filename}")
+            return output_path
+        except (wavio.UnsupportedAudio, OSError, RuntimeError) as e:
+            # the reference lets subprocess.CalledProcessError escape (:928-930); keep the caller's except clause working
+            logging.error(f"❌ 檔案轉換失敗: {e}")
+            raise subprocess.CalledProcessError(1, ["b2a_resample", input_path], stderr=str(e).encode()) from e
+
+    # -- preprocess_audio (audio_processor.py:305-314; silence strip intended at :1046) ----------------------------
+    def preprocess_audio(self, audio_path: str) -> str:
+        """預處理音頻: ensure 16 kHz mono WAV, then strip silence.  Returns the same path when nothing changed, else
+        a new ``<stem>.trimmed.wav`` (the caller removes the old file when the path differs, :1048-1051)."""
+        logging.info(f"🔄 預處理音頻: {os.path.basename(audio_path)}")
+        if not audio_path.lower().endswith(".wav"):
+            audio_path = self.convert_to_wav(audio_path)
+        if not self.strip_silence:
+            return audio_path
+        pcm, rate = wavio.read_wav(audio_path)
+        if rate != ops.SAMPLE_RATE or pcm.ndim != 1 or pcm.dtype != np.int16:
+            audio_path = self.convert_to_wav(audio_path)
+            pcm, rate = wavio.read_wav(audio_path)
+        dev = self._to_device(pcm)
+        res = ops.detect(dev, rate, self.min_silence_len, self.silence_thresh, self.keep_silence, self.seek_step)
+        self.last_segments = res.kept
+        if res.n_keep == len(pcm):
+            logging.info("✅ 音頻預處理完成")
+            return audio_path
+        out = ops.compact(dev, res, rate)[: res.n_keep]
+        new_path = os.path.splitext(audio_path)[0] + ".trimmed.wav"
+        wavio.write_wav_s16(new_path, out.cpu().numpy(), rate)
+        logging.info("✅ 音頻預處理完成")
+        return new_path
+
+    # -- what model.transcribe computes first (audio_processor.py:1076) ------------------------------------
+    def log_mel(self, audio_path: str, padding: int = whisper_audio.N_SAMPLES):
+        return whisper_audio.log_mel_spectrogram(audio_path, n_mels=self.n_mels, padding=padding, device=self.device)
+
+    # -- all three without touching the filesystem in between ---------------------------------------------------
+    def process_pcm(self, pcm, in_rate: int, padding: int = 0) -> Tuple["object", "object", List[List[int]]]:
+        """(trimmed 16 kHz s16 PCM, log-mel, kept [start_ms, end_ms]) for raw PCM, one fused device pass."""
+        r = ops.pipeline(self._to_device(pcm), in_rate, n_mels=self.n_mels, padding=padding, trim=self.strip_silence,
+                         min_silence_len=self.min_silence_len, silence_thresh=self.silence_thresh,
+                         keep_silence=self.keep_silence, seek_step=self.seek_step)
+        return r.pcm, r.mel, r.kept
+
+    def _to_device(self, pcm):
+        torch = ops.require_cuda()
+        t = torch.from_numpy(np.ascontiguousarray(pcm)) if isinstance(pcm, np.ndarray) else pcm
+        return t.to(self.device if self.device is not None else "cuda", non_blocking=True)
+
+
+def remap_time(t_trimmed_s: float, kept_ms: List[List[int]]) -> float:
+    """Map a timestamp on the silence-stripped timeline back to the original recording:
+    Whisper's segment start/end refer to the trimmed audio, diarization (audio_processor.py:1105-1145) to the
+    original."""
+    t_ms = t_trimmed_s * 1000.0
+    acc = 0.0
+    for s, e in kept_ms:
+        d = e - s
+        if t_ms <= acc + d:
+            return (s + (t_ms - acc)) / 1000.0
+        acc += d
+    return (kept_ms[-1][1] / 1000.0) if kept_ms else t_trimmed_s

@@ -21,7 +21,10 @@ s16<->float scaling and lrintf quantisation):
             w = 2*((i-center) - ph/L)/taps ... normalised so every phase sums to 1.
   run       y[m] = sum_i h[ph][i] * x[idx - center + i],  idx = (m*M)//L, ph = (m*M)%L
   edges     x[-k] = x[k] (reflect) before the start; x[n-1+k] = x[n-k] (symmetric) after
-            the end;  n_out = floor((n_in-1)*L/M) + 1
+            the end;  n_out = ceil(n_in*L/M) = every output whose centre tap floor(m*M/L) lies inside the
+            input.  (The real library emits this many or ONE FEWER: at flush it reflects
+            (min(buffered, taps)+1)/2 samples and `buffered` depends on its streaming state — probed.
+            Parity is therefore checked on the common prefix with |len difference| <= 1.)
   convert   s16 in: x/32768 ; stereo→mono: 0.5*L + 0.5*R (float) when resampling;
             s16 out: clip(rint(32768*y)) round-half-even.
             Same-rate s16 stereo → mono stays integer: (L + R + 1) >> 1.
@@ -57,7 +60,7 @@ def out_len(n_in: int, in_rate: int, out_rate: int) -> int:
     L, M = ratio(in_rate, out_rate)
     if L == 1 and M == 1:
         return n_in
-    return ((n_in - 1) * L) // M + 1
+    return -((-n_in * L) // M)
 
 
 def design(in_rate: int, out_rate: int) -> np.ndarray:

@@ -1,0 +1,167 @@
+"""C-ABI surface (no compute without a GPU) and host-side logic."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _built_lib():
+    from audio_processor_b200 import build
+    return build.build()
+
+
+def test_library_exports_every_declared_symbol():
+    from audio_processor_b200 import _abi
+    path = _built_lib()
+    hdr = open(os.path.join(ROOT, "include", "b2a.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(b2a_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = C.CDLL(path)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/b2a.h but not exported by libb2a.so"
+    assert declared == set(_abi.SIGNATURES.keys()), declared ^ set(_abi.SIGNATURES.keys())
+    _abi.declare(lib)
+    assert lib.b2a_version() >= 100
+    assert isinstance(lib.b2a_last_error(), bytes)
+
+
+def test_host_only_entry_points_match_the_oracle():
+    """design helpers run on the host (no GPU): filter bank, mel filterbank, length rules"""
+    from audio_processor_b200 import _abi
+    from oracle import resample_oracle as ro, whisper_logmel as wl
+    lib = _abi.declare(C.CDLL(_built_lib()))
+    for rate in (44100, 48000, 22050, 32000, 8000):
+        ph = C.c_int(0)
+        taps = lib.b2a_resample_ntaps(rate, 16000, C.byref(ph))
+        assert (ph.value, taps) == (ro.ratio(rate, 16000)[0], ro.n_taps(rate, 16000))
+        buf = np.zeros(ph.value * taps, dtype=np.float32)
+        assert lib.b2a_resample_taps(rate, 16000, buf.ctypes.data_as(C.c_void_p), buf.size) == 0
+        ref = ro.design(rate, 16000).astype(np.float32).reshape(-1)
+        assert np.abs(buf - ref).max() <= 2e-8                    # same design, independent implementations
+        for n in (100, 4000, 4001, 4003, 158760000):
+            assert lib.b2a_resample_out_len(n, rate, 16000) == ro.out_len(n, rate, 16000)
+    assert lib.b2a_resample_out_len(2646000, 44100, 16000) == 960000
+    for nm in (80, 128):
+        f = np.zeros((nm, 201), dtype=np.float32)
+        assert lib.b2a_mel_filters(nm, f.ctypes.data_as(C.c_void_p), f.size) == 0
+        assert np.abs(f - wl.mel_filters(nm)).max() <= 1e-9 and (f != 0).sum() == (wl.mel_filters(nm) != 0).sum()
+    assert lib.b2a_log_mel_frames(960000, 480000) == 9000 and lib.b2a_energy_len(57600001, 16000) == 3600001
+    assert lib.b2a_mel_filters(64, None, 0) < 0 and b"bad argument" in lib.b2a_last_error()
+
+
+def test_generated_tap_table_is_current():
+    """csrc/fir_taps_gen.inc must be what tools/gen_fir_taps.cpp emits (immediates == runtime design)."""
+    exe = os.path.join(ROOT, "audio_processor_b200", "_build", "gen_fir_taps_test")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(["g++", "-O2", "-o", exe, os.path.join(ROOT, "tools", "gen_fir_taps.cpp")], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert out == open(os.path.join(ROOT, "audio_processor_b200", "csrc", "fir_taps_gen.inc")).read()
+
+
+def test_product_path_has_no_cpu_fallback():
+    import torch
+    from audio_processor_b200 import ops
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.log_mel(np.zeros(16000, dtype=np.float32))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.resample(np.zeros((4410, 2), dtype=np.int16), 44100)
+    # and nothing under the package imports the oracle
+    pkg = os.path.join(ROOT, "audio_processor_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_wav_roundtrip_and_errors(tmp_path):
+    from audio_processor_b200 import wavio
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal((1000, 2)) * 3000).astype(np.int16)
+    p = str(tmp_path / "a.wav")
+    wavio.write_wav_s16(p, x, 44100)
+    y, sr = wavio.read_wav(p)
+    assert sr == 44100 and np.array_equal(x, y)
+    wavio.write_wav_s16(p, x[:, 0], 16000)
+    y, sr = wavio.read_wav(p)
+    assert sr == 16000 and y.ndim == 1 and np.array_equal(x[:, 0], y)
+    bad = tmp_path / "b.m4a"
+    bad.write_bytes(b"\x00\x00\x00\x20ftypM4A ")
+    with pytest.raises(wavio.UnsupportedAudio):
+        wavio.read_wav(str(bad))
+
+
+def test_segment_standin_matches_pydub_restatement():
+    from audio_processor_b200.silence import AudioSegment
+    from oracle import pydub_silence as ps
+    x = (np.arange(56009) % 1000).astype(np.int16)
+    a, b = AudioSegment(x), ps.Segment(x)
+    assert len(a) == len(b) == 3501
+    for sl in (slice(0, 100), slice(3400, 3501), slice(1999, 99999), slice(None, None)):
+        assert np.array_equal(a[sl].get_array_of_samples(), b[sl].samples())      # incl. the zero-filled tail
+    assert np.array_equal((a[0:10] + a[20:30]).get_array_of_samples(), (b[0:10] + b[20:30]).samples())
+
+
+def test_remap_time_and_sharding():
+    from audio_processor_b200 import sharding
+    from audio_processor_b200.service import remap_time
+    kept = [[0, 3093], [4907, 8000]]
+    assert remap_time(1.0, kept) == 1.0 and abs(remap_time(3.093 + 0.5, kept) - 5.407) < 1e-9
+    bins = sharding.shard_clips([3600.0] * 1024, 8)
+    assert all(len(b) == 128 for b in bins) and sorted(sum(bins, [])) == list(range(1024))
+    bins = sharding.shard_clips([10, 1, 1, 1, 7, 3], 2)
+    loads = [sum([10, 1, 1, 1, 7, 3][i] for i in b) for b in bins]
+    assert abs(loads[0] - loads[1]) <= 1
+    counts, padded = sharding.pack_tables([[[0, 5], [7, 9]], []], cap=4)
+    assert counts.tolist() == [2, 0] and padded[0, :2].tolist() == [[0, 5], [7, 9]]
+
+
+def test_synth_recipe():
+    from audio_processor_b200 import synth
+    x = synth.synth_clip(2, 16000, 1, 30.0, 0.3)
+    y = synth.synth_clip(2, 16000, 1, 30.0, 0.3)
+    assert x.dtype.is_floating_point is False and x.shape == (480000,) and bool((x == y).all())
+    from oracle import pydub_silence as ps
+    ns = ps.detect_nonsilent_fast(x.numpy(), 16000, 1000, -40, 1)
+    assert len(ns) >= 2                                       # gaps are long and quiet enough to be detected
+    st = synth.synth_clip(4, 48000, 2, 2.0, 0.5)
+    assert st.shape == (96000, 2)
+
+
+_GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch.distributed as dist
+from audio_processor_b200 import sharding
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{sys.argv[2]}", rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+durations = [5.0, 1.0, 4.0, 2.0, 3.0]
+mine = sharding.shard_clips(durations, 2)[rank]
+tables = [[[i * 10, i * 10 + rank + 1]] * (i % 3) for i in mine]        # ragged, incl. empty tables
+out = sharding.gather_segment_tables(mine, tables, cap=4)
+expect = sorted((i, [[i * 10, i * 10 + r + 1]] * (i % 3)) for r in range(2) for i in sharding.shard_clips(durations, 2)[r])
+assert out == expect, (out, expect)
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_gather_segment_tables_world_size_2_gloo(tmp_path):
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs

@@ -1,0 +1,132 @@
+"""Kernel logic on the TEST-ONLY CPU emulation (tests/emu): the very .cu sources, compiled by g++ against a fiber
+model of the CUDA execution model, checked against the oracles.  This is how index math, barrier structure and
+integer exactness are verified on a box without a GPU; the GPU parity tests proper are in test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+from oracle import pydub_silence as ps, resample_oracle as ro, swr_ref, whisper_logmel as wl
+from tests import helpers as H
+
+G = H.golden_json()
+A = H.golden_arrays()
+
+
+def _cmp16(y, ref, min_exact):
+    assert 0 <= len(y) - len(ref) <= 1
+    d = np.abs(y[:len(ref)].astype(int) - ref.astype(int))
+    assert d.max() <= 1 and (d == 0).mean() >= min_exact, (d.max(), (d == 0).mean())
+
+
+@pytest.mark.parametrize("name,rate,min_exact", [("R1", 44100, 0.998), ("R2", 48000, 0.998), ("N441", 44100, 0.998),
+                                                 ("N480", 48000, 0.998), ("N220", 22050, 0.995)])
+def test_emu_resample_golden(emu, name, rate, min_exact):
+    x = H.tone_pair(rate, G["resample"][name]["n_in"]) if name.startswith("R") else A[f"{name}_in"]
+    _cmp16(emu.resample(x, rate), A[f"{name}_out"], min_exact)
+
+
+@pytest.mark.parametrize("rate,ch,n", [(44100, 2, 14112 * 3 + 1234), (44100, 1, 14112 * 2 + 77), (48000, 2, 1632 * 4 + 777),
+                                       (48000, 1, 1632 * 3 + 5), (32000, 2, 9000), (11025, 1, 6000)])
+def test_emu_resample_fast_and_generic_paths(emu, rate, ch, n):
+    rng = np.random.default_rng(rate + ch)
+    x = (rng.standard_normal((n, ch)) * 6000).clip(-32768, 32767).astype(np.int16)
+    x = x[:, 0].copy() if ch == 1 else x
+    y, yf, en = emu.resample(x, rate, want_f32=True, want_energy=True)
+    assert len(y) == ro.out_len(n, rate, 16000)
+    assert np.abs(yf - ro.resample_float(x, rate)).max() <= 1e-5          # normalised-PCM gate (float64 restatement)
+    d = np.abs(y.astype(int) - ro.convert(x, rate).astype(int))
+    assert d.max() <= 1
+    if swr_ref.available():
+        _cmp16(y, swr_ref.convert(x, rate), 0.998 if rate in (44100, 48000) else 0.95)   # named pairs: SURVEY A.4 gate
+    assert np.array_equal(en.astype(np.int64), H.energy_oracle(y))         # exact-integer epilogue
+
+
+def test_emu_resample_float_input_and_same_rate(emu):
+    rng = np.random.default_rng(5)
+    xf = (rng.standard_normal((20000, 2)) * 0.2).astype(np.float32)
+    y = emu.resample(xf, 44100)
+    assert np.abs(y.astype(int) - ro.convert(xf, 44100).astype(int)).max() <= 1
+    x = (rng.standard_normal((4001, 2)) * 9000).clip(-32768, 32767).astype(np.int16)
+    y, en = emu.resample(x, 16000, want_energy=True)
+    assert np.array_equal(y, ro.convert(x, 16000)) and np.array_equal(en.astype(np.int64), H.energy_oracle(y))
+    assert np.array_equal(emu.resample(x[:, 0].copy(), 16000), x[:, 0])
+    f = np.array([0.5, 1.5, 2.5, 32766.5, 32768.0, -49152.0] * 40, dtype=np.float32) / 32768.0
+    assert emu.resample(f, 16000)[:6].tolist() == [0, 2, 2, 32766, 32767, -32768]
+
+
+@pytest.mark.parametrize("name", sorted(G["silence"].keys()))
+def test_emu_silence_golden(emu, name):
+    g = G["silence"][name]
+    x = H.piecewise([tuple(p) for p in g["parts"]], g["extra"])
+    W, th, keep, step = g["params"]
+    r = emu.detect(x, 16000, W, th, keep, step)
+    assert r["silent"] == g["silent"] and r["nonsilent"] == g["nonsilent"] and r["kept"] == g["kept"]
+    assert int(r["info"][4]) == g["len_ms"] and len(r["compact"]) == g["n_keep"]
+
+
+def test_emu_silence_random_properties(emu):
+    rng = np.random.default_rng(11)
+    for trial in range(24):
+        n = int(rng.integers(20000, 150000)) + int(rng.integers(0, 16))      # up to ~9.4 s: several 2048-ms tiles
+        x = H.random_speechlike(rng, n, min_span=800, max_span=20000)
+        W = int(rng.choice([100, 250, 500, 1000]))
+        th = float(rng.choice([-16, -30, -40, -50, -60.5]))
+        keep = [0, 50, 100, 200, 700, True, False][trial % 7]
+        step = int(rng.choice([1, 1, 1, 3, 10, 25, 300, 1200]))
+        r = emu.detect(x, 16000, W, th, keep, step)
+        assert r["silent"] == ps.detect_silence_fast(x, 16000, W, th, step), (trial, W, th, step)
+        assert r["nonsilent"] == ps.detect_nonsilent_fast(x, 16000, W, th, step), (trial, W, th, step)
+        assert r["kept"] == ps.kept_ranges_fast(x, 16000, W, th, keep, step), (trial, W, th, keep, step)
+        st = ps.strip_silence_fast(x, 16000, min_silence_len=W, silence_thresh=th, keep_silence=keep, seek_step=step)
+        assert np.array_equal(r["compact"], st)
+
+
+def test_emu_silence_edge_cases(emu):
+    z = np.zeros(0, dtype=np.int16)
+    r = emu.detect(np.zeros(5, dtype=np.int16))           # len_ms == 0
+    assert r["nonsilent"] == [[0, 0]] and len(r["compact"]) == 0
+    x = np.full(16000 * 3, 9000, dtype=np.int16)          # nothing silent
+    r = emu.detect(x, 16000, 1000, -40, 100, 1)
+    assert r["silent"] == [] and r["nonsilent"] == [[0, 3000]] and np.array_equal(r["compact"], x)
+    r = emu.detect(x[:8000], 16000, 1000, -40, 100, 1)    # shorter than the window
+    assert r["nonsilent"] == [[0, 500]]
+    assert len(z) == 0
+
+
+@pytest.mark.parametrize("nm", [80, 128])
+def test_emu_logmel_golden(emu, nm):
+    t = np.arange(16000) / 16000.0
+    tone = (0.5 * np.sin(2 * np.pi * 1000 * t)).astype(np.float32)
+    assert np.abs(emu.log_mel(tone, nm) - A[f"mel_tone_{nm}"]).max() <= 1e-4
+    assert np.abs(emu.log_mel(A["mel_noise_in"], nm, padding=480) - A[f"mel_noise_{nm}_pad480"]).max() <= 1e-4
+
+
+def test_emu_logmel_cases(emu):
+    rng = np.random.default_rng(2)
+    # tone + -70 dB noise (worst probed dynamic range), zeros, click, batch with whole-call max and per-clip max
+    t = np.arange(16000 * 2) / 16000.0
+    hd = (0.5 * np.sin(2 * np.pi * 440 * t) + 0.5 * 10 ** (-70 / 20) * rng.standard_normal(len(t))).astype(np.float32)
+    assert np.abs(emu.log_mel(hd, 80) - wl.log_mel_spectrogram(hd, 80).numpy()).max() <= 1e-4
+    assert np.all(emu.log_mel(np.zeros(16000, np.float32), 80) == -1.5)
+    click = np.zeros(8000, np.float32); click[4000] = 1.0
+    assert np.abs(emu.log_mel(click, 128, padding=4000) - wl.log_mel_spectrogram(click, 128, padding=4000).numpy()).max() <= 1e-4
+    b = (rng.standard_normal((3, 4000)) * np.array([[0.3], [0.01], [0.0003]])).astype(np.float32)
+    assert np.abs(emu.log_mel(b, 80) - wl.log_mel_spectrogram(b, 80).numpy()).max() <= 1e-4
+    assert np.abs(emu.log_mel(b, 80, norm_mode=1) - wl.log_mel_spectrogram(b, 80, per_clip_max=True).numpy()).max() <= 1e-4
+    s = (rng.standard_normal(5000) * 3000).astype(np.int16)
+    assert np.abs(emu.log_mel(s, 80) - wl.log_mel_spectrogram(s.astype(np.float32) / 32768.0, 80).numpy()).max() <= 1e-4
+
+
+def test_emu_pipeline(emu):
+    from audio_processor_b200 import synth
+    x = synth.synth_clip(3, 44100, 2, 7.0, 0.35).numpy()
+    r = emu.pipeline(x, 44100, n_mels=80, padding=0)
+    full = emu.resample(x, 44100)
+    kw = dict(min_silence_len=1000, silence_thresh=-40, keep_silence=200, seek_step=1)
+    assert r["nonsilent"] == ps.detect_nonsilent_fast(full, 16000, 1000, -40, 1)
+    assert r["kept"] == ps.kept_ranges_fast(full, 16000, **kw)
+    trimmed = ps.strip_silence_fast(full, 16000, **kw)
+    assert np.array_equal(r["pcm"], trimmed) and 0 < len(trimmed) < len(full)
+    assert np.abs(r["mel"] - wl.log_mel_spectrogram(trimmed.astype(np.float32) / 32768.0, 80).numpy()).max() <= 1e-4
+    r2 = emu.pipeline(x, 44100, n_mels=128, padding=1600, trim=False)
+    assert np.array_equal(r2["pcm"], full)
+    assert np.abs(r2["mel"] - wl.log_mel_spectrogram(full.astype(np.float32) / 32768.0, 128, padding=1600).numpy()).max() <= 1e-4

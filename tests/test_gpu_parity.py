@@ -1,0 +1,323 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI, libb2a.so) against the oracle on the same bytes.
+Gates (SURVEY.md A.4 / BASELINE.md §5): silence ranges, keep-mask and compacted PCM bit-exact; 16 kHz PCM <= 1 LSB
+from libswresample with >= 99.8 % identical samples and <= 1e-5 (normalised float) from the float64 restatement;
+log-mel <= 1e-4 abs from the float64 oracle."""
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+G = H.golden_json()
+A = H.golden_arrays()
+MEL_TOL = 1e-4
+PCM_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def T():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+@pytest.fixture(scope="module")
+def ops(T):
+    from audio_processor_b200 import _lib, ops as o
+    _lib.lib()          # fails loudly if libb2a.so is missing — there is no fallback to test instead
+    return o
+
+
+def _cmp16(y, ref, min_exact=0.998):
+    assert 0 <= len(y) - len(ref) <= 1
+    d = np.abs(y[:len(ref)].astype(int) - ref.astype(int))
+    assert d.max() <= 1 and (d == 0).mean() >= min_exact, (d.max(), (d == 0).mean())
+
+
+# ---------------------------------------------------------------- conversion
+@pytest.mark.parametrize("name,rate,min_exact", [("R1", 44100, 0.998), ("R2", 48000, 0.998), ("N441", 44100, 0.998),
+                                                 ("N480", 48000, 0.998), ("N220", 22050, 0.995)])
+def test_resample_golden(ops, name, rate, min_exact):
+    x = H.tone_pair(rate, G["resample"][name]["n_in"]) if name.startswith("R") else A[f"{name}_in"]
+    y, _, _ = ops.resample(x, rate)
+    _cmp16(y.cpu().numpy(), A[f"{name}_out"], min_exact)
+
+
+@pytest.mark.parametrize("rate,ch,secs", [(44100, 2, 12.3), (44100, 1, 7.7), (48000, 2, 9.1), (48000, 1, 3.3), (32000, 2, 2.0),
+                                          (22050, 1, 2.0), (8000, 1, 2.0)])
+def test_resample_vs_oracles(ops, T, rate, ch, secs):
+    from oracle import resample_oracle as ro, swr_ref
+    rng = np.random.default_rng(rate * 3 + ch)
+    n = int(rate * secs) + 13
+    x = (rng.standard_normal((n, ch)) * 5000).clip(-32768, 32767).astype(np.int16)
+    x = x[:, 0].copy() if ch == 1 else x
+    y, yf, en = ops.resample(T.from_numpy(x).cuda(), rate, want_f32=True, want_energy=True)
+    y, yf, en = y.cpu().numpy(), yf.cpu().numpy(), en.cpu().numpy()
+    assert len(y) == ro.out_len(n, rate, 16000)
+    assert np.abs(yf - ro.resample_float(x, rate)).max() <= PCM_TOL
+    assert np.abs(y.astype(int) - ro.convert(x, rate).astype(int)).max() <= 1
+    if swr_ref.available():
+        _cmp16(y, swr_ref.convert(x, rate), 0.998 if rate in (44100, 48000) else 0.95)
+    assert np.array_equal(en, H.energy_oracle(y))
+
+
+def test_resample_float_input_same_rate_and_unaligned(ops, T):
+    from oracle import resample_oracle as ro
+    rng = np.random.default_rng(5)
+    xf = (rng.standard_normal((30000, 2)) * 0.2).astype(np.float32)
+    y, _, _ = ops.resample(xf, 44100)
+    assert np.abs(y.cpu().numpy().astype(int) - ro.convert(xf, 44100).astype(int)).max() <= 1
+    x = (rng.standard_normal((40001, 2)) * 9000).clip(-32768, 32767).astype(np.int16)
+    y, _, en = ops.resample(x, 16000, want_energy=True)
+    assert np.array_equal(y.cpu().numpy(), ro.convert(x, 16000))                       # (L+R+1)>>1, bit exact
+    assert np.array_equal(en.cpu().numpy(), H.energy_oracle(y.cpu().numpy()))
+    y, _, _ = ops.resample(x[:, 0].copy(), 16000)
+    assert np.array_equal(y.cpu().numpy(), x[:, 0])                                     # identity
+    # a 4-byte-aligned (not 16-byte) device pointer must take the table-driven kernel and still be right
+    big = T.from_numpy((rng.standard_normal((14112 * 3 + 1, 2)) * 4000).astype(np.int16)).cuda()
+    view = big[1:]
+    y2, _, _ = ops.resample(view, 44100)
+    assert np.abs(y2.cpu().numpy().astype(int) - ro.convert(view.cpu().numpy(), 44100).astype(int)).max() <= 1
+
+
+def test_resample_linearity_full_minute(ops, T):
+    """size-independent property at a BASELINE size (60 s): FIR is linear, so R(a)+R(b) ~= R(a+b) before rounding"""
+    from audio_processor_b200 import synth
+    a = synth.synth_clip(1, 44100, 2, 60.0, 0.25, device="cuda")
+    b = synth.synth_clip(2, 44100, 2, 60.0, 0.25, device="cuda")
+    half = lambda t: (t.to(T.int32) // 2).to(T.int16)
+    _, fa, _ = ops.resample(half(a), 44100, want_s16=False, want_f32=True)
+    _, fb, _ = ops.resample(half(b), 44100, want_s16=False, want_f32=True)
+    _, fs, _ = ops.resample(half(a) + half(b), 44100, want_s16=False, want_f32=True)
+    assert fs.shape[0] == 960000
+    assert float((fa + fb - fs).abs().max()) <= 2e-6
+
+
+# ---------------------------------------------------------------- silence
+@pytest.mark.parametrize("name", sorted(G["silence"].keys()))
+def test_silence_golden(ops, name):
+    g = G["silence"][name]
+    x = H.piecewise([tuple(p) for p in g["parts"]], g["extra"])
+    W, th, keep, step = g["params"]
+    r = ops.detect(x, 16000, W, th, keep, step)
+    assert r.silent == g["silent"] and r.nonsilent == g["nonsilent"] and r.kept == g["kept"]
+    assert r.len_ms == g["len_ms"] and r.n_keep == g["n_keep"]
+
+
+def test_silence_random_bit_exact(ops, T):
+    from oracle import pydub_silence as ps
+    rng = np.random.default_rng(13)
+    for trial in range(40):
+        n = int(rng.integers(20000, 900000)) + int(rng.integers(0, 16))
+        x = H.random_speechlike(rng, n, min_span=800, max_span=60000)
+        W = int(rng.choice([100, 250, 500, 1000, 2500]))
+        th = float(rng.choice([-16, -30, -40, -50, -60.5]))
+        keep = [0, 50, 100, 200, 700, True, False][trial % 7]
+        step = int(rng.choice([1, 1, 1, 3, 10, 25, 300, 1200]))
+        d = T.from_numpy(x).cuda()
+        r = ops.detect(d, 16000, W, th, keep, step)
+        assert r.silent == ps.detect_silence_fast(x, 16000, W, th, step), (trial, W, th, step)
+        assert r.nonsilent == ps.detect_nonsilent_fast(x, 16000, W, th, step), (trial, W, th, step)
+        assert r.kept == ps.kept_ranges_fast(x, 16000, W, th, keep, step), (trial, W, th, keep, step)
+        out = ops.compact(d, r)[: r.n_keep].cpu().numpy()
+        st = ps.strip_silence_fast(x, 16000, min_silence_len=W, silence_thresh=th, keep_silence=keep, seek_step=step)
+        assert np.array_equal(out, st)
+
+
+def test_silence_literal_pydub_loop_small(ops):
+    """the oracle of record (one audioop.rms per window) on a short clip"""
+    from oracle import pydub_silence as ps
+    rng = np.random.default_rng(3)
+    x = H.random_speechlike(rng, 16000 * 6 + 9, min_span=3000, max_span=30000)
+    s = ps.Segment(x)
+    r = ops.detect(x, 16000, 500, -35, 150, 1)
+    assert r.silent == ps.detect_silence(s, 500, -35, 1)
+    assert r.nonsilent == ps.detect_nonsilent(s, 500, -35, 1)
+    assert r.kept == ps.kept_ranges(s, 500, -35, 150, 1)
+
+
+def test_silence_edges_and_api(ops, T):
+    from audio_processor_b200 import silence as S
+    r = ops.detect(np.zeros(5, dtype=np.int16))
+    assert r.nonsilent == [[0, 0]] and r.n_keep == 0
+    x = np.full(16000 * 3, 9000, dtype=np.int16)
+    r = ops.detect(x, 16000, 1000, -40, 100, 1)
+    assert r.silent == [] and r.nonsilent == [[0, 3000]] and r.n_keep == len(x)
+    k1 = H.piecewise([(3, 1000), (2, 0), (3, 1000)])
+    seg = S.AudioSegment(k1)
+    assert S.detect_silence(seg, 1000, -40) == [[2893, 5107]]
+    assert S.detect_nonsilent(seg, 1000, -40) == [[0, 2893], [5107, 8000]]
+    chunks = S.split_on_silence(seg, 1000, -40, keep_silence=200)
+    assert [len(c) for c in chunks] == [3093, 3093]
+    st = S.strip_silence(seg, 1000, -40, keep_silence=200)
+    assert np.array_equal(st.get_array_of_samples(), np.concatenate([c.get_array_of_samples() for c in chunks]))
+    with pytest.raises(RuntimeError):
+        ops.detect(x, 44100)                       # 44.1 samples per ms: unsupported, loudly
+
+
+def test_silence_idempotent_full_hour(ops, T):
+    """size-independent properties at the cfg2 size (1 h @ 16 kHz): sorted, disjoint, inside the clip, and
+    trimming the trimmed audio with keep_silence >= min_silence_len/2 removes (almost) nothing more."""
+    from audio_processor_b200 import synth
+    x = synth.synth_clip(2, 16000, 1, 3600.0, 0.2, device="cuda")
+    r = ops.detect(x, 16000, 1000, -40, 200, 1)
+    kept = np.asarray(r.kept)
+    assert len(kept) > 100 and (kept[:, 0] < kept[:, 1]).all() and (kept[1:, 0] >= kept[:-1, 1]).all()
+    assert kept[0, 0] >= 0 and kept[-1, 1] <= r.len_ms == 3600000
+    assert r.n_keep == int(((kept[:, 1] - kept[:, 0]) * 16).sum())
+    out = ops.compact(x, r)[: r.n_keep]
+    # checksum of checksums: compacted audio is exactly the concatenation of the kept slices
+    xs = x.to(T.int64)
+    csum = T.cumsum(xs * xs, 0)
+    tot = sum(int(csum[e * 16 - 1] - (csum[s * 16 - 1] if s else 0)) for s, e in kept.tolist())
+    assert tot == int((out.to(T.int64) ** 2).sum())
+
+
+# ---------------------------------------------------------------- log-mel
+@pytest.mark.parametrize("nm", [80, 128])
+def test_logmel_golden(ops, nm):
+    t = np.arange(16000) / 16000.0
+    tone = (0.5 * np.sin(2 * np.pi * 1000 * t)).astype(np.float32)
+    m = ops.log_mel(tone, nm).cpu().numpy()
+    assert np.abs(m - A[f"mel_tone_{nm}"]).max() <= MEL_TOL
+    g = G["logmel"][f"M{nm}"]
+    assert abs(m.max() - g["max"]) <= MEL_TOL and int(m.argmax() // m.shape[1]) == g["argmax_mel"]
+    mn = ops.log_mel(A["mel_noise_in"], nm, padding=480).cpu().numpy()
+    assert np.abs(mn - A[f"mel_noise_{nm}_pad480"]).max() <= MEL_TOL
+
+
+def test_logmel_cases(ops, T):
+    from oracle import whisper_logmel as wl
+    rng = np.random.default_rng(2)
+    t = np.arange(16000 * 2) / 16000.0
+    hd = (0.5 * np.sin(2 * np.pi * 440 * t) + 0.5 * 10 ** (-70 / 20) * rng.standard_normal(len(t))).astype(np.float32)
+    assert np.abs(ops.log_mel(hd, 80).cpu().numpy() - wl.log_mel_spectrogram(hd, 80).numpy()).max() <= MEL_TOL
+    assert bool((ops.log_mel(np.zeros(16000, np.float32), 80) == -1.5).all())
+    click = np.zeros(8000, np.float32); click[4000] = 1.0
+    assert np.abs(ops.log_mel(click, 128, padding=4000).cpu().numpy() - wl.log_mel_spectrogram(click, 128, padding=4000).numpy()).max() <= MEL_TOL
+    b = (rng.standard_normal((5, 48000)) * np.array([[0.3], [0.01], [0.0003], [0.1], [0.9]])).astype(np.float32)
+    assert np.abs(ops.log_mel(b, 80).cpu().numpy() - wl.log_mel_spectrogram(b, 80).numpy()).max() <= MEL_TOL
+    assert np.abs(ops.log_mel(b, 128, per_clip_max=True).cpu().numpy() - wl.log_mel_spectrogram(b, 128, per_clip_max=True).numpy()).max() <= MEL_TOL
+    s = (rng.standard_normal(60 * 16000) * 3000).astype(np.int16)                        # cfg1 shape: 60 s -> [80, 6000]
+    m = ops.log_mel(s, 80).cpu().numpy()
+    assert m.shape == (80, 6000)
+    assert np.abs(m - wl.log_mel_spectrogram(s.astype(np.float32) / 32768.0, 80).numpy()).max() <= MEL_TOL
+    m = ops.log_mel(s, 80, padding=480000).cpu().numpy()                                    # transcribe's call
+    assert m.shape == (80, 9000)
+    assert np.abs(m - wl.log_mel_spectrogram(s.astype(np.float32) / 32768.0, 80, padding=480000).numpy()).max() <= MEL_TOL
+
+
+def test_logmel_whisper_api(ops, T, tmp_path):
+    from audio_processor_b200 import wavio, whisper_audio as wa
+    from oracle import whisper_logmel as wl
+    rng = np.random.default_rng(9)
+    x = (rng.standard_normal(16000 * 3) * 2500).astype(np.int16)
+    p = str(tmp_path / "c.wav")
+    wavio.write_wav_s16(p, x, 16000)
+    a = wa.load_audio(p)
+    assert a.dtype == np.float32 and np.array_equal(a, x.astype(np.float32) / 32768.0)
+    m = wa.log_mel_spectrogram(p, n_mels=80, padding=wa.N_SAMPLES)
+    assert tuple(m.shape) == (80, (len(x) + wa.N_SAMPLES) // 160)
+    assert np.abs(m.cpu().numpy() - wl.log_mel_spectrogram(a, 80, padding=wa.N_SAMPLES).numpy()).max() <= MEL_TOL
+    assert wa.pad_or_trim(T.zeros(10), 4).shape == (4,) and wa.pad_or_trim(np.zeros((2, 3)), 5).shape == (2, 5)
+    assert np.abs(wa.mel_filters(None, 80).numpy() - wl.mel_filters(80)).max() <= 1e-9
+
+
+def test_logmel_batch_4096_property(ops, T):
+    """cfg3 shape [4096, 480000] f32 -> [4096, 128, 3000]; spot-check rows against the oracle and the floor invariant"""
+    from audio_processor_b200 import synth
+    from oracle import whisper_logmel as wl
+    x = synth.noise_batch(3, 4096, 480000, device="cuda")
+    m = ops.log_mel(x, 128)
+    assert tuple(m.shape) == (4096, 128, 3000)
+    gmax = float(m.max())
+    assert abs(float(m.min()) - max(float(m.min()), gmax - 2.0)) < 1e-6         # nothing below the floor (max-8)/4
+    rows = [0, 1777, 4095]
+    sub = x[rows].cpu().numpy()
+    ref = wl.log_mel_spectrogram(sub, 128).numpy()
+    # the floor of the full batch can only be >= the floor of 3 rows; noise never reaches it, so rows agree exactly in form
+    assert np.abs(m[rows].cpu().numpy() - ref).max() <= MEL_TOL
+
+
+# ---------------------------------------------------------------- whole path
+@pytest.mark.parametrize("rate,ch,secs,nm,pad", [(44100, 2, 20.0, 80, 0), (48000, 2, 15.0, 80, 0), (16000, 1, 60.0, 80, 0),
+                                                 (44100, 1, 9.0, 128, 480000)])
+def test_pipeline_vs_oracle(ops, T, rate, ch, secs, nm, pad):
+    from audio_processor_b200 import synth
+    from oracle import pydub_silence as ps, whisper_logmel as wl
+    x = synth.synth_clip(rate + ch, rate, ch, secs, 0.35, device="cuda")
+    r = ops.pipeline(x, rate, n_mels=nm, padding=pad, min_silence_len=1000, silence_thresh=-40, keep_silence=200)
+    full, _, _ = ops.resample(x, rate)
+    full = full.cpu().numpy()
+    kw = dict(min_silence_len=1000, silence_thresh=-40, keep_silence=200, seek_step=1)
+    assert r.nonsilent == ps.detect_nonsilent_fast(full, 16000, 1000, -40, 1)
+    assert r.kept == ps.kept_ranges_fast(full, 16000, **kw)
+    trimmed = ps.strip_silence_fast(full, 16000, **kw)
+    assert np.array_equal(r.pcm.cpu().numpy(), trimmed) and 0 < len(trimmed) < len(full)
+    ref = wl.log_mel_spectrogram(trimmed.astype(np.float32) / 32768.0, nm, padding=pad).numpy()
+    assert tuple(r.mel.shape) == ref.shape and np.abs(r.mel.cpu().numpy() - ref).max() <= MEL_TOL
+
+
+def test_pipeline_notrim_and_service(ops, T, tmp_path):
+    from audio_processor_b200 import synth, wavio
+    from audio_processor_b200.service import AudioFrontend
+    from oracle import pydub_silence as ps, resample_oracle as ro, whisper_logmel as wl
+    x = synth.synth_clip(5, 44100, 2, 12.0, 0.3, device="cuda")
+    r = ops.pipeline(x, 44100, n_mels=80, trim=False)
+    full, _, _ = ops.resample(x, 44100)
+    assert np.array_equal(r.pcm.cpu().numpy(), full.cpu().numpy())
+    ref = wl.log_mel_spectrogram(full.cpu().numpy().astype(np.float32) / 32768.0, 80).numpy()
+    assert np.abs(r.mel.cpu().numpy() - ref).max() <= MEL_TOL
+    # the reference's helpers, on files
+    src = str(tmp_path / "meeting.wav.orig")
+    wavio.write_wav_s16(src, x.cpu().numpy(), 44100)
+    fe = AudioFrontend()
+    wav = fe.convert_to_wav(src)
+    assert wav == str(tmp_path / "meeting.wav.wav") or wav.endswith(".wav")
+    y, sr = wavio.read_wav(wav)
+    assert sr == 16000 and y.ndim == 1 and np.abs(y.astype(int) - ro.convert(x.cpu().numpy(), 44100).astype(int)).max() <= 1
+    out = fe.preprocess_audio(wav)
+    assert out != wav and out.endswith(".wav")
+    z, _ = wavio.read_wav(out)
+    assert np.array_equal(z, ps.strip_silence_fast(y, 16000, min_silence_len=1000, silence_thresh=-40, keep_silence=200, seek_step=1))
+    assert fe.last_segments == ps.kept_ranges_fast(y, 16000, 1000, -40, 200, 1)
+    import subprocess
+    bad = tmp_path / "x.m4a"; bad.write_bytes(b"not audio")
+    with pytest.raises(subprocess.CalledProcessError):
+        fe.convert_to_wav(str(bad))
+
+
+def test_pipeline_full_hour_properties(ops, T):
+    """cfg2 at full size: 1 h 44.1 kHz stereo.  Oracle-free invariants + a sampled window against the oracle."""
+    from audio_processor_b200 import synth
+    from oracle import pydub_silence as ps, resample_oracle as ro, whisper_logmel as wl
+    x = synth.synth_clip(2, 44100, 2, 3600.0, 0.2, device="cuda")
+    plan = ops.PipelinePlan(x.shape[0], 44100, 2, x.dtype, n_mels=80)
+    r = plan.run(x, min_silence_len=1000, silence_thresh=-40, keep_silence=200)
+    kept = np.asarray(r.kept)
+    assert (kept[:, 0] < kept[:, 1]).all() and (kept[1:, 0] >= kept[:-1, 1]).all() and kept[-1, 1] <= 3600000
+    assert r.n_keep == int(((kept[:, 1] - kept[:, 0]) * 16).sum()) and r.n_frames == r.n_keep // 160
+    mel = r.mel
+    assert bool(T.isfinite(mel).all()) and float(mel.min()) >= float(mel.max()) - 2.0 - 1e-6
+    # sampled window: first 30 s of input (head incl. reflect) against libswresample-equivalent oracle
+    head = x[: 44100 * 30].cpu().numpy()
+    full, _, _ = ops.resample(x, 44100)
+    o = ro.convert(head, 44100)
+    d = np.abs(full[: len(o) - 200].cpu().numpy().astype(int) - o[:-200].astype(int))
+    assert d.max() <= 1 and (d == 0).mean() >= 0.998
+    # ranges recomputed by the oracle from the GPU's own 16 kHz PCM: bit exact over the whole hour
+    f16 = full.cpu().numpy()
+    assert r.kept == ps.kept_ranges_fast(f16, 16000, 1000, -40, 200, 1)
+    trimmed = ps.strip_silence_fast(f16, 16000, min_silence_len=1000, silence_thresh=-40, keep_silence=200, seek_step=1)
+    assert np.array_equal(r.pcm.cpu().numpy(), trimmed)
+    # mel of a middle slice vs the oracle on the same trimmed samples.  seg = trimmed[160a:160b] => oracle frame j is
+    # centred on trimmed sample 160(a+j), i.e. it IS frame a+j of the full clip except near the slice edges (reflect).
+    a, b = 100000, 103000
+    seg = trimmed[a * 160: b * 160].astype(np.float32) / 32768.0
+    refm = wl.log_mel_spectrogram(seg, 80).numpy()[:, 2:-2]
+    sub = mel[:, a + 2: b - 2].cpu().numpy()
+    assert sub.shape == refm.shape
+    # the two floors differ (slice max vs whole-clip max): compare where neither side is clamped
+    mask = (refm > refm.max() - 1.9) & (sub > float(mel.max()) - 1.9)
+    assert mask.mean() > 0.5 and np.abs(sub - refm)[mask].max() <= MEL_TOL
