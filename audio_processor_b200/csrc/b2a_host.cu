@@ -11,6 +11,8 @@
 #include <vector>
 
 #include "b2a_tables.cuh"
+#include "f16_bits.h"
+#include "fir_mma.cuh"
 #include "fir_design.h"
 
 namespace b2a {
@@ -148,6 +150,60 @@ const ResampleDesign* get_resample_design(int in_rate, int out_rate) {
     r->d_taps = d;
     g_resample[key] = r;
     return r;
+}
+
+// ---- filter bank of the tensor-core FIR (fir_mma.cuh) as mma.m16n8k16 B fragments ------------------------------
+// layout [block b][k-step s][8-output half nt][term: 0 = T_hi, 1 = T_lo][lane] -> uint2 {b0, b1};
+// lane (g = lane >> 2, t = lane & 3): b0 = B[k = 2t, 2t+1][n = g], b1 = B[k = 2t+8, 2t+9][n = g] with
+// B[k][n] = 2^12 * tap[phase(J)][kb + 16 s + k - (J M)/L],  J = 16 b + 8 nt + n  (zero outside the filter).
+template <int IN_RATE>
+static void build_fir_mma_table(const float* taps /*[L][TAPS]*/, std::vector<uint2>& out) {
+    using G = FirMmaGeom<IN_RATE>;
+    out.assign((size_t)kFmBlocks * G::KS * 2 * 2 * 32, make_uint2(0u, 0u));
+    for (int b = 0; b < kFmBlocks; b++)
+        for (int s = 0; s < G::KS; s++)
+            for (int nt = 0; nt < 2; nt++)
+                for (int lane = 0; lane < 32; lane++) {
+                    const int g = lane >> 2, t = lane & 3;
+                    const int J = 16 * b + 8 * nt + g;
+                    const int BJ = (J * G::M) / G::L, ph = (J * G::M) % G::L;
+                    uint16_t hi[4], lo[4];
+                    for (int e = 0; e < 4; e++) {
+                        const int k = 2 * t + (e & 1) + 8 * (e >> 1);
+                        const int i = G::kb(b) + 16 * s + k - BJ;
+                        float T = 0.0f;
+                        if (i >= 0 && i < G::TAPS) T = taps[(size_t)ph * G::TAPS + i] * (float)(1 << kFmTapShift);
+                        hi[e] = b2a_f16::f32_to_f16(T);
+                        lo[e] = b2a_f16::f32_to_f16(T - b2a_f16::f16_to_f32(hi[e]));
+                    }
+                    const size_t base = ((((size_t)b * G::KS + s) * 2 + nt) * 2) * 32 + lane;
+                    out[base] = make_uint2((unsigned)hi[0] | ((unsigned)hi[1] << 16), (unsigned)hi[2] | ((unsigned)hi[3] << 16));
+                    out[base + 32] = make_uint2((unsigned)lo[0] | ((unsigned)lo[1] << 16), (unsigned)lo[2] | ((unsigned)lo[3] << 16));
+                }
+}
+
+static std::map<std::pair<int, int>, const uint2*> g_fir_mma;   // (device, in_rate)
+
+const uint2* get_fir_mma_table(int in_rate) {
+    const ResampleDesign* des = get_resample_design(in_rate, kSampleRate);
+    if (!des) return nullptr;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { cuda_fail(e, "cudaGetDevice"); return nullptr; }
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto key = std::make_pair(dev, in_rate);
+    auto it = g_fir_mma.find(key);
+    if (it != g_fir_mma.end()) return it->second;
+    std::vector<uint2> h;
+    if (in_rate == 44100) build_fir_mma_table<44100>(des->h_taps, h);
+    else if (in_rate == 48000) build_fir_mma_table<48000>(des->h_taps, h);
+    else { set_error("no tensor-core FIR table for %d Hz", in_rate); return nullptr; }
+    uint2* d = nullptr;
+    e = cudaMalloc((void**)&d, h.size() * sizeof(uint2));
+    if (e == cudaSuccess) e = cudaMemcpy(d, h.data(), h.size() * sizeof(uint2), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cuda_fail(e, "FIR table upload"); return nullptr; }
+    g_fir_mma[key] = d;
+    return d;
 }
 
 }  // namespace b2a

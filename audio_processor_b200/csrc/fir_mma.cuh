@@ -1,0 +1,331 @@
+// fir_mma.cuh — fused s16-stereo decode + downmix + polyphase FIR as a banded-Toeplitz product on the tensor
+// cores (sm_100a), for the two named rate pairs (44.1 kHz and 48 kHz -> 16 kHz).
+//
+// Replaces libswresample's swr_convert inner loop behind the reference's
+//   ffmpeg -ar 16000 -ac 1 -c:a pcm_s16le   (app/services/audio_processor.py:912-923).
+//
+// Why tensor cores: the polyphase FIR needs 92 (100) multiply-adds per output with 160 distinct phases.  With
+// CUDA-core FFMAs every (phase, tap) pair is its own instruction; the fully unrolled immediate-operand form is a
+// ~280 KB instruction stream that ncu shows stalled on instruction fetch (profiles/r01_fir_history.md:
+// smsp no_instruction stall 12.4 per issue, 18 % issue utilisation), and register-operand FFMAs issue at half
+// rate.  As a matrix product the filter bank is a constant operand that lives in registers and the code is a
+// 200-instruction loop.
+//
+// Formulation.  A run = 160 consecutive outputs (one phase period at 44.1 kHz, L = 160) = 10 blocks of 16.
+// For block b the 16 outputs read a window of <= 16*KS input frames starting at frame kb = (16 b M) / L of the
+// run, so for 16 runs at once
+//     D[16 runs x 16 outputs] = X[16 runs x 16 KS frames] * T_b[16 KS frames x 16 outputs]
+// with T_b the (constant, zero padded) taps of the block.  mma.sync.m16n8k16 (f16 in, f32 accumulate) computes it:
+// A = X from shared memory, B = T_b from registers (loaded once per persistent warp; warp b owns block b).
+//
+// Exactness.  The window value is v = L + R (17-bit integer; the output is sum(t * v) / 2).  v = 128 * hv + lo
+// with hv in [-512, 511] and lo in [0, 127]: both exact in f16.  Taps are scaled by 2^12 and split T = T_hi + T_lo
+// (f16 each, |T - T_hi - T_lo| <= 2^-22 |T|).  All four cross terms are accumulated in f32:
+//     out = 2^-6 * (T_hi + T_lo) . hv  +  2^-13 * (T_hi + T_lo) . lo
+// f16 x f16 products are exact in f32, so the only differences from the f32 FMA chain of the CPU engine are the
+// 2^-22 tap representation and the summation order — the same size as f32 rounding itself (tests: <= 1 LSB from
+// libswresample, >= 99.8 % of samples identical, <= 1e-5 from the float64 restatement).
+//
+// Per tile of RT = 32 runs a persistent CTA of 10 warps:
+//   1. waits for the tile's raw frames (one contiguous span, fetched by 1-D bulk TMA into a double buffer while
+//      the previous tile is processed; completion on an mbarrier),
+//   2. converts them to (hv | lo) f16 pairs, one 32-bit word per frame, in run-major rows of pitch P (P mod 32
+//      = 8 or 24 makes the 8-byte A-fragment loads conflict free),
+//   3. runs the MMAs (warp b = block b, two 16-run tiles), rounds half-to-even + clips to s16 (swr audioconvert)
+//      into a staging tile,
+//   4. copies the staging tile out with coalesced 16-byte stores and accumulates the per-millisecond sum of
+//      squares of the QUANTISED samples (uint64) that the silence detector consumes.
+#pragma once
+#include "b2a_common.cuh"
+
+namespace b2a {
+
+template <int IN_RATE> struct FirMmaTraits;
+template <> struct FirMmaTraits<44100> { static constexpr int L = 160, M = 441, TAPS = 92, KS = 9, P = 536; };
+template <> struct FirMmaTraits<48000> { static constexpr int L = 1, M = 3, TAPS = 100, KS = 10, P = 584; };
+
+constexpr int kFmNout = 160;            // outputs per run (10 ms)
+constexpr int kFmBlocks = 10;           // 16-output blocks per run
+constexpr int kFmRT = 32;               // runs per CTA tile
+constexpr int kFmWarps = 10;            // warp b owns block b
+constexpr int kFmThreads = kFmWarps * 32;
+constexpr int kFmOutPitch = 168;        // staging-tile row pitch in samples (84 words: conflict-free fragment stores)
+constexpr int kFmTapShift = 12;         // taps are scaled by 2^12 before the f16 split
+
+template <int IN_RATE>
+struct FirMmaGeom {
+    using TR = FirMmaTraits<IN_RATE>;
+    static constexpr int L = TR::L, M = TR::M, TAPS = TR::TAPS, KS = TR::KS, P = TR::P;
+    static constexpr int CENTER = (TAPS - 1) / 2;
+    static constexpr int S = kFmNout * M / L;                       // input frames per run (441 / 480)
+    static constexpr int CENTER_BYTES16 = (CENTER * 4 + 15) / 16 * 16;
+    static constexpr int AL = (CENTER_BYTES16 - CENTER * 4) / 4;    // frames the raw tile starts early (16-byte alignment)
+    static constexpr int RAWF = (kFmRT - 1) * S + P;                // frames a tile's rows touch
+    static constexpr int RAW_BYTES = ((AL + RAWF) * 4 + 15) / 16 * 16;
+    static constexpr int PLANE_BYTES = kFmRT * P * 4 + 256;         // + zeroed pad (last row's K padding reads past P)
+    static constexpr int OUT_BYTES = kFmRT * kFmOutPitch * 2;
+    static constexpr int SMEM_BYTES = 2 * RAW_BYTES + PLANE_BYTES + OUT_BYTES + 64;
+    static constexpr int CHUNKS = (P + 31) / 32;                    // 32-frame conversion units per row
+    static constexpr int kb(int b) { return (16 * b * M) / L; }     // window start of block b (frames from the row origin)
+    static_assert((kFmRT * S * 4) % 16 == 0, "tile pitch must keep 16-byte alignment");
+    static_assert(P % 2 == 0 && (P % 32 == 8 || P % 32 == 24), "row pitch must make 8-byte fragment loads conflict free");
+    static_assert(P >= S + TAPS, "row must hold a run plus the filter span");
+    static_assert(16 * KS >= ((15 * M) / L + 1) + TAPS, "K must cover the widest window of a block");
+};
+
+struct FirMmaArgs {
+    const unsigned char* in;     // raw interleaved s16 stereo frames
+    int16_t* out_s16;            // nullable
+    u64* energy;                 // nullable
+    const uint2* btab;           // [block][KS][nt][term][lane] B fragments (taps), see build_fir_mma_table
+    i64 tile_lo, tile_hi;        // tiles [tile_lo, tile_hi) are produced (tile t = runs [t*RT, (t+1)*RT))
+};
+
+// ---- primitives (GPU: PTX; TEST-ONLY emulation: tests/emu) -------------------------------------------------
+#ifndef B2A_EMU
+typedef unsigned saddr_t;
+__device__ __forceinline__ saddr_t smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(saddr_t bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(saddr_t bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(saddr_t bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+// 1-D bulk copy global -> shared (TMA engine), completion counted on the mbarrier
+__device__ __forceinline__ void bulk_load(saddr_t dst, const void* src, unsigned bytes, saddr_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned sel) {
+    unsigned r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+// packed f16 subtraction on raw bits
+__device__ __forceinline__ unsigned hsub2_bits(unsigned a, unsigned b) {
+    unsigned r;
+    asm("sub.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ void mma_16816(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+#else
+typedef uintptr_t saddr_t;
+static inline saddr_t smem_addr(const void* p) { return (uintptr_t)p; }
+// mbarrier stand-in: word 0 = completed phases, word 1 = bytes still expected in the current phase
+static inline void mbar_init(saddr_t bar, unsigned) { ((unsigned*)bar)[0] = 0; ((unsigned*)bar)[1] = 0; }
+static inline void mbar_fence_init() {}
+static inline void mbar_expect_tx(saddr_t bar, unsigned bytes) { ((unsigned*)bar)[1] = bytes; }
+static inline void mbar_wait(saddr_t bar, unsigned parity) { while ((((volatile unsigned*)bar)[0] & 1u) == parity) emu::yield(); }
+static inline void bulk_load(saddr_t dst, const void* src, unsigned bytes, saddr_t bar) {
+    memcpy((void*)dst, src, bytes);
+    unsigned* b = (unsigned*)bar;
+    b[1] -= bytes;
+    if (b[1] == 0) b[0]++;
+}
+static inline unsigned prmt(unsigned a, unsigned b, unsigned sel) {
+    unsigned long long v = ((unsigned long long)b << 32) | a;
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) r |= (unsigned)((v >> (8 * ((sel >> (4 * i)) & 7))) & 0xff) << (8 * i);
+    return r;
+}
+static inline unsigned hsub2_bits(unsigned a, unsigned b) {
+    unsigned lo = emu::f32_to_f16(emu::f16_to_f32((unsigned short)(a & 0xffff)) - emu::f16_to_f32((unsigned short)(b & 0xffff)));
+    unsigned hi = emu::f32_to_f16(emu::f16_to_f32((unsigned short)(a >> 16)) - emu::f16_to_f32((unsigned short)(b >> 16)));
+    return lo | (hi << 16);
+}
+static inline void mma_16816(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) { emu::mma_m16n8k16_f16(d, a, b0, b1); }
+#endif
+
+// one (block, 16-run tile): D12 = (T_hi + T_lo) . hv,  D34 = (T_hi + T_lo) . lo
+template <int IN_RATE>
+__device__ __forceinline__ void fir_mma_block(const unsigned* __restrict__ rows, int kb, int g, int t,
+                                              const uint2 (&breg)[FirMmaTraits<IN_RATE>::KS][2][2],
+                                              float (&d12)[2][4], float (&d34)[2][4]) {
+    using G = FirMmaGeom<IN_RATE>;
+    const unsigned* ra = rows + (size_t)g * G::P + kb + 2 * t;
+    const unsigned* rb = ra + 8 * G::P;
+#pragma unroll
+    for (int s = 0; s < G::KS; s++) {
+        const uint2 w0 = *(const uint2*)(ra + 16 * s);
+        const uint2 w1 = *(const uint2*)(rb + 16 * s);
+        const uint2 w2 = *(const uint2*)(ra + 16 * s + 8);
+        const uint2 w3 = *(const uint2*)(rb + 16 * s + 8);
+        // word = hv (low half) | lo (high half); a fragment register holds two consecutive k
+        const unsigned ahv[4] = {prmt(w0.x, w0.y, 0x5410), prmt(w1.x, w1.y, 0x5410), prmt(w2.x, w2.y, 0x5410), prmt(w3.x, w3.y, 0x5410)};
+        const unsigned alo[4] = {prmt(w0.x, w0.y, 0x7632), prmt(w1.x, w1.y, 0x7632), prmt(w2.x, w2.y, 0x7632), prmt(w3.x, w3.y, 0x7632)};
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++) {
+            mma_16816(d12[nt], ahv, breg[s][nt][0].x, breg[s][nt][0].y);
+            mma_16816(d34[nt], alo, breg[s][nt][0].x, breg[s][nt][0].y);
+            mma_16816(d12[nt], ahv, breg[s][nt][1].x, breg[s][nt][1].y);
+            mma_16816(d34[nt], alo, breg[s][nt][1].x, breg[s][nt][1].y);
+        }
+    }
+}
+
+template <int IN_RATE>
+__global__ void __launch_bounds__(kFmThreads, 1) fir_mma_kernel(const FirMmaArgs a) {
+    using G = FirMmaGeom<IN_RATE>;
+    B2A_DYN_SMEM(smem);
+    unsigned char* raw0 = smem;
+    unsigned* planes = (unsigned*)(smem + 2 * G::RAW_BYTES);
+    int16_t* otile = (int16_t*)(smem + 2 * G::RAW_BYTES + G::PLANE_BYTES);
+    const saddr_t bars = smem_addr(smem + 2 * G::RAW_BYTES + G::PLANE_BYTES + G::OUT_BYTES);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+
+    // constant operand: this warp's block of the filter bank, as B fragments (hi, lo) per k-step and 8-output half
+    uint2 breg[G::KS][2][2];
+    {
+        const uint2* bt = a.btab + (size_t)warp * (G::KS * 2 * 2 * 32) + lane;
+#pragma unroll
+        for (int s = 0; s < G::KS; s++)
+#pragma unroll
+            for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+                for (int term = 0; term < 2; term++) breg[s][nt][term] = bt[((s * 2 + nt) * 2 + term) * 32];
+    }
+    if (tid == 0) {
+        mbar_init(bars, 1);
+        mbar_init(bars + 8, 1);
+        mbar_fence_init();
+    }
+    for (int i = tid; i < 64; i += kFmThreads) planes[kFmRT * G::P + i] = 0u;   // zero pad after the last row
+    __syncthreads();
+
+    auto issue = [&](i64 tile, int buf) {
+        // raw span of the tile: frames [tile*RT*S - CENTER - AL, +RAW_BYTES/4), 16-byte aligned at both ends
+        const unsigned char* src = a.in + ((i64)tile * kFmRT * G::S - G::CENTER - G::AL) * 4;
+        const saddr_t bar = bars + 8u * buf;
+        mbar_expect_tx(bar, (unsigned)G::RAW_BYTES);
+        constexpr int PIECE = 16384;
+#pragma unroll 1
+        for (int off = 0; off < G::RAW_BYTES; off += PIECE) {
+            const int nb = (G::RAW_BYTES - off) < PIECE ? (G::RAW_BYTES - off) : PIECE;
+            bulk_load(smem_addr(raw0 + (size_t)buf * G::RAW_BYTES + off), src + off, (unsigned)nb, bar);
+        }
+    };
+
+    i64 tile = a.tile_lo + blockIdx.x;
+    if (tid == 0 && tile < a.tile_hi) issue(tile, 0);
+    const int kb = G::kb(0) + (16 * warp * G::M) / G::L;   // == G::kb(warp)
+    int it = 0;
+    for (; tile < a.tile_hi; tile += gridDim.x, it++) {
+        const int buf = it & 1;
+        if (tid == 0 && tile + gridDim.x < a.tile_hi) issue(tile + gridDim.x, buf ^ 1);   // other buffer: its readers passed the last barrier
+        mbar_wait(bars + 8u * buf, (unsigned)((it >> 1) & 1));
+
+        // ---- 2. raw s16 stereo -> (hv | lo) f16 words, run-major rows ----
+        {
+            const unsigned* raw = (const unsigned*)(raw0 + (size_t)buf * G::RAW_BYTES) + G::AL;
+#pragma unroll 2
+            for (int u = warp; u < kFmRT * G::CHUNKS; u += kFmWarps) {
+                const int n = u / G::CHUNKS, c = u - n * G::CHUNKS;
+                const int k = 32 * c + lane;
+                if (k < G::P) {
+                    const int v = __dp2a_lo((int)raw[n * G::S + k], 0x0101, 0);        // L + R, exact
+                    const unsigned hv = (unsigned)(0x6600 + (v >> 7)) & 0xffffu;        // f16 bits of 1536 + (v >> 7)
+                    const unsigned lo = (unsigned)(0x6400 + (v & 127));                 // f16 bits of 1024 + (v & 127)
+                    planes[n * G::P + k] = hsub2_bits(hv | (lo << 16), 0x64006600u);    // minus (1536, 1024): exact integers
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- 3. tensor-core product, quantise, stage ----
+#pragma unroll 1
+        for (int mt = 0; mt < kFmRT / 16; mt++) {
+            float d12[2][4], d34[2][4];
+#pragma unroll
+            for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+                for (int e = 0; e < 4; e++) { d12[nt][e] = 0.f; d34[nt][e] = 0.f; }
+            fir_mma_block<IN_RATE>(planes + (size_t)(16 * mt) * G::P, kb, g, t, breg, d12, d34);
+#pragma unroll
+            for (int nt = 0; nt < 2; nt++) {
+                // d[0],d[1]: run g, outputs 2t, 2t+1 of this 8-output half; d[2],d[3]: run g + 8
+                const float sc12 = 1.0f / 64.0f, sc34 = 1.0f / 8192.0f;
+                const int q0 = quant_s16(fmaf(d12[nt][0], sc12, d34[nt][0] * sc34));
+                const int q1 = quant_s16(fmaf(d12[nt][1], sc12, d34[nt][1] * sc34));
+                const int q2 = quant_s16(fmaf(d12[nt][2], sc12, d34[nt][2] * sc34));
+                const int q3 = quant_s16(fmaf(d12[nt][3], sc12, d34[nt][3] * sc34));
+                const int col = 16 * warp + 8 * nt + 2 * t;
+                *(unsigned*)(otile + (16 * mt + g) * kFmOutPitch + col) = (unsigned)(q0 & 0xffff) | ((unsigned)q1 << 16);
+                *(unsigned*)(otile + (16 * mt + g + 8) * kFmOutPitch + col) = (unsigned)(q2 & 0xffff) | ((unsigned)q3 << 16);
+            }
+        }
+        __syncthreads();
+
+        // ---- 4. coalesced copy-out + per-millisecond energy of the quantised samples ----
+        {
+            const i64 m_tile = (i64)tile * kFmRT * kFmNout;
+#pragma unroll
+            for (int id = tid; id < kFmRT * (kFmNout / 8); id += kFmThreads) {   // 640 = 2 per thread: full warps
+                const int n = id / (kFmNout / 8), c = id - n * (kFmNout / 8);
+                const uint4 v = *(const uint4*)(otile + n * kFmOutPitch + 8 * c);
+                const i64 m = m_tile + (i64)n * kFmNout + 8 * c;
+                if (a.out_s16) *(uint4*)(a.out_s16 + m) = v;
+                const unsigned w[4] = {v.x, v.y, v.z, v.w};
+                u64 e = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int s0 = (int)(short)(w[j] & 0xffff), s1 = (int)(short)(w[j] >> 16);
+                    e += (u64)(unsigned)(s0 * s0) + (u64)(unsigned)(s1 * s1);
+                }
+                e += __shfl_xor_sync(0xffffffffu, e, 1);                         // the other half of the millisecond
+                if (a.energy && (c & 1) == 0) a.energy[m >> 4] = e;
+            }
+        }
+        // the next iteration's conversion only writes `planes` (all MMA reads are behind the barrier above) and its
+        // staging writes come after its own first barrier, i.e. after every thread finished this copy-out
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+struct FirMmaPlan {
+    i64 out_lo, out_hi;    // outputs [out_lo, out_hi) come from the tensor-core kernel
+};
+
+const uint2* get_fir_mma_table(int in_rate);   // device table for the current device (b2a_host.cu); nullptr + error on failure
+
+template <int IN_RATE>
+static inline int fir_mma_launch(const void* d_in, i64 n_in, int16_t* d_out_s16, u64* d_energy, FirMmaPlan* plan, cudaStream_t stream) {
+    using G = FirMmaGeom<IN_RATE>;
+    plan->out_lo = plan->out_hi = 0;
+    // tile t reads frames [t*RT*S - CENTER - AL, that + RAW_BYTES/4): t >= 1 keeps the start inside the clip
+    const i64 span_end = (i64)G::RAW_BYTES / 4 - G::CENTER - G::AL;          // relative to the tile's first run start
+    const i64 tile_hi = (n_in - span_end) >= 0 ? (n_in - span_end) / ((i64)kFmRT * G::S) + 1 : 0;   // exclusive
+    if (tile_hi <= 1) return 0;
+    const uint2* tab = get_fir_mma_table(IN_RATE);
+    if (!tab) return B2A_ECUDA;
+    auto k = fir_mma_kernel<IN_RATE>;
+    static bool attr_done = false;    // idempotent; a benign race only repeats the call
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fir_mma_kernel)");
+        attr_done = true;
+    }
+    FirMmaArgs a;
+    a.in = (const unsigned char*)d_in; a.out_s16 = d_out_s16; a.energy = d_energy; a.btab = tab;
+    a.tile_lo = 1; a.tile_hi = tile_hi;
+    const i64 tiles = tile_hi - 1;
+    const unsigned grid = (unsigned)(tiles < 148 ? tiles : 148);             // persistent: one CTA per SM
+    B2A_LAUNCH(k, grid, kFmThreads, G::SMEM_BYTES, stream, a);
+    B2A_CHECK_LAUNCH("fir_mma_kernel");
+    plan->out_lo = (i64)kFmRT * kFmNout;
+    plan->out_hi = tile_hi * kFmRT * kFmNout;
+    return 1;
+}
+
+}  // namespace b2a

@@ -18,7 +18,10 @@
 // consumes — so trimming never re-reads the PCM to find energies.
 #pragma once
 #include "b2a_common.cuh"
+#ifndef B2A_FIR_TAPS_INCLUDED
+#define B2A_FIR_TAPS_INCLUDED
 #include "fir_taps_gen.inc"
+#endif
 
 namespace b2a {
 

@@ -35,6 +35,7 @@ class AudioFrontend:
         self.strip_silence = strip_silence
         self.device = device
         self.last_segments: Optional[List[List[int]]] = None   # kept [start_ms, end_ms] of the last preprocess_audio
+        self._plans = {}                                        # PipelinePlan per clip shape (buffers reused across calls)
 
     # -- convert_to_wav (audio_processor.py:901-930) ----------------------------------------------------
     def convert_to_wav(self, input_path: str) -> str:
@@ -86,9 +87,17 @@ class AudioFrontend:
     # -- all three without touching the filesystem in between ---------------------------------------------------
     def process_pcm(self, pcm, in_rate: int, padding: int = 0) -> Tuple["object", "object", List[List[int]]]:
         """(trimmed 16 kHz s16 PCM, log-mel, kept [start_ms, end_ms]) for raw PCM, one fused device pass."""
-        r = ops.pipeline(self._to_device(pcm), in_rate, n_mels=self.n_mels, padding=padding, trim=self.strip_silence,
-                         min_silence_len=self.min_silence_len, silence_thresh=self.silence_thresh,
-                         keep_silence=self.keep_silence, seek_step=self.seek_step)
+        x = self._to_device(pcm).contiguous()
+        ch = 1 if x.dim() == 1 else int(x.shape[1])
+        key = (int(x.shape[0]), int(in_rate), ch, x.dtype, self.n_mels, int(padding), str(x.device))
+        plan = self._plans.get(key)
+        if plan is None:
+            if len(self._plans) >= 4:
+                self._plans.clear()
+            plan = self._plans[key] = ops.PipelinePlan(key[0], in_rate, ch, x.dtype, n_mels=self.n_mels, padding=padding,
+                                                       device=x.device)
+        r = plan.run(x, trim=self.strip_silence, min_silence_len=self.min_silence_len, silence_thresh=self.silence_thresh,
+                     keep_silence=self.keep_silence, seek_step=self.seek_step)
         return r.pcm, r.mel, r.kept
 
     def _to_device(self, pcm):

@@ -40,6 +40,7 @@ void run_block(void (*entry)(void*), void* arg, int nthreads) {
     b->walive.assign(nw, 0);
     for (int t = 0; t < nthreads; t++) b->walive[t / 32]++;
     b->xchg.assign((size_t)nw * 32, 0);
+    b->wscr.assign((size_t)nw * 32 * 8, 0);
     if ((int)b->fib.size() < nthreads) b->fib.resize(nthreads);
     for (int t = 0; t < nthreads; t++) {
         Fiber& f = b->fib[t];

@@ -25,6 +25,8 @@
 #include <cstring>
 #include <vector>
 
+#include "../../audio_processor_b200/csrc/f16_bits.h"
+
 #define __global__
 #define __device__
 #define __host__
@@ -102,6 +104,7 @@ struct Block {
     std::vector<unsigned> wbar_gen;
     std::vector<int> walive;
     std::vector<uint64_t> xchg;  // [nwarps*32]
+    std::vector<uint32_t> wscr;  // [nwarps*32*8] per-lane scratch for warp-collective emulations (mma)
     void (*entry)(void*) = nullptr;
     void* entry_arg = nullptr;
 };
@@ -150,11 +153,47 @@ template <class T> inline T exchange(T v, int src_lane) {
 
 void run_block(void (*entry)(void*), void* arg, int nthreads);
 
+static inline float f16_to_f32(unsigned short h) { return b2a_f16::f16_to_f32(h); }
+static inline unsigned short f32_to_f16(float f) { return b2a_f16::f32_to_f16(f); }
+
+// mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32, warp collective: every lane publishes its fragments, then
+// computes its four D elements in f32 (k ascending).  Fragment layouts per the PTX ISA.
+inline void mma_m16n8k16_f16(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    Block* b = g_blk;
+    const int w = b->cur / 32, lane = b->cur % 32;
+    uint32_t* scr = b->wscr.data() + (size_t)w * 32 * 8;
+    for (int i = 0; i < 4; i++) scr[lane * 8 + i] = a[i];
+    scr[lane * 8 + 4] = b0;
+    scr[lane * 8 + 5] = b1;
+    syncwarp();
+    const int g = lane >> 2, t = lane & 3;
+    auto A = [&](int row, int k) -> float {
+        const int l = (row & 7) * 4 + ((k & 7) >> 1);
+        const int reg = (row >> 3) + 2 * (k >> 3);
+        const uint32_t v = scr[l * 8 + reg];
+        return f16_to_f32((unsigned short)((k & 1) ? (v >> 16) : (v & 0xffff)));
+    };
+    auto B = [&](int k, int col) -> float {
+        const int l = col * 4 + ((k & 7) >> 1);
+        const uint32_t v = scr[l * 8 + 4 + (k >> 3)];
+        return f16_to_f32((unsigned short)((k & 1) ? (v >> 16) : (v & 0xffff)));
+    };
+    float r[4];
+    for (int e = 0; e < 4; e++) {
+        const int row = g + 8 * (e >> 1), col = 2 * t + (e & 1);
+        float acc = d[e];
+        for (int k = 0; k < 16; k++) acc += A(row, k) * B(k, col);
+        r[e] = acc;
+    }
+    syncwarp();
+    for (int e = 0; e < 4; e++) d[e] = r[e];
+}
+
 template <class... KArgs, class... Args>
 inline void launch(dim3 grid, dim3 block, size_t smem, void (*k)(KArgs...), Args... args) {
     g_gridDim = grid; g_blockDim = block;
-    std::vector<unsigned char> dyn(smem + 64);
-    g_dyn_smem = (unsigned char*)(((uintptr_t)dyn.data() + 63) & ~(uintptr_t)63);
+    std::vector<unsigned char> dyn(smem + 1024);
+    g_dyn_smem = (unsigned char*)(((uintptr_t)dyn.data() + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B boxes need 1 KiB alignment
     auto thunk = [&]() { k(static_cast<KArgs>(args)...); };
     using Th = decltype(thunk);
     for (unsigned bz = 0; bz < grid.z; bz++)
