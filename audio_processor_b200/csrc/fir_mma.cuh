@@ -67,6 +67,17 @@ struct FirMmaGeom {
     static constexpr int SMEM_BYTES = 2 * RAW_BYTES + PLANE_BYTES + OUT_BYTES + 64;
     static constexpr int CHUNKS = (P + 31) / 32;                    // 32-frame conversion units per row
     static constexpr int kb(int b) { return (16 * b * M) / L; }     // window start of block b (frames from the row origin)
+    // k-step s contributes to the 8-output half nt of SOME block iff [16 s, 16 s + 16) meets a window of that half
+    static constexpr bool needed(int s, int nt) {
+        int lo = 1 << 30, hi = 0;
+        for (int b = 0; b < kFmBlocks; b++)
+            for (int j = 8 * nt; j < 8 * nt + 8; j++) {
+                const int rel = ((16 * b + j) * M) / L - kb(b);
+                lo = rel < lo ? rel : lo;
+                hi = rel + TAPS > hi ? rel + TAPS : hi;
+            }
+        return 16 * s < hi && 16 * s + 16 > lo;
+    }
     static_assert((kFmRT * S * 4) % 16 == 0, "tile pitch must keep 16-byte alignment");
     static_assert(P % 2 == 0 && (P % 32 == 8 || P % 32 == 24), "row pitch must make 8-byte fragment loads conflict free");
     static_assert(P >= S + TAPS, "row must hold a run plus the filter span");
@@ -167,6 +178,7 @@ __device__ __forceinline__ void fir_mma_block(const unsigned* __restrict__ rows,
         const unsigned alo[4] = {prmt(w0.x, w0.y, 0x7632), prmt(w1.x, w1.y, 0x7632), prmt(w2.x, w2.y, 0x7632), prmt(w3.x, w3.y, 0x7632)};
 #pragma unroll
         for (int nt = 0; nt < 2; nt++) {
+            if (!G::needed(s, nt)) continue;          // all-zero taps for every block: compile-time skip
             mma_16816(d12[nt], ahv, breg[s][nt][0].x, breg[s][nt][0].y);
             mma_16816(d34[nt], alo, breg[s][nt][0].x, breg[s][nt][0].y);
             mma_16816(d12[nt], ahv, breg[s][nt][1].x, breg[s][nt][1].y);
@@ -194,7 +206,8 @@ __global__ void __launch_bounds__(kFmThreads, 1) fir_mma_kernel(const FirMmaArgs
 #pragma unroll
             for (int nt = 0; nt < 2; nt++)
 #pragma unroll
-                for (int term = 0; term < 2; term++) breg[s][nt][term] = bt[((s * 2 + nt) * 2 + term) * 32];
+                for (int term = 0; term < 2; term++)
+                    breg[s][nt][term] = G::needed(s, nt) ? bt[((s * 2 + nt) * 2 + term) * 32] : make_uint2(0u, 0u);
     }
     if (tid == 0) {
         mbar_init(bars, 1);
@@ -227,17 +240,27 @@ __global__ void __launch_bounds__(kFmThreads, 1) fir_mma_kernel(const FirMmaArgs
         mbar_wait(bars + 8u * buf, (unsigned)((it >> 1) & 1));
 
         // ---- 2. raw s16 stereo -> (hv | lo) f16 words, run-major rows ----
+        // item i = n * P + k (plane word) <-> raw frame n * S + k; a thread walks i = tid, tid + 320, ... and keeps
+        // (k, raw index) incrementally; four independent items per trip so the LDS -> ALU chains overlap
         {
             const unsigned* raw = (const unsigned*)(raw0 + (size_t)buf * G::RAW_BYTES) + G::AL;
-#pragma unroll 2
-            for (int u = warp; u < kFmRT * G::CHUNKS; u += kFmWarps) {
-                const int n = u / G::CHUNKS, c = u - n * G::CHUNKS;
-                const int k = 32 * c + lane;
-                if (k < G::P) {
-                    const int v = __dp2a_lo((int)raw[n * G::S + k], 0x0101, 0);        // L + R, exact
-                    const unsigned hv = (unsigned)(0x6600 + (v >> 7)) & 0xffffu;        // f16 bits of 1536 + (v >> 7)
-                    const unsigned lo = (unsigned)(0x6400 + (v & 127));                 // f16 bits of 1024 + (v & 127)
-                    planes[n * G::P + k] = hsub2_bits(hv | (lo << 16), 0x64006600u);    // minus (1536, 1024): exact integers
+            constexpr int ITEMS = kFmRT * G::P;
+            int k = tid, ri = tid;
+#pragma unroll 1
+            for (int i = tid; i < ITEMS; i += 4 * kFmThreads) {
+                unsigned rv[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    rv[e] = (i + e * kFmThreads < ITEMS) ? raw[ri] : 0u;
+                    k += kFmThreads; ri += kFmThreads;
+                    if (k >= G::P) { k -= G::P; ri += G::S - G::P; }
+                }
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    // u = L + R + 65536 in [0, 131070]: u >> 7 = hv + 512, u & 127 = lo
+                    const unsigned u = (unsigned)__dp2a_lo((int)rv[e], 0x0101, 65536);
+                    const unsigned w = ((u & 127u) << 16) + ((u >> 7) + 0x64006400u);   // f16 bits (1024 + hv + 512 | 1024 + lo)
+                    if (i + e * kFmThreads < ITEMS) planes[i + e * kFmThreads] = hsub2_bits(w, 0x64006600u);   // minus (1536, 1024): exact
                 }
             }
         }
