@@ -59,10 +59,24 @@ def gen_taps(force: bool = False) -> None:
     subprocess.run([exe, out], check=True)
 
 
+def gen_mel(force: bool = False) -> None:
+    """csrc/mel_tables_gen.inc from tools/gen_mel_tables.cpp (+ csrc/mel_design.h, the design the runtime also uses)."""
+    out = os.path.join(CSRC, "mel_tables_gen.inc")
+    src = os.path.join(ROOT, "tools", "gen_mel_tables.cpp")
+    dep = max(os.path.getmtime(src), os.path.getmtime(os.path.join(CSRC, "mel_design.h")))
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= dep:
+        return
+    os.makedirs(OBJ, exist_ok=True)
+    exe = os.path.join(OBJ, "gen_mel_tables")
+    subprocess.run(["g++", "-O2", "-o", exe, src], check=True)
+    subprocess.run([exe, out], check=True)
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
     gen_taps(force)
+    gen_mel(force)
     dep_m = _deps_mtime()
     jobs = []
     for s in SOURCES:

@@ -14,6 +14,7 @@
 #include "f16_bits.h"
 #include "fir_mma.cuh"
 #include "fir_design.h"
+#include "mel_design.h"
 
 namespace b2a {
 
@@ -41,36 +42,8 @@ void design_resampler_host(int in_rate, int out_rate, int* L_out, int* M_out, in
     b2a_design::design_resampler(in_rate, out_rate, L_out, M_out, taps_out, h_taps_out);
 }
 
-// ---- slaney mel filterbank (librosa.filters.mel(sr=16000, n_fft=400, n_mels), whisper mel_filters.npz)
-static double hz_to_mel(double f) {
-    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
-    const double logstep = std::log(6.4) / 27.0;
-    return f >= min_log_hz ? min_log_mel + std::log(f / min_log_hz) / logstep : f / f_sp;
-}
-static double mel_to_hz(double m) {
-    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
-    const double logstep = std::log(6.4) / 27.0;
-    return m >= min_log_mel ? min_log_hz * std::exp(logstep * (m - min_log_mel)) : f_sp * m;
-}
-
-void design_mel_host(int n_mels, float* filters) {
-    const int nb = kNBins;
-    const double sr = (double)kSampleRate;
-    std::vector<double> fftf(nb), melf(n_mels + 2);
-    for (int k = 0; k < nb; k++) fftf[k] = (sr / 2.0) * (double)k / (double)(nb - 1);
-    double m0 = hz_to_mel(0.0), m1 = hz_to_mel(sr / 2.0);
-    for (int i = 0; i < n_mels + 2; i++) melf[i] = mel_to_hz(m0 + (m1 - m0) * (double)i / (double)(n_mels + 1));
-    for (int i = 0; i < n_mels; i++) {
-        double fd0 = melf[i + 1] - melf[i], fd1 = melf[i + 2] - melf[i + 1];
-        double enorm = 2.0 / (melf[i + 2] - melf[i]);
-        for (int k = 0; k < nb; k++) {
-            double lower = (fftf[k] - melf[i]) / fd0;
-            double upper = (melf[i + 2] - fftf[k]) / fd1;
-            double w = std::fmax(0.0, std::fmin(lower, upper));
-            filters[(size_t)i * nb + k] = (float)(w * enorm);
-        }
-    }
-}
+// ---- slaney mel filterbank (whisper mel_filters.npz): design in mel_design.h, shared with tools/gen_mel_tables.cpp
+void design_mel_host(int n_mels, float* filters) { b2a_design::design_mel(n_mels, kNBins, (double)kSampleRate, filters); }
 
 // ---- device table cache ------------------------------------------------------------------------
 static std::mutex g_mu;

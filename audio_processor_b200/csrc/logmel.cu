@@ -6,28 +6,41 @@
 //   drop last frame | slaney mel [n_mels x 201] | log10(max(.,1e-10)) | max(., gmax-8) | (x+4)/4
 //
 // Kernel design (K4 "stft_mel", K5 "mel_floor"):
-//  * persistent blocks of 128 threads; each iteration handles a tile of 24 frames of one clip.
-//  * the tile's 4080 samples are staged once in shared memory as f32 (reflect / zero-pad resolved
-//    at load), skewed by 10 words per hop so the 6 frames a warp works on hit disjoint banks.
-//  * one real 400-point FFT per frame = one complex 200-point FFT of (even,odd) samples, done by
-//    5 threads: radix-10 butterflies (2x5 prime-factor) -> twiddle -> shared-memory transpose ->
-//    radix-20 butterflies (4x5 prime-factor).  Each thread owns output residues {u, 10-u} mod 10,
-//    so the real-FFT unpack pairs (k, 200-k) stay inside one thread: no second exchange.
-//  * power spectrum goes back to shared memory; the sparse mel projection (<=14 bins per filter),
-//    log10, running max/min and the [n_mels][T] store are done per (mel, 8-frame group) so each
-//    filter row is loaded once per 8 frames and stores are 32-byte runs.
+//  * persistent CTAs of 160 threads = 5 warps; each iteration handles a tile of 32 frames of one clip.
+//    lane = frame, warp = role: every per-role quantity (twiddles, window slice, mel group) is warp-uniform,
+//    so table reads are shared-memory broadcasts and per-lane addresses are "base + compile-time offset".
+//  * the tile's 5360 samples are staged once in shared memory as f32 (reflect / zero-pad resolved at load,
+//    16-byte vector loads on the interior path), skewed by 2 words per hop so that the 32 lanes of a warp,
+//    whose frames start 160 samples apart, hit distinct banks.
+//  * one real 400-point FFT per frame = one complex 200-point FFT of (even, odd) samples, split over the 5 roles:
+//    role u does the radix-10 butterflies (2x5 prime-factor) of columns n2 = u + 5j, applies the stage twiddles,
+//    transposes through shared memory (pitch 201 complex per frame: conflict free), then the radix-20 butterflies
+//    (4x5 prime-factor) of output residues {u, 10-u} mod 10 — so the real-FFT unpack pairs (k, 200-k) stay inside
+//    one thread.  The unpack produces 4|X|^2 (16 flops per conjugate pair); the 1/4 lives in the mel weights.
+//  * mel projection: warp g owns a contiguous group of mels (balanced by non-zero weights), lane = frame.  The
+//    sparse filterbank is compile-time data (mel_tables_gen.inc): fully unrolled, each weight an FFMA immediate,
+//    each power bin loaded once from shared memory (pitch 203: conflict free).  log10, running max/min and the
+//    [n_mels][T] store follow; a warp stores 32 consecutive frames of one mel = one 128-byte line.
 //  * K5 applies Whisper's global floor in place and skips tiles whose minimum is already above it.
 #include "b2a_tables.cuh"
 
 namespace b2a {
 
-constexpr int LM_FRAMES = 24;                       // frames per tile
-constexpr int LM_THREADS = 128;                     // 4 warps x (6 frames x 5 threads)
-constexpr int LM_TILE = LM_FRAMES * kHop + 240;     // 4080 samples
-constexpr int LM_SKEW = 10;                         // extra words per hop (bank de-phasing)
+constexpr int LM_FRAMES = 32;                       // frames per tile (lane = frame)
+constexpr int LM_ROLES = 5;                         // warps per CTA (warp = FFT role / mel group)
+constexpr int LM_THREADS = LM_ROLES * 32;
+constexpr int LM_TILE = LM_FRAMES * kHop + 240;     // 5360 samples
+constexpr int LM_SKEW = 2;                          // extra words per hop (bank de-phasing, keeps 8-byte alignment)
+constexpr int LM_HOPW = kHop + LM_SKEW;             // words between consecutive frames in the skewed tile
 constexpr int LM_TILE_WORDS = LM_TILE + LM_SKEW * (LM_TILE / kHop + 1);
-constexpr int LM_EF = 426;                          // exchange words per frame (>= 400, = 10 mod 32)
-constexpr int LM_MW = kMelMaxWidth + 1;             // padded mel weight row
+constexpr int LM_EXP = 201;                         // exchange pitch per frame, in complex values (odd: conflict free)
+constexpr int LM_PP = 203;                          // power-spectrum pitch per frame, in floats (odd)
+
+#ifndef B2A_MEL_TABLES_INCLUDED
+#define B2A_MEL_TABLES_INCLUDED
+#include "mel_tables_gen.inc"
+#endif
+template <int NM> __device__ __forceinline__ float mel_w(int idx) { return NM == 80 ? kMelW80[idx] : kMelW128[idx]; }
 
 struct cpx { float r, i; };
 __device__ __forceinline__ cpx cadd(cpx a, cpx b) { return {a.r + b.r, a.i + b.i}; }
@@ -97,16 +110,18 @@ __device__ __forceinline__ void dft20(const cpx (&x)[20], cpx (&y)[20]) {
     }
 }
 
-// real-FFT unpack of one conjugate pair + power:  Z = FFT200(x_even + i x_odd), m = 200-k.
-__device__ __forceinline__ void unpack_pair(cpx zk, cpx zm, float2 tw, float& pk, float& pm) {
-    float er = 0.5f * (zk.r + zm.r), ei = 0.5f * (zk.i - zm.i);
-    float orr = 0.5f * (zk.r - zm.r), oi = 0.5f * (zk.i + zm.i);
-    float tr = tw.x * oi - tw.y * orr;
-    float ti = tw.x * orr + tw.y * oi;
-    float ar = er + tr, ai = ei - ti;
-    float br = er - tr, bi = ei + ti;
-    pk = ar * ar + ai * ai;
-    pm = br * br + bi * bi;
+// real-FFT unpack of one conjugate pair + power, scaled by 4:  Z = FFT200(x_even + i x_odd), m = 200-k.
+//   2X[k] = E + t, 2X[200-k] = conj(E - t)  with  E = Zk + conj(Zm),  t = W400^k * (-i)(Zk - conj(Zm)).
+// The sums are formed BEFORE squaring (|E|^2 + |t|^2 +- 2Re(..) would cancel catastrophically in quiet bins).
+__device__ __forceinline__ void unpack_pair4(cpx zk, cpx zm, float2 tw, float& pk, float& pm) {
+    const float er = zk.r + zm.r, ei = zk.i - zm.i;
+    const float orr = zk.r - zm.r, oi = zk.i + zm.i;
+    const float tr = tw.x * oi - tw.y * orr;
+    const float ti = tw.x * orr + tw.y * oi;
+    const float ar = er + tr, ai = ei - ti;
+    const float br = er - tr, bi = ei + ti;
+    pk = fmaf(ar, ar, ai * ai);
+    pm = fmaf(br, br, bi * bi);
 }
 
 struct LogMelParams {
@@ -132,184 +147,217 @@ __device__ __forceinline__ float load_sample(const void* audio, int fmt, i64 idx
     return ((const float*)audio)[idx];
 }
 
-__global__ void __launch_bounds__(LM_THREADS, 3) stft_mel_kernel(LogMelParams p) {
+// ---- mel projection of one frame for the mels [M, M1) of a warp's group: compile-time sparse filterbank ----
+template <int NM, int M, int M1>
+struct MelLoop {
+    __device__ static __forceinline__ void run(const float* __restrict__ Pf, float* __restrict__ ocol, i64 T, bool valid,
+                                               float& run_max, float& tmin) {
+        constexpr int st = MelC<NM>::start[M], ln = MelC<NM>::len[M];
+        float acc = 0.0f;
+#pragma unroll
+        for (int j = 0; j < ln; j++) acc = fmaf(mel_w<NM>(M * kMelMaxWidth + j), Pf[st + j], acc);
+        const float lg = __log2f(fmaxf(acc, 1e-10f)) * 0.30102999566398120f;
+        const float sv = (lg + 4.0f) * 0.25f;
+        if (valid) {
+            run_max = fmaxf(run_max, lg);
+            tmin = fminf(tmin, sv);
+            ocol[(size_t)M * (size_t)T] = sv;
+        }
+        MelLoop<NM, M + 1, M1>::run(Pf, ocol, T, valid, run_max, tmin);
+    }
+};
+template <int NM, int M1>
+struct MelLoop<NM, M1, M1> {
+    __device__ static __forceinline__ void run(const float*, float*, i64, bool, float&, float&) {}
+};
+template <int NM, int G>
+__device__ __forceinline__ void mel_group(const float* __restrict__ Pf, float* __restrict__ ocol, i64 T, bool valid,
+                                          float& run_max, float& tmin) {
+    MelLoop<NM, MelC<NM>::group[G], MelC<NM>::group[G + 1]>::run(Pf, ocol, T, valid, run_max, tmin);
+}
+
+template <int NM>
+__global__ void __launch_bounds__(LM_THREADS, 2) stft_mel_kernel(LogMelParams p) {
     B2A_DYN_SMEM(smem_raw);
-    float* s_tile = (float*)smem_raw;                       // LM_TILE_WORDS
-    float* s_ex = s_tile + LM_TILE_WORDS;                   // LM_FRAMES * LM_EF
-    float* s_win = s_ex + LM_FRAMES * LM_EF;                // 400
-    float2* s_tw200 = (float2*)(s_win + kNFFT);             // 200
-    float2* s_tw400 = s_tw200 + 200;                        // 201 (+1 pad)
-    float* s_melw = (float*)(s_tw400 + 202);                // n_mels * LM_MW
-    int* s_mstart = (int*)(s_melw + kMelMaxMels * LM_MW);   // 128
-    int* s_mlen = s_mstart + kMelMaxMels;                   // 128
-    float* s_red = (float*)(s_mlen + kMelMaxMels);          // 8
+    float* s_tile = (float*)smem_raw;                                   // LM_TILE_WORDS
+    float2* s_ex = (float2*)(s_tile + LM_TILE_WORDS);                   // LM_FRAMES * LM_EXP complex
+    float* s_P = (float*)(s_ex + LM_FRAMES * LM_EXP);                   // LM_FRAMES * LM_PP
+    float* s_win = s_P + LM_FRAMES * LM_PP;                             // 400
+    float2* s_tw200 = (float2*)(s_win + kNFFT);                         // 200
+    float2* s_tw400 = s_tw200 + 200;                                    // 201 (+1 pad)
+    float* s_red = (float*)(s_tw400 + 202);                             // 8
 
     const int tid = threadIdx.x;
-    const int n_mels = p.n_mels;
     const LogMelTables* tab = p.tab;
-
-    // ---- stage the tables once per block ----
     for (int i = tid; i < kNFFT; i += LM_THREADS) s_win[i] = tab->win[i];
     for (int i = tid; i < 200; i += LM_THREADS) s_tw200[i] = tab->tw200[i];
     for (int i = tid; i < kNBins; i += LM_THREADS) s_tw400[i] = tab->tw400[i];
-    for (int i = tid; i < n_mels * kMelMaxWidth; i += LM_THREADS) {
-        int m = i / kMelMaxWidth, j = i % kMelMaxWidth;
-        s_melw[m * LM_MW + j] = tab->mel_w[i];
-    }
-    for (int i = tid; i < n_mels; i += LM_THREADS) { s_mstart[i] = tab->mel_start[i]; s_mlen[i] = tab->mel_len[i]; }
 
     i64 n_act = p.n;
     if (p.d_n) { n_act = *p.d_n; if (n_act > p.n) n_act = p.n; if (n_act < 0) n_act = 0; }
     const i64 ltot = n_act + p.padding;          // padded length
     const i64 T = ltot / kHop;                   // frames
     const i64 tiles = (T + LM_FRAMES - 1) / LM_FRAMES;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0 && p.d_frames_out) *p.d_frames_out = T;
+    if (blockIdx.x == 0 && tid == 0 && p.d_frames_out) *p.d_frames_out = T;
 
-    const int warp = tid >> 5, lane = tid & 31;
-    const int fl_w = lane / 5, u = lane % 5;     // frame within warp, role within frame
-    const bool fft_lane = lane < 30;
-    const int fl = warp * 6 + fl_w;              // frame within tile
+    const int u = tid >> 5, f = tid & 31;        // role (warp-uniform), frame within the tile
     const int k1a = u, k1b = (u == 0) ? 5 : 10 - u;
+    const float* ps = s_tile + LM_HOPW * f + 2 * u;          // + 40 n1 + 10 j + 2 (n1 / 4)
+    const float* pw = s_win + 2 * u;                         // + 40 n1 + 10 j
+    const float2* pt = s_tw200 + 10 * u;                     // + 50 j + k1
+    float2* pex_w = s_ex + LM_EXP * f + u;                   // + 20 k1 + 5 j
+    const float2* pex_a = s_ex + LM_EXP * f + 20 * k1a;      // + n2
+    const float2* pex_b = s_ex + LM_EXP * f + 20 * k1b;
+    float* pP = s_P + LM_PP * f;
+    const int elem = p.fmt == B2A_FMT_S16 ? 2 : 4;
 
     float run_max = -3.0e38f;
+    i64 prev_slot = -1;                          // tile_min slot of the previous work item (written one barrier later)
 
     for (i64 work = blockIdx.x; work < tiles * p.batch; work += gridDim.x) {
         const int b = (int)(work / tiles);
-        const i64 tile = work % tiles;
+        const i64 tile = work - (i64)b * tiles;
         const i64 t0 = tile * LM_FRAMES;
-        const char* row = (const char*)p.audio + (size_t)b * (size_t)p.row_stride * (p.fmt == B2A_FMT_S16 ? 2 : 4);
+        const char* row = (const char*)p.audio + (size_t)b * (size_t)p.row_stride * elem;
 
-        __syncthreads();   // previous iteration's readers are done with s_tile / s_ex (and tables are staged)
+        __syncthreads();   // tables staged; previous tile fully consumed (s_tile by stage 1, s_red by the line below)
+        if (tid == 0 && prev_slot >= 0) {
+            p.tile_min[prev_slot] = fminf(fminf(fminf(s_red[0], s_red[1]), fminf(s_red[2], s_red[3])), s_red[4]);
+        }
         // ---- tile load: padded-domain index q = 160*t0 - 200 + i, reflect at both ends, zeros past n_act ----
-        for (int i = tid; i < LM_TILE; i += LM_THREADS) {
-            i64 q = t0 * kHop - 200 + i;
-            if (q < 0) q = -q;
-            if (q >= ltot) q = 2 * (ltot - 1) - q;
-            float v = 0.0f;
-            if (q >= 0 && q < n_act) v = load_sample(row, p.fmt, q);
-            s_tile[i + LM_SKEW * (i / kHop)] = v;
+        {
+            const i64 q0 = t0 * kHop - 200;
+            const char* src = row + q0 * elem;
+            const bool interior = q0 >= 0 && q0 + LM_TILE <= n_act && ((((uintptr_t)src) & 15) == 0);
+            if (interior && p.fmt == B2A_FMT_S16) {
+                const uint4* v4 = (const uint4*)src;
+                for (int j = tid; j < LM_TILE / 8; j += LM_THREADS) {
+                    const uint4 v = v4[j];
+                    float* d = s_tile + 8 * j + LM_SKEW * (j / 20);
+                    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int e = 0; e < 4; e++)
+                        *(float2*)(d + 2 * e) = make_float2((float)(short)(w[e] & 0xffff) * (1.0f / 32768.0f),
+                                                            (float)(short)(w[e] >> 16) * (1.0f / 32768.0f));
+                }
+            } else if (interior) {
+                const float4* v4 = (const float4*)src;
+                for (int j = tid; j < LM_TILE / 4; j += LM_THREADS) {
+                    const float4 v = v4[j];
+                    float* d = s_tile + 4 * j + LM_SKEW * (j / 40);
+                    *(float2*)d = make_float2(v.x, v.y);
+                    *(float2*)(d + 2) = make_float2(v.z, v.w);
+                }
+            } else {
+                for (int i = tid; i < LM_TILE; i += LM_THREADS) {
+                    i64 q = q0 + i;
+                    if (q < 0) q = -q;
+                    if (q >= ltot) q = 2 * (ltot - 1) - q;
+                    float v = 0.0f;
+                    if (q >= 0 && q < n_act) v = load_sample(row, p.fmt, q);
+                    s_tile[i + LM_SKEW * (i / kHop)] = v;
+                }
+            }
         }
         __syncthreads();
 
         // ---- stage 1: radix-10 butterflies over n1 for n2 = u + 5j, twiddle, transpose into s_ex ----
-        float* ex = s_ex + fl * LM_EF;
-        if (fft_lane) {
-            const float* fr = s_tile + fl * (kHop + LM_SKEW);
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int n2 = u + 5 * j;
-                cpx x[10], y[10];
+        for (int j = 0; j < 4; j++) {
+            cpx x[10], y[10];
 #pragma unroll
-                for (int n1 = 0; n1 < 10; n1++) {
-                    const int n = 20 * n1 + n2;
-                    float2 xv = *(const float2*)(fr + 2 * n + LM_SKEW * (n1 / 4));
-                    float2 wv = *(const float2*)(s_win + 2 * n);
-                    x[n1].r = xv.x * wv.x;
-                    x[n1].i = xv.y * wv.y;
-                }
-                dft10(x, y);
+            for (int n1 = 0; n1 < 10; n1++) {
+                const float2 xv = *(const float2*)(ps + 40 * n1 + 10 * j + LM_SKEW * (n1 / 4));
+                const float2 wv = *(const float2*)(pw + 40 * n1 + 10 * j);
+                x[n1].r = xv.x * wv.x;
+                x[n1].i = xv.y * wv.y;
+            }
+            dft10(x, y);
 #pragma unroll
-                for (int k1 = 0; k1 < 10; k1++) {
-                    float2 tw = s_tw200[n2 * 10 + k1];
-                    cpx w = {tw.x, tw.y};
-                    cpx v = (k1 == 0) ? y[0] : cmul(y[k1], w);
-                    *(float2*)(ex + k1 * 40 + 2 * n2) = make_float2(v.r, v.i);
-                }
+            for (int k1 = 0; k1 < 10; k1++) {
+                const float2 tw = pt[50 * j + k1];
+                const cpx w = {tw.x, tw.y};
+                const cpx v = (k1 == 0) ? y[0] : cmul(y[k1], w);
+                pex_w[20 * k1 + 5 * j] = make_float2(v.r, v.i);
             }
         }
-        __syncwarp();
+        __syncthreads();
 
         // ---- stage 2: radix-20 butterflies over n2 for residues k1a, k1b; unpack conjugate pairs in registers ----
-        cpx za[20], zb[20];
-        if (fft_lane) {
-            cpx x[20];
+        {
+            cpx za[20], zb[20];
+            {
+                cpx x[20];
 #pragma unroll
-            for (int n2 = 0; n2 < 20; n2++) { float2 v = *(const float2*)(ex + k1a * 40 + 2 * n2); x[n2] = {v.x, v.y}; }
-            dft20(x, za);
+                for (int n2 = 0; n2 < 20; n2++) { const float2 v = pex_a[n2]; x[n2] = {v.x, v.y}; }
+                dft20(x, za);
 #pragma unroll
-            for (int n2 = 0; n2 < 20; n2++) { float2 v = *(const float2*)(ex + k1b * 40 + 2 * n2); x[n2] = {v.x, v.y}; }
-            dft20(x, zb);
-        }
-        __syncwarp();   // every lane has read its exchange rows: the power spectrum may overwrite them
-        if (fft_lane) {
-            float* pw = ex;   // P[0..200] aliases the frame's exchange area
+                for (int n2 = 0; n2 < 20; n2++) { const float2 v = pex_b[n2]; x[n2] = {v.x, v.y}; }
+                dft20(x, zb);
+            }
             if (u != 0) {
                 // Z[k] = za[j] (k = u+10j),  Z[200-k] = zb[19-j]
+                const float2* ptw = s_tw400 + u;
+                float* p0 = pP + u;
+                float* p1 = pP + 200 - u;
 #pragma unroll
                 for (int j = 0; j < 20; j++) {
-                    const int k = u + 10 * j;
                     float pk, pm;
-                    unpack_pair(za[j], zb[19 - j], s_tw400[k], pk, pm);
-                    pw[k] = pk;
-                    pw[200 - k] = pm;
+                    unpack_pair4(za[j], zb[19 - j], ptw[10 * j], pk, pm);
+                    p0[10 * j] = pk;
+                    p1[-10 * j] = pm;
                 }
             } else {
                 // residue 0 pairs with itself: (10j, 200-10j); residue 5: (5+10j, 195-10j)
 #pragma unroll
                 for (int j = 0; j <= 10; j++) {
-                    const int k = 10 * j;
                     float pk, pm;
-                    unpack_pair(za[j], za[(20 - j) % 20], s_tw400[k], pk, pm);
-                    pw[k] = pk;
-                    pw[200 - k] = pm;
+                    unpack_pair4(za[j], za[(20 - j) % 20], s_tw400[10 * j], pk, pm);
+                    pP[10 * j] = pk;
+                    pP[200 - 10 * j] = pm;
                 }
 #pragma unroll
                 for (int j = 0; j < 10; j++) {
-                    const int k = 5 + 10 * j;
                     float pk, pm;
-                    unpack_pair(zb[j], zb[19 - j], s_tw400[k], pk, pm);
-                    pw[k] = pk;
-                    pw[200 - k] = pm;
+                    unpack_pair4(zb[j], zb[19 - j], s_tw400[5 + 10 * j], pk, pm);
+                    pP[5 + 10 * j] = pk;
+                    pP[195 - 10 * j] = pm;
                 }
             }
         }
         __syncthreads();
 
-        // ---- mel projection + log10 + store, one (mel, 8-frame group) per task ----
+        // ---- mel projection + log10 + store: warp u = mel group, lane = frame ----
         float tmin = 3.0e38f;
-        float* outb = p.out + (size_t)b * (size_t)n_mels * (size_t)T;
-        for (int task = tid; task < n_mels * (LM_FRAMES / 8); task += LM_THREADS) {
-            const int g = task / n_mels, m = task % n_mels;
-            const int ks = s_mstart[m], kl = s_mlen[m];
-            float acc[8];
-#pragma unroll
-            for (int f = 0; f < 8; f++) acc[f] = 0.0f;
-            const float* pp = s_ex + (g * 8) * LM_EF + ks;
-            for (int j = 0; j < kl; j++) {
-                const float w = s_melw[m * LM_MW + j];
-#pragma unroll
-                for (int f = 0; f < 8; f++) acc[f] = fmaf(w, pp[f * LM_EF + j], acc[f]);
-            }
-            const i64 tbase = t0 + g * 8;
-            float* orow = outb + (size_t)m * (size_t)T + tbase;
-#pragma unroll
-            for (int f = 0; f < 8; f++) {
-                if (tbase + f < T) {
-                    float lg = __log2f(fmaxf(acc[f], 1e-10f)) * 0.30102999566398120f;
-                    run_max = fmaxf(run_max, lg);
-                    float sv = (lg + 4.0f) * 0.25f;
-                    tmin = fminf(tmin, sv);
-                    orow[f] = sv;
-                }
+        {
+            const i64 t = t0 + f;
+            const bool valid = t < T;
+            float* ocol = p.out + (size_t)b * (size_t)NM * (size_t)T + (valid ? t : 0);
+            switch (u) {
+                case 0: mel_group<NM, 0>(pP, ocol, T, valid, run_max, tmin); break;
+                case 1: mel_group<NM, 1>(pP, ocol, T, valid, run_max, tmin); break;
+                case 2: mel_group<NM, 2>(pP, ocol, T, valid, run_max, tmin); break;
+                case 3: mel_group<NM, 3>(pP, ocol, T, valid, run_max, tmin); break;
+                default: mel_group<NM, 4>(pP, ocol, T, valid, run_max, tmin); break;
             }
         }
-        // per-tile minimum (lets mel_floor skip tiles that need no clamping)
+        // per-tile minimum (lets mel_floor skip tiles that need no clamping): written after the next barrier
         tmin = warp_reduce_min_f(tmin);
-        if (lane == 0) s_red[warp] = tmin;
-        __syncthreads();
-        if (tid == 0) {
-            float m0 = fminf(fminf(s_red[0], s_red[1]), fminf(s_red[2], s_red[3]));
-            p.tile_min[(size_t)b * (size_t)p.tiles_cap + (size_t)tile] = m0;
-        }
+        if (f == 0) s_red[u] = tmin;
+        prev_slot = (i64)b * p.tiles_cap + tile;
         if (p.per_clip) {
-            float bm = warp_reduce_max_f(run_max);
-            if (lane == 0 && bm > -1.0e38f) atomicMax(p.gmax_key + b, float_to_key(bm));
+            const float bm = warp_reduce_max_f(run_max);
+            if (f == 0 && bm > -1.0e38f) atomicMax(p.gmax_key + b, float_to_key(bm));
             run_max = -3.0e38f;
         }
     }
+    __syncthreads();
+    if (tid == 0 && prev_slot >= 0) {
+        p.tile_min[prev_slot] = fminf(fminf(fminf(s_red[0], s_red[1]), fminf(s_red[2], s_red[3])), s_red[4]);
+    }
     if (!p.per_clip) {
-        float bm = warp_reduce_max_f(run_max);
-        if (lane == 0 && bm > -1.0e38f) atomicMax(p.gmax_key, float_to_key(bm));
+        const float bm = warp_reduce_max_f(run_max);
+        if (f == 0 && bm > -1.0e38f) atomicMax(p.gmax_key, float_to_key(bm));
     }
 }
 
@@ -345,8 +393,7 @@ __global__ void logmel_init_kernel(int* gmax_key, int n) {
 }
 
 static size_t logmel_smem_bytes() {
-    size_t words = (size_t)LM_TILE_WORDS + (size_t)LM_FRAMES * LM_EF + kNFFT + 2 * 200 + 2 * 202 +
-                   (size_t)kMelMaxMels * LM_MW + 2 * kMelMaxMels + 8;
+    size_t words = (size_t)LM_TILE_WORDS + 2 * (size_t)LM_FRAMES * LM_EXP + (size_t)LM_FRAMES * LM_PP + kNFFT + 2 * 200 + 2 * 202 + 8;
     return words * 4;
 }
 
@@ -388,14 +435,12 @@ int logmel_launch(const void* d_audio, int fmt, i64 batch, i64 n, i64 row_stride
     auto kinit = logmel_init_kernel;
     B2A_LAUNCH(kinit, (nkeys + 255) / 256, 256, 0, stream, p.gmax_key, nkeys);
     size_t smem = logmel_smem_bytes();
-    auto k4 = stft_mel_kernel;
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto k4 = n_mels == 80 ? stft_mel_kernel<80> : stft_mel_kernel<128>;
+    {
+        cudaError_t e = cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // idempotent, cheap
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(stft_mel)");
-        attr_set = true;
     }
-    i64 grid = work < 148 * 3 * 2 ? work : 148 * 3 * 2;   // persistent: 3 CTAs/SM x 2 rounds of 148 SMs
+    i64 grid = work < 148 * 2 ? work : 148 * 2;   // persistent: 2 CTAs per SM (shared-memory bound)
     B2A_LAUNCH(k4, (unsigned)grid, LM_THREADS, smem, stream, p);
     B2A_CHECK_LAUNCH("stft_mel_kernel");
     i64 grid5 = work < 148 * 8 ? work : 148 * 8;
