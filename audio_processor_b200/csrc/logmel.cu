@@ -148,33 +148,45 @@ __device__ __forceinline__ float load_sample(const void* audio, int fmt, i64 idx
 }
 
 // ---- mel projection of one frame for the mels [M, M1) of a warp's group: compile-time sparse filterbank ----
+// lmax / lmin track log2(mel) over the group (converted once per tile by the caller); only the store is predicated
 template <int NM, int M, int M1>
 struct MelLoop {
-    __device__ static __forceinline__ void run(const float* __restrict__ Pf, float* __restrict__ ocol, i64 T, bool valid,
-                                               float& run_max, float& tmin) {
+    __device__ static __forceinline__ void run(const float* __restrict__ Pf, float* __restrict__ ocol, size_t Tstride, bool valid,
+                                               float& lmax, float& lmin) {
         constexpr int st = MelC<NM>::start[M], ln = MelC<NM>::len[M];
         float acc = 0.0f;
 #pragma unroll
         for (int j = 0; j < ln; j++) acc = fmaf(mel_w<NM>(M * kMelMaxWidth + j), Pf[st + j], acc);
-        const float lg = __log2f(fmaxf(acc, 1e-10f)) * 0.30102999566398120f;
-        const float sv = (lg + 4.0f) * 0.25f;
-        if (valid) {
-            run_max = fmaxf(run_max, lg);
-            tmin = fminf(tmin, sv);
-            ocol[(size_t)M * (size_t)T] = sv;
-        }
-        MelLoop<NM, M + 1, M1>::run(Pf, ocol, T, valid, run_max, tmin);
+        const float l2 = __log2f(fmaxf(acc, 1e-10f));
+        lmax = fmaxf(lmax, l2);
+        lmin = fminf(lmin, l2);
+        if (valid) *ocol = fmaf(l2 * 0.30102999566398120f, 0.25f, 1.0f);      // (log10 + 4) / 4, same roundings as Whisper's two steps
+        MelLoop<NM, M + 1, M1>::run(Pf, ocol + Tstride, Tstride, valid, lmax, lmin);
     }
 };
 template <int NM, int M1>
 struct MelLoop<NM, M1, M1> {
-    __device__ static __forceinline__ void run(const float*, float*, i64, bool, float&, float&) {}
+    __device__ static __forceinline__ void run(const float*, float*, size_t, bool, float&, float&) {}
 };
 template <int NM, int G>
-__device__ __forceinline__ void mel_group(const float* __restrict__ Pf, float* __restrict__ ocol, i64 T, bool valid,
-                                          float& run_max, float& tmin) {
-    MelLoop<NM, MelC<NM>::group[G], MelC<NM>::group[G + 1]>::run(Pf, ocol, T, valid, run_max, tmin);
+__device__ __forceinline__ void mel_group(const float* __restrict__ Pf, float* __restrict__ ocol, size_t Tstride, bool valid,
+                                          float& lmax, float& lmin) {
+    MelLoop<NM, MelC<NM>::group[G], MelC<NM>::group[G + 1]>::run(Pf, ocol + (size_t)MelC<NM>::group[G] * Tstride, Tstride, valid, lmax, lmin);
 }
+
+#ifndef B2A_EMU
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_drain() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
+#else
+static inline void cp_async8(void* smem_dst, const void* gsrc) { memcpy(smem_dst, gsrc, 8); }
+static inline void cp_async_drain() {}
+#endif
+
+constexpr int LM_PAIRS = LM_TILE / 2;                                   // 2680 sample pairs per tile
+constexpr int LM_PRE = (LM_PAIRS + LM_THREADS - 1) / LM_THREADS;        // 17 pairs per thread
 
 template <int NM>
 __global__ void __launch_bounds__(LM_THREADS, 2) stft_mel_kernel(LogMelParams p) {
@@ -213,62 +225,92 @@ __global__ void __launch_bounds__(LM_THREADS, 2) stft_mel_kernel(LogMelParams p)
 
     float run_max = -3.0e38f;
     i64 prev_slot = -1;                          // tile_min slot of the previous work item (written one barrier later)
+    const i64 n_work = tiles * p.batch;
 
-    for (i64 work = blockIdx.x; work < tiles * p.batch; work += gridDim.x) {
+    // where a work item's samples live: row base, first padded-domain index, and whether the fast (interior) path applies
+    struct Src { const char* row; i64 q0; int mode; };   // mode 0: generic (reflect / zero pad), 1: interior s16, 2: interior f32
+    auto locate = [&](i64 work) -> Src {
+        Src r;
+        const int b = (int)(work / tiles);
+        const i64 tile = work - (i64)b * tiles;
+        r.row = (const char*)p.audio + (size_t)b * (size_t)p.row_stride * elem;
+        r.q0 = tile * (LM_FRAMES * kHop) - 200;
+        const bool interior = r.q0 >= 0 && r.q0 + LM_TILE <= n_act && ((((uintptr_t)(r.row + r.q0 * elem)) & 7) == 0);
+        r.mode = interior ? (p.fmt == B2A_FMT_S16 ? 1 : 2) : 0;
+        return r;
+    };
+    // generic tile load: padded-domain index q = q0 + i, reflect at both ends, zeros past n_act
+    auto load_generic = [&](const Src& sc) {
+        for (int i = tid; i < LM_TILE; i += LM_THREADS) {
+            i64 q = sc.q0 + i;
+            if (q < 0) q = -q;
+            if (q >= ltot) q = 2 * (ltot - 1) - q;
+            float v = 0.0f;
+            if (q >= 0 && q < n_act) v = load_sample(sc.row, p.fmt, q);
+            s_tile[i + LM_SKEW * (i / kHop)] = v;
+        }
+    };
+    // pair pr (samples 2pr, 2pr+1) lives at word 2pr + LM_SKEW * (pr / 80) of the skewed tile
+    auto store_s16_pairs = [&](const unsigned (&pre)[LM_PRE]) {
+#pragma unroll
+        for (int i = 0; i < LM_PRE; i++) {
+            const int pr = tid + LM_THREADS * i;
+            if (pr < LM_PAIRS)
+                *(float2*)(s_tile + 2 * pr + LM_SKEW * (pr / 80)) =
+                    make_float2((float)(short)(pre[i] & 0xffff) * (1.0f / 32768.0f), (float)(short)(pre[i] >> 16) * (1.0f / 32768.0f));
+        }
+    };
+    auto fetch_s16_pairs = [&](const Src& sc, unsigned (&pre)[LM_PRE]) {
+        const unsigned* g = (const unsigned*)(sc.row + sc.q0 * 2);
+#pragma unroll
+        for (int i = 0; i < LM_PRE; i++) {
+            const int pr = tid + LM_THREADS * i;
+            pre[i] = pr < LM_PAIRS ? g[pr] : 0u;
+        }
+    };
+    auto copy_f32_pairs = [&](const Src& sc) {
+        const float2* g = (const float2*)(sc.row + sc.q0 * 4);
+#pragma unroll
+        for (int i = 0; i < LM_PRE; i++) {
+            const int pr = tid + LM_THREADS * i;
+            if (pr < LM_PAIRS) cp_async8(s_tile + 2 * pr + LM_SKEW * (pr / 80), g + pr);
+        }
+    };
+
+    // first tile of this CTA: synchronous
+    if ((i64)blockIdx.x < n_work) {
+        const Src sc = locate(blockIdx.x);
+        if (sc.mode == 1) { unsigned pre[LM_PRE]; fetch_s16_pairs(sc, pre); store_s16_pairs(pre); }
+        else if (sc.mode == 2) { copy_f32_pairs(sc); cp_async_drain(); }
+        else load_generic(sc);
+    }
+
+    for (i64 work = blockIdx.x; work < n_work; work += gridDim.x) {
         const int b = (int)(work / tiles);
         const i64 tile = work - (i64)b * tiles;
         const i64 t0 = tile * LM_FRAMES;
-        const char* row = (const char*)p.audio + (size_t)b * (size_t)p.row_stride * elem;
+        const i64 nwork = work + gridDim.x;
+        Src nsc;
+        nsc.mode = -1;
+        if (nwork < n_work) nsc = locate(nwork);
 
-        __syncthreads();   // tables staged; previous tile fully consumed (s_tile by stage 1, s_red by the line below)
+        __syncthreads();   // s_tile (and, first time, the tables) visible; previous tile's s_red written
         if (tid == 0 && prev_slot >= 0) {
-            p.tile_min[prev_slot] = fminf(fminf(fminf(s_red[0], s_red[1]), fminf(s_red[2], s_red[3])), s_red[4]);
+            const float l2 = fminf(fminf(fminf(s_red[0], s_red[1]), fminf(s_red[2], s_red[3])), s_red[4]);
+            p.tile_min[prev_slot] = fmaf(l2 * 0.30102999566398120f, 0.25f, 1.0f);
         }
-        // ---- tile load: padded-domain index q = 160*t0 - 200 + i, reflect at both ends, zeros past n_act ----
-        {
-            const i64 q0 = t0 * kHop - 200;
-            const char* src = row + q0 * elem;
-            const bool interior = q0 >= 0 && q0 + LM_TILE <= n_act && ((((uintptr_t)src) & 15) == 0);
-            if (interior && p.fmt == B2A_FMT_S16) {
-                const uint4* v4 = (const uint4*)src;
-                for (int j = tid; j < LM_TILE / 8; j += LM_THREADS) {
-                    const uint4 v = v4[j];
-                    float* d = s_tile + 8 * j + LM_SKEW * (j / 20);
-                    const unsigned w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int e = 0; e < 4; e++)
-                        *(float2*)(d + 2 * e) = make_float2((float)(short)(w[e] & 0xffff) * (1.0f / 32768.0f),
-                                                            (float)(short)(w[e] >> 16) * (1.0f / 32768.0f));
-                }
-            } else if (interior) {
-                const float4* v4 = (const float4*)src;
-                for (int j = tid; j < LM_TILE / 4; j += LM_THREADS) {
-                    const float4 v = v4[j];
-                    float* d = s_tile + 4 * j + LM_SKEW * (j / 40);
-                    *(float2*)d = make_float2(v.x, v.y);
-                    *(float2*)(d + 2) = make_float2(v.z, v.w);
-                }
-            } else {
-                for (int i = tid; i < LM_TILE; i += LM_THREADS) {
-                    i64 q = q0 + i;
-                    if (q < 0) q = -q;
-                    if (q >= ltot) q = 2 * (ltot - 1) - q;
-                    float v = 0.0f;
-                    if (q >= 0 && q < n_act) v = load_sample(row, p.fmt, q);
-                    s_tile[i + LM_SKEW * (i / kHop)] = v;
-                }
-            }
-        }
-        __syncthreads();
+        // next tile's s16 samples travel global -> registers while stage 1 runs
+        unsigned pre[LM_PRE];
+        if (nsc.mode == 1) fetch_s16_pairs(nsc, pre);
 
         // ---- stage 1: radix-10 butterflies over n1 for n2 = u + 5j, twiddle, transpose into s_ex ----
-#pragma unroll
+#pragma unroll 1
         for (int j = 0; j < 4; j++) {
             cpx x[10], y[10];
 #pragma unroll
             for (int n1 = 0; n1 < 10; n1++) {
-                const float2 xv = *(const float2*)(ps + 40 * n1 + 10 * j + LM_SKEW * (n1 / 4));
-                const float2 wv = *(const float2*)(pw + 40 * n1 + 10 * j);
+                const float2 xv = *(const float2*)(ps + 10 * j + 40 * n1 + LM_SKEW * (n1 / 4));
+                const float2 wv = *(const float2*)(pw + 10 * j + 40 * n1);
                 x[n1].r = xv.x * wv.x;
                 x[n1].i = xv.y * wv.y;
             }
@@ -278,10 +320,15 @@ __global__ void __launch_bounds__(LM_THREADS, 2) stft_mel_kernel(LogMelParams p)
                 const float2 tw = pt[50 * j + k1];
                 const cpx w = {tw.x, tw.y};
                 const cpx v = (k1 == 0) ? y[0] : cmul(y[k1], w);
-                pex_w[20 * k1 + 5 * j] = make_float2(v.r, v.i);
+                pex_w[5 * j + 20 * k1] = make_float2(v.r, v.i);
             }
         }
-        __syncthreads();
+        __syncthreads();   // exchange complete; every stage-1 read of s_tile is done
+
+        // ---- next tile -> s_tile (overlaps stage 2 + mel projection) ----
+        if (nsc.mode == 1) store_s16_pairs(pre);
+        else if (nsc.mode == 2) copy_f32_pairs(nsc);
+        else if (nsc.mode == 0) load_generic(nsc);
 
         // ---- stage 2: radix-20 butterflies over n2 for residues k1a, k1b; unpack conjugate pairs in registers ----
         {
@@ -325,35 +372,38 @@ __global__ void __launch_bounds__(LM_THREADS, 2) stft_mel_kernel(LogMelParams p)
                 }
             }
         }
-        __syncthreads();
+        __syncthreads();   // power spectra complete
 
         // ---- mel projection + log10 + store: warp u = mel group, lane = frame ----
-        float tmin = 3.0e38f;
         {
             const i64 t = t0 + f;
             const bool valid = t < T;
             float* ocol = p.out + (size_t)b * (size_t)NM * (size_t)T + (valid ? t : 0);
+            float lmax = -3.0e38f, lmin = 3.0e38f;
             switch (u) {
-                case 0: mel_group<NM, 0>(pP, ocol, T, valid, run_max, tmin); break;
-                case 1: mel_group<NM, 1>(pP, ocol, T, valid, run_max, tmin); break;
-                case 2: mel_group<NM, 2>(pP, ocol, T, valid, run_max, tmin); break;
-                case 3: mel_group<NM, 3>(pP, ocol, T, valid, run_max, tmin); break;
-                default: mel_group<NM, 4>(pP, ocol, T, valid, run_max, tmin); break;
+                case 0: mel_group<NM, 0>(pP, ocol, (size_t)T, valid, lmax, lmin); break;
+                case 1: mel_group<NM, 1>(pP, ocol, (size_t)T, valid, lmax, lmin); break;
+                case 2: mel_group<NM, 2>(pP, ocol, (size_t)T, valid, lmax, lmin); break;
+                case 3: mel_group<NM, 3>(pP, ocol, (size_t)T, valid, lmax, lmin); break;
+                default: mel_group<NM, 4>(pP, ocol, (size_t)T, valid, lmax, lmin); break;
             }
+            if (valid) run_max = fmaxf(run_max, lmax * 0.30102999566398120f);
+            // per-tile minimum (lets mel_floor skip tiles that need no clamping): published after the next barrier
+            lmin = warp_reduce_min_f(valid ? lmin : 3.0e38f);
+            if (f == 0) s_red[u] = lmin;
         }
-        // per-tile minimum (lets mel_floor skip tiles that need no clamping): written after the next barrier
-        tmin = warp_reduce_min_f(tmin);
-        if (f == 0) s_red[u] = tmin;
         prev_slot = (i64)b * p.tiles_cap + tile;
         if (p.per_clip) {
             const float bm = warp_reduce_max_f(run_max);
             if (f == 0 && bm > -1.0e38f) atomicMax(p.gmax_key + b, float_to_key(bm));
             run_max = -3.0e38f;
         }
+        if (nsc.mode == 2) cp_async_drain();
     }
     __syncthreads();
     if (tid == 0 && prev_slot >= 0) {
-        p.tile_min[prev_slot] = fminf(fminf(fminf(s_red[0], s_red[1]), fminf(s_red[2], s_red[3])), s_red[4]);
+        const float l2 = fminf(fminf(fminf(s_red[0], s_red[1]), fminf(s_red[2], s_red[3])), s_red[4]);
+        p.tile_min[prev_slot] = fmaf(l2 * 0.30102999566398120f, 0.25f, 1.0f);
     }
     if (!p.per_clip) {
         const float bm = warp_reduce_max_f(run_max);
