@@ -97,20 +97,22 @@ __global__ void __launch_bounds__(SIL_THREADS) cover_kernel(const u64* __restric
     const i64 ebase = t0 - W - 1;               // energy index of local slot 0
     if (tid < 2) s_cnt[tid] = 0;
 
-    // ---- exclusive prefix of energies over the tile + halos (each thread owns a contiguous chunk) ----
+    // ---- exclusive prefix of energies over the tile + halos ----
+    // coalesced load of the raw energies (slot j+1), then each thread scans a contiguous chunk; the chunk length is odd
+    // so that the 8-byte shared-memory accesses of a warp (stride = chunk) fall in distinct banks
+    for (int j = tid; j < NE; j += SIL_THREADS) {
+        const i64 t = ebase + j;
+        s_p[j + 1] = (t >= 0 && t < c.len_ms && t < c.n_energy) ? e[t] : 0ull;
+    }
+    __syncthreads();
     {
-        const int per = (NE + SIL_THREADS - 1) / SIL_THREADS;
-        const int lo = tid * per, hi = min(lo + per, NE);
+        const int per = ((NE + SIL_THREADS - 1) / SIL_THREADS) | 1;
+        const int lo = min(tid * per, NE), hi = min(lo + per, NE);
         u64 sum = 0;
-        for (int j = lo; j < hi; j++) {
-            i64 t = ebase + j;
-            u64 v = (t >= 0 && t < c.len_ms && t < c.n_energy) ? e[t] : 0ull;
-            s_p[j + 1] = v;                     // stash raw value one slot up; fixed below
-            sum += v;
-        }
+        for (int j = lo; j < hi; j++) sum += s_p[j + 1];
         u64 tot;
         u64 pre = block_exclusive_scan<u64>(sum, s_w64, &tot);
-        // turn the stashed raw values into an exclusive prefix: s_p[j] = sum of slots < j
+        // turn the raw values into an exclusive prefix: s_p[j] = sum of slots < j
         u64 run = pre;
         for (int j = lo; j < hi; j++) {
             u64 v = s_p[j + 1];
@@ -124,13 +126,13 @@ __global__ void __launch_bounds__(SIL_THREADS) cover_kernel(const u64* __restric
     // ---- start flags f[i] for i in [t0-W-1, t0+TS), then their exclusive prefix ----
     {
         const int NF = SIL_TS + W + 1;
-        const int per = (NF + SIL_THREADS - 1) / SIL_THREADS;
-        const int lo = tid * per, hi = min(lo + per, NF);
+        const int per = ((NF + SIL_THREADS - 1) / SIL_THREADS) | 1;      // odd: conflict-free strided shared-memory access
+        const int lo = min(tid * per, NF), hi = min(lo + per, NF);
         int sum = 0;
         for (int j = lo; j < hi; j++) {
             i64 i = ebase + j;                   // flag slot j <-> start ms i (same origin as energies)
             int f = 0;
-            if (i >= 0 && i <= c.last && ((i % c.step) == 0 || i == c.last)) {
+            if (i >= 0 && i <= c.last && (c.step == 1 || (i % c.step) == 0 || i == c.last)) {
                 u64 E = s_p[j + W] - s_p[j];     // sum e[i .. i+W-1]
                 f = E < c.limit;
             }
