@@ -127,8 +127,10 @@ const ResampleDesign* get_resample_design(int in_rate, int out_rate) {
 
 // ---- filter bank of the tensor-core FIR (fir_mma.cuh) as mma.m16n8k16 B fragments ------------------------------
 // layout [block b][k-step s][8-output half nt][term: 0 = T_hi, 1 = T_lo][lane] -> uint2 {b0, b1};
-// lane (g = lane >> 2, t = lane & 3): b0 = B[k = 2t, 2t+1][n = g], b1 = B[k = 2t+8, 2t+9][n = g] with
-// B[k][n] = 2^12 * tap[phase(J)][kb + 16 s + k - (J M)/L],  J = 16 b + 8 nt + n  (zero outside the filter).
+// lane (g = lane >> 2, t = lane & 3): b0 = k-slots (2t, 2t+1), b1 = k-slots (2t+8, 2t+9) of column n = g.  The
+// kernel permutes the k-slots of a k-step so that lane t owns input frames 4t..4t+3 (one 8-byte A load per row):
+// slot 2t, 2t+1, 2t+8, 2t+9 <-> frame offsets f = 4t, 4t+1, 4t+2, 4t+3, and
+// B[f][n] = 2^12 * tap[phase(J)][kb + 16 s + f - (J M)/L],  J = 16 b + 8 nt + n  (zero outside the filter).
 template <int IN_RATE>
 static void build_fir_mma_table(const float* taps /*[L][TAPS]*/, std::vector<uint2>& out) {
     using G = FirMmaGeom<IN_RATE>;
@@ -142,8 +144,8 @@ static void build_fir_mma_table(const float* taps /*[L][TAPS]*/, std::vector<uin
                     const int BJ = (J * G::M) / G::L, ph = (J * G::M) % G::L;
                     uint16_t hi[4], lo[4];
                     for (int e = 0; e < 4; e++) {
-                        const int k = 2 * t + (e & 1) + 8 * (e >> 1);
-                        const int i = G::kb(b) + 16 * s + k - BJ;
+                        const int f = 4 * t + e;
+                        const int i = G::kb(b) + 16 * s + f - BJ;
                         float T = 0.0f;
                         if (i >= 0 && i < G::TAPS) T = taps[(size_t)ph * G::TAPS + i] * (float)(1 << kFmTapShift);
                         hi[e] = b2a_f16::f32_to_f16(T);

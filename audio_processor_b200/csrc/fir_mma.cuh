@@ -16,7 +16,9 @@
 // run, so for 16 runs at once
 //     D[16 runs x 16 outputs] = X[16 runs x 16 KS frames] * T_b[16 KS frames x 16 outputs]
 // with T_b the (constant, zero padded) taps of the block.  mma.sync.m16n8k16 (f16 in, f32 accumulate) computes it:
-// A = X from shared memory, B = T_b from registers (loaded once per persistent warp; warp b owns block b).
+// A = X from shared memory, B = T_b from registers (loaded once per persistent warp; MMA warp b owns block b).
+// Within a k-step the 16 k-slots are permuted so that lane t owns frames 4t..4t+3: an A fragment row is one
+// 8-byte shared-memory load (the filter table is built with the same permutation).
 //
 // Exactness.  The window value is v = L + R (17-bit integer; the output is sum(t * v) / 2).  v = 128 * hv + lo
 // with hv in [-512, 511] and lo in [0, 127]: both exact in f16.  Taps are scaled by 2^12 and split T = T_hi + T_lo
@@ -26,31 +28,36 @@
 // 2^-22 tap representation and the summation order — the same size as f32 rounding itself (tests: <= 1 LSB from
 // libswresample, >= 99.8 % of samples identical, <= 1e-5 from the float64 restatement).
 //
-// Per tile of RT = 32 runs a persistent CTA of 10 warps:
-//   1. waits for the tile's raw frames (one contiguous span, fetched by 1-D bulk TMA into a double buffer while
-//      the previous tile is processed; completion on an mbarrier),
-//   2. converts them to (hv | lo) f16 pairs, one 32-bit word per frame, in run-major rows of pitch P (P mod 32
-//      = 8 or 24 makes the 8-byte A-fragment loads conflict free),
-//   3. runs the MMAs (warp b = block b, two 16-run tiles), rounds half-to-even + clips to s16 (swr audioconvert)
-//      into a staging tile,
-//   4. copies the staging tile out with coalesced 16-byte stores and accumulates the per-millisecond sum of
-//      squares of the QUANTISED samples (uint64) that the silence detector consumes.
+// Kernel: persistent CTA per SM, 16 warps in two roles that run concurrently on different pipes, coupled only by
+// mbarriers (no block-wide barrier in the loop); tile = 16 runs, every buffer double buffered:
+//   converter warps (6): wait for the tile's raw frames (one contiguous span fetched by 1-D bulk TMA, issued two
+//       tiles ahead), split every frame into (hv, lo) f16 and write the two planes (run-major rows, pitch P with
+//       P/2 = 8 or 24 mod 32 words: conflict-free 8-byte fragment loads); then copy the PREVIOUS tile's quantised
+//       outputs from the staging tile to global memory with coalesced 16-byte stores, accumulating the
+//       per-millisecond sum of squares (uint64) that the silence detector consumes.
+//   MMA warps (10): wait for the planes, run the k-steps (all-zero tap k-steps skipped at compile time), round
+//       half-to-even + clip to s16 (swr audioconvert) into the staging tile.
 #pragma once
+#include <cstdlib>
+
 #include "b2a_common.cuh"
 
 namespace b2a {
 
 template <int IN_RATE> struct FirMmaTraits;
-template <> struct FirMmaTraits<44100> { static constexpr int L = 160, M = 441, TAPS = 92, KS = 9, P = 536; };
-template <> struct FirMmaTraits<48000> { static constexpr int L = 1, M = 3, TAPS = 100, KS = 10, P = 584; };
+template <> struct FirMmaTraits<44100> { static constexpr int L = 160, M = 441, TAPS = 92, KS = 9, P = 560; };
+template <> struct FirMmaTraits<48000> { static constexpr int L = 1, M = 3, TAPS = 100, KS = 10, P = 592; };
 
 constexpr int kFmNout = 160;            // outputs per run (10 ms)
 constexpr int kFmBlocks = 10;           // 16-output blocks per run
-constexpr int kFmRT = 32;               // runs per CTA tile
-constexpr int kFmWarps = 10;            // warp b owns block b
-constexpr int kFmThreads = kFmWarps * 32;
+constexpr int kFmRT = 16;               // runs per tile (= MMA M)
+constexpr int kFmMmaWarps = 10;         // MMA warp b owns block b
+constexpr int kFmCvtWarps = 6;          // converter / copy-out warps
+constexpr int kFmCvtThreads = kFmCvtWarps * 32;
+constexpr int kFmThreads = (kFmMmaWarps + kFmCvtWarps) * 32;
 constexpr int kFmOutPitch = 168;        // staging-tile row pitch in samples (84 words: conflict-free fragment stores)
 constexpr int kFmTapShift = 12;         // taps are scaled by 2^12 before the f16 split
+constexpr int kFmBarBytes = 16;         // one mbarrier slot (8 bytes on the GPU; the emulation keeps counters in 16)
 
 template <int IN_RATE>
 struct FirMmaGeom {
@@ -58,15 +65,21 @@ struct FirMmaGeom {
     static constexpr int L = TR::L, M = TR::M, TAPS = TR::TAPS, KS = TR::KS, P = TR::P;
     static constexpr int CENTER = (TAPS - 1) / 2;
     static constexpr int S = kFmNout * M / L;                       // input frames per run (441 / 480)
+    static constexpr int kb(int b) { return (16 * b * M) / L; }     // window start of block b (frames from the row origin)
+    static constexpr int PC = kb(kFmBlocks - 1) + 16 * KS;          // columns actually read by the MMAs (540 / 592)
+    static constexpr int PW = P / 2;                                // words per plane row
     static constexpr int CENTER_BYTES16 = (CENTER * 4 + 15) / 16 * 16;
     static constexpr int AL = (CENTER_BYTES16 - CENTER * 4) / 4;    // frames the raw tile starts early (16-byte alignment)
-    static constexpr int RAWF = (kFmRT - 1) * S + P;                // frames a tile's rows touch
+    static constexpr int RAWF = (kFmRT - 1) * S + PC;               // frames a tile's rows touch
     static constexpr int RAW_BYTES = ((AL + RAWF) * 4 + 15) / 16 * 16;
-    static constexpr int PLANE_BYTES = kFmRT * P * 4 + 256;         // + zeroed pad (last row's K padding reads past P)
+    static constexpr int PLANE_WORDS = kFmRT * PW;                  // one plane (hv or lo) of one tile
+    static constexpr int PLANES_BYTES = 2 * PLANE_WORDS * 4;        // hv + lo
     static constexpr int OUT_BYTES = kFmRT * kFmOutPitch * 2;
-    static constexpr int SMEM_BYTES = 2 * RAW_BYTES + PLANE_BYTES + OUT_BYTES + 64;
-    static constexpr int CHUNKS = (P + 31) / 32;                    // 32-frame conversion units per row
-    static constexpr int kb(int b) { return (16 * b * M) / L; }     // window start of block b (frames from the row origin)
+    static constexpr int NBARS = 12;
+    static constexpr int SMEM_BYTES = 2 * RAW_BYTES + 2 * PLANES_BYTES + 2 * OUT_BYTES + NBARS * kFmBarBytes;
+    static constexpr int PAIRS_ROW = PC / 2;                        // frame pairs converted per row
+    static constexpr int PAIRS = kFmRT * PAIRS_ROW;
+    static constexpr int CVT_TRIPS = (PAIRS + kFmCvtThreads - 1) / kFmCvtThreads;
     // k-step s contributes to the 8-output half nt of SOME block iff [16 s, 16 s + 16) meets a window of that half
     static constexpr bool needed(int s, int nt) {
         int lo = 1 << 30, hi = 0;
@@ -79,9 +92,10 @@ struct FirMmaGeom {
         return 16 * s < hi && 16 * s + 16 > lo;
     }
     static_assert((kFmRT * S * 4) % 16 == 0, "tile pitch must keep 16-byte alignment");
-    static_assert(P % 2 == 0 && (P % 32 == 8 || P % 32 == 24), "row pitch must make 8-byte fragment loads conflict free");
-    static_assert(P >= S + TAPS, "row must hold a run plus the filter span");
+    static_assert(P % 4 == 0 && (PW % 32 == 8 || PW % 32 == 24), "plane pitch must make 8-byte fragment loads conflict free");
+    static_assert(P >= PC && PC % 2 == 0, "row must hold every column the MMAs read");
     static_assert(16 * KS >= ((15 * M) / L + 1) + TAPS, "K must cover the widest window of a block");
+    static_assert(kb(1) % 4 == 0 && kb(3) % 4 == 0 && kb(9) % 4 == 0, "block windows must start on 8-byte plane boundaries");
 };
 
 struct FirMmaArgs {
@@ -103,6 +117,9 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(saddr_t bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(saddr_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(saddr_t bar, unsigned parity) {
     unsigned ok;
     do {
@@ -114,11 +131,6 @@ __device__ __forceinline__ void mbar_wait(saddr_t bar, unsigned parity) {
 __device__ __forceinline__ void bulk_load(saddr_t dst, const void* src, unsigned bytes, saddr_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned sel) {
-    unsigned r;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
-    return r;
 }
 // packed f16 subtraction on raw bits
 __device__ __forceinline__ unsigned hsub2_bits(unsigned a, unsigned b) {
@@ -134,22 +146,20 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const unsigned (&a)[4],
 #else
 typedef uintptr_t saddr_t;
 static inline saddr_t smem_addr(const void* p) { return (uintptr_t)p; }
-// mbarrier stand-in: word 0 = completed phases, word 1 = bytes still expected in the current phase
-static inline void mbar_init(saddr_t bar, unsigned) { ((unsigned*)bar)[0] = 0; ((unsigned*)bar)[1] = 0; }
+// mbarrier stand-in: [0] completed phases, [1] arrivals still expected, [2] arrival count, [3] bytes still expected
+static inline void emu_mbar_try_complete(unsigned* b) {
+    if (b[1] == 0 && (int)b[3] <= 0) { b[0]++; b[1] = b[2]; b[3] = 0; }
+}
+static inline void mbar_init(saddr_t bar, unsigned count) { unsigned* b = (unsigned*)bar; b[0] = 0; b[1] = count; b[2] = count; b[3] = 0; }
 static inline void mbar_fence_init() {}
-static inline void mbar_expect_tx(saddr_t bar, unsigned bytes) { ((unsigned*)bar)[1] = bytes; }
+static inline void mbar_expect_tx(saddr_t bar, unsigned bytes) { unsigned* b = (unsigned*)bar; b[3] += bytes; b[1]--; emu_mbar_try_complete(b); }
+static inline void mbar_arrive(saddr_t bar) { unsigned* b = (unsigned*)bar; b[1]--; emu_mbar_try_complete(b); }
 static inline void mbar_wait(saddr_t bar, unsigned parity) { while ((((volatile unsigned*)bar)[0] & 1u) == parity) emu::yield(); }
 static inline void bulk_load(saddr_t dst, const void* src, unsigned bytes, saddr_t bar) {
     memcpy((void*)dst, src, bytes);
     unsigned* b = (unsigned*)bar;
-    b[1] -= bytes;
-    if (b[1] == 0) b[0]++;
-}
-static inline unsigned prmt(unsigned a, unsigned b, unsigned sel) {
-    unsigned long long v = ((unsigned long long)b << 32) | a;
-    unsigned r = 0;
-    for (int i = 0; i < 4; i++) r |= (unsigned)((v >> (8 * ((sel >> (4 * i)) & 7))) & 0xff) << (8 * i);
-    return r;
+    b[3] -= bytes;
+    emu_mbar_try_complete(b);
 }
 static inline unsigned hsub2_bits(unsigned a, unsigned b) {
     unsigned lo = emu::f32_to_f16(emu::f16_to_f32((unsigned short)(a & 0xffff)) - emu::f16_to_f32((unsigned short)(b & 0xffff)));
@@ -159,23 +169,22 @@ static inline unsigned hsub2_bits(unsigned a, unsigned b) {
 static inline void mma_16816(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) { emu::mma_m16n8k16_f16(d, a, b0, b1); }
 #endif
 
-// one (block, 16-run tile): D12 = (T_hi + T_lo) . hv,  D34 = (T_hi + T_lo) . lo
+// one block of one 16-run tile: D12 = (T_hi + T_lo) . hv,  D34 = (T_hi + T_lo) . lo
+// phv / plo: this lane's row pointers (row g) into the hv / lo planes at column kb + 4t; row g+8 is 8*PW words further
 template <int IN_RATE>
-__device__ __forceinline__ void fir_mma_block(const unsigned* __restrict__ rows, int kb, int g, int t,
+__device__ __forceinline__ void fir_mma_block(const unsigned* __restrict__ phv, const unsigned* __restrict__ plo,
                                               const uint2 (&breg)[FirMmaTraits<IN_RATE>::KS][2][2],
                                               float (&d12)[2][4], float (&d34)[2][4]) {
     using G = FirMmaGeom<IN_RATE>;
-    const unsigned* ra = rows + (size_t)g * G::P + kb + 2 * t;
-    const unsigned* rb = ra + 8 * G::P;
 #pragma unroll
     for (int s = 0; s < G::KS; s++) {
-        const uint2 w0 = *(const uint2*)(ra + 16 * s);
-        const uint2 w1 = *(const uint2*)(rb + 16 * s);
-        const uint2 w2 = *(const uint2*)(ra + 16 * s + 8);
-        const uint2 w3 = *(const uint2*)(rb + 16 * s + 8);
-        // word = hv (low half) | lo (high half); a fragment register holds two consecutive k
-        const unsigned ahv[4] = {prmt(w0.x, w0.y, 0x5410), prmt(w1.x, w1.y, 0x5410), prmt(w2.x, w2.y, 0x5410), prmt(w3.x, w3.y, 0x5410)};
-        const unsigned alo[4] = {prmt(w0.x, w0.y, 0x7632), prmt(w1.x, w1.y, 0x7632), prmt(w2.x, w2.y, 0x7632), prmt(w3.x, w3.y, 0x7632)};
+        // lane t owns frames 4t..4t+3 of the k-step: word 0 = k-slots (2t, 2t+1), word 1 = k-slots (2t+8, 2t+9)
+        const uint2 h0 = *(const uint2*)(phv + 8 * s);
+        const uint2 h1 = *(const uint2*)(phv + 8 * s + 8 * G::PW);
+        const uint2 l0 = *(const uint2*)(plo + 8 * s);
+        const uint2 l1 = *(const uint2*)(plo + 8 * s + 8 * G::PW);
+        const unsigned ahv[4] = {h0.x, h1.x, h0.y, h1.y};
+        const unsigned alo[4] = {l0.x, l1.x, l0.y, l1.y};
 #pragma unroll
         for (int nt = 0; nt < 2; nt++) {
             if (!G::needed(s, nt)) continue;          // all-zero taps for every block: compile-time skip
@@ -191,90 +200,70 @@ template <int IN_RATE>
 __global__ void __launch_bounds__(kFmThreads, 1) fir_mma_kernel(const FirMmaArgs a) {
     using G = FirMmaGeom<IN_RATE>;
     B2A_DYN_SMEM(smem);
-    unsigned char* raw0 = smem;
-    unsigned* planes = (unsigned*)(smem + 2 * G::RAW_BYTES);
-    int16_t* otile = (int16_t*)(smem + 2 * G::RAW_BYTES + G::PLANE_BYTES);
-    const saddr_t bars = smem_addr(smem + 2 * G::RAW_BYTES + G::PLANE_BYTES + G::OUT_BYTES);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    unsigned char* raw0 = smem;                                                  // [2][RAW_BYTES]
+    unsigned* planes0 = (unsigned*)(smem + 2 * G::RAW_BYTES);                    // [2][hv plane | lo plane]
+    int16_t* otile0 = (int16_t*)(smem + 2 * G::RAW_BYTES + 2 * G::PLANES_BYTES); // [2][RT][kFmOutPitch]
+    const saddr_t bars = smem_addr(smem + 2 * G::RAW_BYTES + 2 * G::PLANES_BYTES + 2 * G::OUT_BYTES);
+    // barrier slots: RF raw full (TMA), RE raw empty, PF planes full, PE planes empty, OF staging full, OE staging empty
+    auto RF = [&](int b) { return bars + (unsigned)((0 + b) * kFmBarBytes); };
+    auto RE = [&](int b) { return bars + (unsigned)((2 + b) * kFmBarBytes); };
+    auto PF = [&](int b) { return bars + (unsigned)((4 + b) * kFmBarBytes); };
+    auto PE = [&](int b) { return bars + (unsigned)((6 + b) * kFmBarBytes); };
+    auto OF = [&](int b) { return bars + (unsigned)((8 + b) * kFmBarBytes); };
+    auto OE = [&](int b) { return bars + (unsigned)((10 + b) * kFmBarBytes); };
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    // constant operand: this warp's block of the filter bank, as B fragments (hi, lo) per k-step and 8-output half
-    uint2 breg[G::KS][2][2];
-    {
-        const uint2* bt = a.btab + (size_t)warp * (G::KS * 2 * 2 * 32) + lane;
-#pragma unroll
-        for (int s = 0; s < G::KS; s++)
-#pragma unroll
-            for (int nt = 0; nt < 2; nt++)
-#pragma unroll
-                for (int term = 0; term < 2; term++)
-                    breg[s][nt][term] = G::needed(s, nt) ? bt[((s * 2 + nt) * 2 + term) * 32] : make_uint2(0u, 0u);
-    }
     if (tid == 0) {
-        mbar_init(bars, 1);
-        mbar_init(bars + 8, 1);
+        for (int b = 0; b < 2; b++) {
+            mbar_init(RF(b), 1);
+            mbar_init(RE(b), kFmCvtWarps);
+            mbar_init(PF(b), kFmCvtWarps);
+            mbar_init(PE(b), kFmMmaWarps);
+            mbar_init(OF(b), kFmMmaWarps);
+            mbar_init(OE(b), kFmCvtWarps);
+        }
         mbar_fence_init();
     }
-    for (int i = tid; i < 64; i += kFmThreads) planes[kFmRT * G::P + i] = 0u;   // zero pad after the last row
     __syncthreads();
 
-    auto issue = [&](i64 tile, int buf) {
-        // raw span of the tile: frames [tile*RT*S - CENTER - AL, +RAW_BYTES/4), 16-byte aligned at both ends
-        const unsigned char* src = a.in + ((i64)tile * kFmRT * G::S - G::CENTER - G::AL) * 4;
-        const saddr_t bar = bars + 8u * buf;
-        mbar_expect_tx(bar, (unsigned)G::RAW_BYTES);
-        constexpr int PIECE = 16384;
-#pragma unroll 1
-        for (int off = 0; off < G::RAW_BYTES; off += PIECE) {
-            const int nb = (G::RAW_BYTES - off) < PIECE ? (G::RAW_BYTES - off) : PIECE;
-            bulk_load(smem_addr(raw0 + (size_t)buf * G::RAW_BYTES + off), src + off, (unsigned)nb, bar);
-        }
-    };
+    const i64 tile0 = a.tile_lo + blockIdx.x;
+    const i64 stride = gridDim.x;
 
-    i64 tile = a.tile_lo + blockIdx.x;
-    if (tid == 0 && tile < a.tile_hi) issue(tile, 0);
-    const int kb = G::kb(0) + (16 * warp * G::M) / G::L;   // == G::kb(warp)
-    int it = 0;
-    for (; tile < a.tile_hi; tile += gridDim.x, it++) {
-        const int buf = it & 1;
-        if (tid == 0 && tile + gridDim.x < a.tile_hi) issue(tile + gridDim.x, buf ^ 1);   // other buffer: its readers passed the last barrier
-        mbar_wait(bars + 8u * buf, (unsigned)((it >> 1) & 1));
-
-        // ---- 2. raw s16 stereo -> (hv | lo) f16 words, run-major rows ----
-        // item i = n * P + k (plane word) <-> raw frame n * S + k; a thread walks i = tid, tid + 320, ... and keeps
-        // (k, raw index) incrementally; four independent items per trip so the LDS -> ALU chains overlap
+    if (warp < kFmMmaWarps) {
+        // =================================== MMA warps: block b = warp ===================================
+        const int g = lane >> 2, t = lane & 3;
+        // constant operand: this warp's block of the filter bank, as B fragments (hi, lo) per k-step and 8-output half
+        uint2 breg[G::KS][2][2];
         {
-            const unsigned* raw = (const unsigned*)(raw0 + (size_t)buf * G::RAW_BYTES) + G::AL;
-            constexpr int ITEMS = kFmRT * G::P;
-            int k = tid, ri = tid;
-#pragma unroll 1
-            for (int i = tid; i < ITEMS; i += 4 * kFmThreads) {
-                unsigned rv[4];
+            const uint2* bt = a.btab + (size_t)warp * (G::KS * 2 * 2 * 32) + lane;
 #pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    rv[e] = (i + e * kFmThreads < ITEMS) ? raw[ri] : 0u;
-                    k += kFmThreads; ri += kFmThreads;
-                    if (k >= G::P) { k -= G::P; ri += G::S - G::P; }
-                }
+            for (int s = 0; s < G::KS; s++)
 #pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    // u = L + R + 65536 in [0, 131070]: u >> 7 = hv + 512, u & 127 = lo
-                    const unsigned u = (unsigned)__dp2a_lo((int)rv[e], 0x0101, 65536);
-                    const unsigned w = ((u & 127u) << 16) + ((u >> 7) + 0x64006400u);   // f16 bits (1024 + hv + 512 | 1024 + lo)
-                    if (i + e * kFmThreads < ITEMS) planes[i + e * kFmThreads] = hsub2_bits(w, 0x64006600u);   // minus (1536, 1024): exact
-                }
-            }
+                for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+                    for (int term = 0; term < 2; term++)
+                        breg[s][nt][term] = G::needed(s, nt) ? bt[((s * 2 + nt) * 2 + term) * 32] : make_uint2(0u, 0u);
         }
-        __syncthreads();
-
-        // ---- 3. tensor-core product, quantise, stage ----
-#pragma unroll 1
-        for (int mt = 0; mt < kFmRT / 16; mt++) {
+        const int kbw = ((16 * warp * G::M) / G::L) / 2;            // window start of this block, in plane words
+        const int frag_off = g * G::PW + kbw + 2 * t;               // row g, frames kb + 4t ..
+        const int col = 16 * warp + 2 * t;
+        int it = 0;
+        for (i64 tile = tile0; tile < a.tile_hi; tile += stride, it++) {
+            const int b = it & 1;
+            const unsigned ph = (unsigned)((it >> 1) & 1);
+            const unsigned* phv = planes0 + (size_t)b * (2 * G::PLANE_WORDS) + frag_off;
+            const unsigned* plo = phv + G::PLANE_WORDS;
             float d12[2][4], d34[2][4];
 #pragma unroll
             for (int nt = 0; nt < 2; nt++)
 #pragma unroll
                 for (int e = 0; e < 4; e++) { d12[nt][e] = 0.f; d34[nt][e] = 0.f; }
-            fir_mma_block<IN_RATE>(planes + (size_t)(16 * mt) * G::P, kb, g, t, breg, d12, d34);
+            mbar_wait(PF(b), ph);
+            fir_mma_block<IN_RATE>(phv, plo, breg, d12, d34);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(PE(b));                      // planes[b] may be refilled
+            mbar_wait(OE(b), ph ^ 1u);                              // staging tile b drained (passes on first use)
+            int16_t* ot = otile0 + (size_t)b * (kFmRT * kFmOutPitch);
 #pragma unroll
             for (int nt = 0; nt < 2; nt++) {
                 // d[0],d[1]: run g, outputs 2t, 2t+1 of this 8-output half; d[2],d[3]: run g + 8
@@ -283,20 +272,34 @@ __global__ void __launch_bounds__(kFmThreads, 1) fir_mma_kernel(const FirMmaArgs
                 const int q1 = quant_s16(fmaf(d12[nt][1], sc12, d34[nt][1] * sc34));
                 const int q2 = quant_s16(fmaf(d12[nt][2], sc12, d34[nt][2] * sc34));
                 const int q3 = quant_s16(fmaf(d12[nt][3], sc12, d34[nt][3] * sc34));
-                const int col = 16 * warp + 8 * nt + 2 * t;
-                *(unsigned*)(otile + (16 * mt + g) * kFmOutPitch + col) = (unsigned)(q0 & 0xffff) | ((unsigned)q1 << 16);
-                *(unsigned*)(otile + (16 * mt + g + 8) * kFmOutPitch + col) = (unsigned)(q2 & 0xffff) | ((unsigned)q3 << 16);
+                *(unsigned*)(ot + g * kFmOutPitch + col + 8 * nt) = (unsigned)(q0 & 0xffff) | ((unsigned)q1 << 16);
+                *(unsigned*)(ot + (g + 8) * kFmOutPitch + col + 8 * nt) = (unsigned)(q2 & 0xffff) | ((unsigned)q3 << 16);
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(OF(b));
         }
-        __syncthreads();
-
-        // ---- 4. coalesced copy-out + per-millisecond energy of the quantised samples ----
-        {
+    } else {
+        // ============================ converter / copy-out warps (and the TMA issuer) ============================
+        const int ctid = tid - kFmMmaWarps * 32;
+        auto issue = [&](i64 tile, int b) {
+            // raw span of the tile: frames [tile*RT*S - CENTER - AL, +RAW_BYTES/4), 16-byte aligned at both ends
+            const unsigned char* src = a.in + ((i64)tile * kFmRT * G::S - G::CENTER - G::AL) * 4;
+            mbar_expect_tx(RF(b), (unsigned)G::RAW_BYTES);
+            constexpr int PIECE = 16384;
+#pragma unroll 1
+            for (int off = 0; off < G::RAW_BYTES; off += PIECE) {
+                const int nb = (G::RAW_BYTES - off) < PIECE ? (G::RAW_BYTES - off) : PIECE;
+                bulk_load(smem_addr(raw0 + (size_t)b * G::RAW_BYTES + off), src + off, (unsigned)nb, RF(b));
+            }
+        };
+        // copy-out of one staged tile: coalesced 16-byte stores + per-millisecond energy of the quantised samples
+        auto copy_out = [&](i64 tile, int b) {
+            const int16_t* ot = otile0 + (size_t)b * (kFmRT * kFmOutPitch);
             const i64 m_tile = (i64)tile * kFmRT * kFmNout;
 #pragma unroll
-            for (int id = tid; id < kFmRT * (kFmNout / 8); id += kFmThreads) {   // 640 = 2 per thread: full warps
+            for (int id = ctid; id < kFmRT * (kFmNout / 8); id += kFmCvtThreads) {   // 320 items: whole warps in every trip
                 const int n = id / (kFmNout / 8), c = id - n * (kFmNout / 8);
-                const uint4 v = *(const uint4*)(otile + n * kFmOutPitch + 8 * c);
+                const uint4 v = *(const uint4*)(ot + n * kFmOutPitch + 8 * c);
                 const i64 m = m_tile + (i64)n * kFmNout + 8 * c;
                 if (a.out_s16) *(uint4*)(a.out_s16 + m) = v;
                 const unsigned w[4] = {v.x, v.y, v.z, v.w};
@@ -306,12 +309,82 @@ __global__ void __launch_bounds__(kFmThreads, 1) fir_mma_kernel(const FirMmaArgs
                     const int s0 = (int)(short)(w[j] & 0xffff), s1 = (int)(short)(w[j] >> 16);
                     e += (u64)(unsigned)(s0 * s0) + (u64)(unsigned)(s1 * s1);
                 }
-                e += __shfl_xor_sync(0xffffffffu, e, 1);                         // the other half of the millisecond
+                e += __shfl_xor_sync(0xffffffffu, e, 1);                             // the other half of the millisecond
                 if (a.energy && (c & 1) == 0) a.energy[m >> 4] = e;
             }
+        };
+        static_assert((kFmRT * (kFmNout / 8)) % 32 == 0 && kFmCvtThreads % 32 == 0, "copy-out trips must be whole warps");
+
+        if (ctid == 0) {
+            if (tile0 < a.tile_hi) issue(tile0, 0);
+            if (tile0 + stride < a.tile_hi) issue(tile0 + stride, 1);
         }
-        // the next iteration's conversion only writes `planes` (all MMA reads are behind the barrier above) and its
-        // staging writes come after its own first barrier, i.e. after every thread finished this copy-out
+        int it = 0;
+        i64 tile = tile0;
+        for (; tile < a.tile_hi; tile += stride, it++) {
+            const int b = it & 1;
+            const unsigned ph = (unsigned)((it >> 1) & 1);
+            mbar_wait(RF(b), ph);                                   // raw frames landed
+            mbar_wait(PE(b), ph ^ 1u);                              // planes[b] released by the MMA warps (passes on first use)
+            // ---- raw s16 stereo -> hv / lo f16 planes.  pair q = tid + 192 j of the tile <-> row n = q / PAIRS_ROW,
+            //      columns 2kp, 2kp+1 (kp = q % PAIRS_ROW); for a fixed trip j the row is n0(j) or n0(j)+1.
+            {
+                const unsigned* rawt = (const unsigned*)(raw0 + (size_t)b * G::RAW_BYTES) + G::AL + 2 * ctid;
+                unsigned* plt = planes0 + (size_t)b * (2 * G::PLANE_WORDS) + ctid;
+#pragma unroll
+                for (int j0 = 0; j0 < G::CVT_TRIPS; j0 += 4) {
+                    unsigned r0[4], r1[4];
+                    int po[4];
+                    bool ok[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const int j = j0 + e;
+                        const int qbase = kFmCvtThreads * j;                           // q = qbase + ctid
+                        const int n0 = qbase / G::PAIRS_ROW;
+                        const int thr = (n0 + 1) * G::PAIRS_ROW - qbase;               // ctid >= thr  <=>  row n0 + 1
+                        const bool up = ctid >= thr;
+                        ok[e] = j < G::CVT_TRIPS && (qbase + ctid) < G::PAIRS;
+                        // raw frame index = n*S + 2*kp = 2q + n*(S - 2*PAIRS_ROW);  plane word = n*PW + kp = q + n*(PW - PAIRS_ROW)
+                        const int ro = 2 * qbase + (n0 + (up ? 1 : 0)) * (G::S - 2 * G::PAIRS_ROW);
+                        po[e] = qbase + (n0 + (up ? 1 : 0)) * (G::PW - G::PAIRS_ROW);
+                        r0[e] = ok[e] ? rawt[ro] : 0u;
+                        r1[e] = ok[e] ? rawt[ro + 1] : 0u;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        // u = L + R + 65536 in [0, 131070]: u >> 7 = hv + 512, u & 127 = lo
+                        const unsigned u0 = (unsigned)__dp2a_lo((int)r0[e], 0x0101, 65536);
+                        const unsigned u1 = (unsigned)__dp2a_lo((int)r1[e], 0x0101, 65536);
+                        const unsigned whv = ((u1 >> 7) << 16) + ((u0 >> 7) + 0x64006400u);       // f16 bits of 1024 + hv + 512
+                        const unsigned wlo = ((u1 & 127u) << 16) + ((u0 & 127u) + 0x64006400u);   // f16 bits of 1024 + lo
+                        if (ok[e]) {
+                            plt[po[e]] = hsub2_bits(whv, 0x66006600u);                            // minus 1536: exact integers
+                            plt[po[e] + G::PLANE_WORDS] = hsub2_bits(wlo, 0x64006400u);           // minus 1024
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(PF(b)); mbar_arrive(RE(b)); }
+            // refill raw[b] with the tile two steps ahead once every converter warp has released it
+            if (ctid == 0 && tile + 2 * stride < a.tile_hi) {
+                mbar_wait(RE(b), ph);
+                issue(tile + 2 * stride, b);
+            }
+            // copy-out of the previous tile (its MMAs ran while this tile was being converted)
+            if (it >= 1) {
+                const int pb = (it - 1) & 1;
+                mbar_wait(OF(pb), (unsigned)(((it - 1) >> 1) & 1));
+                copy_out(tile - stride, pb);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(OE(pb));
+            }
+        }
+        if (it >= 1) {
+            const int pb = (it - 1) & 1;
+            mbar_wait(OF(pb), (unsigned)(((it - 1) >> 1) & 1));
+            copy_out(tile - stride, pb);
+        }
     }
 }
 
@@ -326,10 +399,12 @@ template <int IN_RATE>
 static inline int fir_mma_launch(const void* d_in, i64 n_in, int16_t* d_out_s16, u64* d_energy, FirMmaPlan* plan, cudaStream_t stream) {
     using G = FirMmaGeom<IN_RATE>;
     plan->out_lo = plan->out_hi = 0;
-    // tile t reads frames [t*RT*S - CENTER - AL, that + RAW_BYTES/4): t >= 1 keeps the start inside the clip
+    // tile t reads frames [t*RT*S - CENTER - AL, that + RAW_BYTES/4): t >= 1 keeps the start inside the clip; the first
+    // 16 runs (reflect head) and the tail go to the table-driven kernel
+    const i64 tile_lo = 1;
     const i64 span_end = (i64)G::RAW_BYTES / 4 - G::CENTER - G::AL;          // relative to the tile's first run start
     const i64 tile_hi = (n_in - span_end) >= 0 ? (n_in - span_end) / ((i64)kFmRT * G::S) + 1 : 0;   // exclusive
-    if (tile_hi <= 1) return 0;
+    if (tile_hi <= tile_lo) return 0;
     const uint2* tab = get_fir_mma_table(IN_RATE);
     if (!tab) return B2A_ECUDA;
     auto k = fir_mma_kernel<IN_RATE>;
@@ -341,12 +416,16 @@ static inline int fir_mma_launch(const void* d_in, i64 n_in, int16_t* d_out_s16,
     }
     FirMmaArgs a;
     a.in = (const unsigned char*)d_in; a.out_s16 = d_out_s16; a.energy = d_energy; a.btab = tab;
-    a.tile_lo = 1; a.tile_hi = tile_hi;
-    const i64 tiles = tile_hi - 1;
-    const unsigned grid = (unsigned)(tiles < 148 ? tiles : 148);             // persistent: one CTA per SM
+    a.tile_lo = tile_lo; a.tile_hi = tile_hi;
+    const i64 tiles = tile_hi - tile_lo;
+    unsigned grid = (unsigned)(tiles < 148 ? tiles : 148);                   // persistent: one CTA per SM
+    if (const char* gs = getenv("B2A_FIR_GRID")) {                           // test knob: few CTAs => many tiles per CTA
+        const int gv = atoi(gs);
+        if (gv > 0 && (unsigned)gv < grid) grid = (unsigned)gv;
+    }
     B2A_LAUNCH(k, grid, kFmThreads, G::SMEM_BYTES, stream, a);
     B2A_CHECK_LAUNCH("fir_mma_kernel");
-    plan->out_lo = (i64)kFmRT * kFmNout;
+    plan->out_lo = tile_lo * kFmRT * kFmNout;
     plan->out_hi = tile_hi * kFmRT * kFmNout;
     return 1;
 }

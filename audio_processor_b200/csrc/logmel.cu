@@ -412,27 +412,27 @@ __global__ void __launch_bounds__(LM_THREADS, 2) stft_mel_kernel(LogMelParams p)
 }
 
 // K5: out = max(out, ((gmax - 8) + 4) / 4) in place; tiles whose minimum already clears the floor are skipped.
+// One warp per 32-frame tile (lane = frame): the skip test is a single broadcast load per warp.
 __global__ void __launch_bounds__(256) mel_floor_kernel(LogMelParams p) {
     i64 n_act = p.n;
     if (p.d_n) { n_act = *p.d_n; if (n_act > p.n) n_act = p.n; if (n_act < 0) n_act = 0; }
     const i64 T = (n_act + p.padding) / kHop;
     const i64 tiles = (T + LM_FRAMES - 1) / LM_FRAMES;
     const int n_mels = p.n_mels;
-    for (i64 work = blockIdx.x; work < tiles * p.batch; work += gridDim.x) {
+    const int lane = threadIdx.x & 31;
+    const i64 warps = (i64)gridDim.x * (blockDim.x >> 5);
+    for (i64 work = (i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); work < tiles * p.batch; work += warps) {
         const int b = (int)(work / tiles);
-        const i64 tile = work % tiles;
+        const i64 tile = work - (i64)b * tiles;
         const float gmax = key_to_float(p.gmax_key[p.per_clip ? b : 0]);
         const float floor_v = ((gmax - 8.0f) + 4.0f) * 0.25f;
         if (p.tile_min[(size_t)b * (size_t)p.tiles_cap + (size_t)tile] >= floor_v) continue;
-        const i64 t0 = tile * LM_FRAMES;
-        float* outb = p.out + (size_t)b * (size_t)n_mels * (size_t)T;
-        for (int e = threadIdx.x; e < n_mels * LM_FRAMES; e += blockDim.x) {
-            const int m = e / LM_FRAMES, f = e % LM_FRAMES;
-            if (t0 + f < T) {
-                float* q = outb + (size_t)m * (size_t)T + t0 + f;
-                float v = *q;
-                if (v < floor_v) *q = floor_v;
-            }
+        const i64 t = tile * LM_FRAMES + lane;
+        if (t >= T) continue;
+        float* q = p.out + (size_t)b * (size_t)n_mels * (size_t)T + t;
+        for (int m = 0; m < n_mels; m++, q += T) {
+            const float v = *q;
+            if (v < floor_v) *q = floor_v;
         }
     }
 }
@@ -493,7 +493,7 @@ int logmel_launch(const void* d_audio, int fmt, i64 batch, i64 n, i64 row_stride
     i64 grid = work < 148 * 2 ? work : 148 * 2;   // persistent: 2 CTAs per SM (shared-memory bound)
     B2A_LAUNCH(k4, (unsigned)grid, LM_THREADS, smem, stream, p);
     B2A_CHECK_LAUNCH("stft_mel_kernel");
-    i64 grid5 = work < 148 * 8 ? work : 148 * 8;
+    i64 grid5 = (work + 7) / 8 < 148 * 8 ? (work + 7) / 8 : 148 * 8;     // 8 warps per block, one tile per warp
     auto k5 = mel_floor_kernel;
     B2A_LAUNCH(k5, (unsigned)grid5, 256, 0, stream, p);
     B2A_CHECK_LAUNCH("mel_floor_kernel");
