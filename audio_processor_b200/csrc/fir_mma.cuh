@@ -30,13 +30,14 @@
 //
 // Kernel: persistent CTA per SM, 16 warps in two roles that run concurrently on different pipes, coupled only by
 // mbarriers (no block-wide barrier in the loop); tile = 16 runs, every buffer double buffered:
-//   converter warps (6): wait for the tile's raw frames (one contiguous span fetched by 1-D bulk TMA, issued two
+//   converter warps (6): wait for the tile's raw frames (one contiguous span fetched by 1-D bulk TMA, issued four
 //       tiles ahead), split every frame into (hv, lo) f16 and write the two planes (run-major rows, pitch P with
-//       P/2 = 8 or 24 mod 32 words: conflict-free 8-byte fragment loads); then copy the PREVIOUS tile's quantised
-//       outputs from the staging tile to global memory with coalesced 16-byte stores, accumulating the
-//       per-millisecond sum of squares (uint64) that the silence detector consumes.
+//       P/2 = 8 or 24 mod 32 words: conflict-free 8-byte fragment loads).
 //   MMA warps (10): wait for the planes, run the k-steps (all-zero tap k-steps skipped at compile time), round
-//       half-to-even + clip to s16 (swr audioconvert) into the staging tile.
+//       half-to-even + clip to s16 (swr audioconvert) and store straight from the accumulator fragments: a lane
+//       holds 2 consecutive outputs of a run, the two 8-output halves of a block fill one 32-byte sector, and a
+//       block of 16 outputs is exactly one millisecond, so the per-millisecond sum of squares (uint64) that the
+//       silence detector consumes is two shuffles away.
 #pragma once
 #include <cstdlib>
 
@@ -52,11 +53,12 @@ constexpr int kFmNout = 160;            // outputs per run (10 ms)
 constexpr int kFmBlocks = 10;           // 16-output blocks per run
 constexpr int kFmRT = 16;               // runs per tile (= MMA M)
 constexpr int kFmMmaWarps = 10;         // MMA warp b owns block b
-constexpr int kFmCvtWarps = 6;          // converter / copy-out warps
+constexpr int kFmCvtWarps = 6;          // converter warps
 constexpr int kFmCvtThreads = kFmCvtWarps * 32;
 constexpr int kFmThreads = (kFmMmaWarps + kFmCvtWarps) * 32;
-constexpr int kFmOutPitch = 168;        // staging-tile row pitch in samples (84 words: conflict-free fragment stores)
 constexpr int kFmTapShift = 12;         // taps are scaled by 2^12 before the f16 split
+constexpr int kFmRawBufs = 4;           // raw-tile ring: TMA loads are issued this many tiles ahead
+constexpr int kCvtIlp = 8;              // frame pairs in flight per converter thread
 constexpr int kFmBarBytes = 16;         // one mbarrier slot (8 bytes on the GPU; the emulation keeps counters in 16)
 
 template <int IN_RATE>
@@ -74,9 +76,8 @@ struct FirMmaGeom {
     static constexpr int RAW_BYTES = ((AL + RAWF) * 4 + 15) / 16 * 16;
     static constexpr int PLANE_WORDS = kFmRT * PW;                  // one plane (hv or lo) of one tile
     static constexpr int PLANES_BYTES = 2 * PLANE_WORDS * 4;        // hv + lo
-    static constexpr int OUT_BYTES = kFmRT * kFmOutPitch * 2;
-    static constexpr int NBARS = 12;
-    static constexpr int SMEM_BYTES = 2 * RAW_BYTES + 2 * PLANES_BYTES + 2 * OUT_BYTES + NBARS * kFmBarBytes;
+    static constexpr int NBARS = 2 * kFmRawBufs + 4;
+    static constexpr int SMEM_BYTES = kFmRawBufs * RAW_BYTES + 2 * PLANES_BYTES + NBARS * kFmBarBytes;
     static constexpr int PAIRS_ROW = PC / 2;                        // frame pairs converted per row
     static constexpr int PAIRS = kFmRT * PAIRS_ROW;
     static constexpr int CVT_TRIPS = (PAIRS + kFmCvtThreads - 1) / kFmCvtThreads;
@@ -185,14 +186,16 @@ __device__ __forceinline__ void fir_mma_block(const unsigned* __restrict__ phv, 
         const uint2 l1 = *(const uint2*)(plo + 8 * s + 8 * G::PW);
         const unsigned ahv[4] = {h0.x, h1.x, h0.y, h1.y};
         const unsigned alo[4] = {l0.x, l1.x, l0.y, l1.y};
+        // issue order: both 8-output halves of the T_hi term, then of the T_lo term, so that two HMMAs on the same
+        // accumulator are four instructions apart (the legacy HMMA result latency is several issue slots)
 #pragma unroll
-        for (int nt = 0; nt < 2; nt++) {
-            if (!G::needed(s, nt)) continue;          // all-zero taps for every block: compile-time skip
-            mma_16816(d12[nt], ahv, breg[s][nt][0].x, breg[s][nt][0].y);
-            mma_16816(d34[nt], alo, breg[s][nt][0].x, breg[s][nt][0].y);
-            mma_16816(d12[nt], ahv, breg[s][nt][1].x, breg[s][nt][1].y);
-            mma_16816(d34[nt], alo, breg[s][nt][1].x, breg[s][nt][1].y);
-        }
+        for (int term = 0; term < 2; term++)
+#pragma unroll
+            for (int nt = 0; nt < 2; nt++) {
+                if (!G::needed(s, nt)) continue;      // all-zero taps for every block: compile-time skip
+                mma_16816(d12[nt], ahv, breg[s][nt][term].x, breg[s][nt][term].y);
+                mma_16816(d34[nt], alo, breg[s][nt][term].x, breg[s][nt][term].y);
+            }
     }
 }
 
@@ -200,27 +203,24 @@ template <int IN_RATE>
 __global__ void __launch_bounds__(kFmThreads, 1) fir_mma_kernel(const FirMmaArgs a) {
     using G = FirMmaGeom<IN_RATE>;
     B2A_DYN_SMEM(smem);
-    unsigned char* raw0 = smem;                                                  // [2][RAW_BYTES]
-    unsigned* planes0 = (unsigned*)(smem + 2 * G::RAW_BYTES);                    // [2][hv plane | lo plane]
-    int16_t* otile0 = (int16_t*)(smem + 2 * G::RAW_BYTES + 2 * G::PLANES_BYTES); // [2][RT][kFmOutPitch]
-    const saddr_t bars = smem_addr(smem + 2 * G::RAW_BYTES + 2 * G::PLANES_BYTES + 2 * G::OUT_BYTES);
-    // barrier slots: RF raw full (TMA), RE raw empty, PF planes full, PE planes empty, OF staging full, OE staging empty
+    unsigned char* raw0 = smem;                                                  // [kFmRawBufs][RAW_BYTES]
+    unsigned* planes0 = (unsigned*)(smem + kFmRawBufs * G::RAW_BYTES);           // [2][hv plane | lo plane]
+    const saddr_t bars = smem_addr(smem + kFmRawBufs * G::RAW_BYTES + 2 * G::PLANES_BYTES);
+    // barrier slots: RF raw full (TMA), RE raw empty, PF planes full, PE planes empty
     auto RF = [&](int b) { return bars + (unsigned)((0 + b) * kFmBarBytes); };
-    auto RE = [&](int b) { return bars + (unsigned)((2 + b) * kFmBarBytes); };
-    auto PF = [&](int b) { return bars + (unsigned)((4 + b) * kFmBarBytes); };
-    auto PE = [&](int b) { return bars + (unsigned)((6 + b) * kFmBarBytes); };
-    auto OF = [&](int b) { return bars + (unsigned)((8 + b) * kFmBarBytes); };
-    auto OE = [&](int b) { return bars + (unsigned)((10 + b) * kFmBarBytes); };
+    auto RE = [&](int b) { return bars + (unsigned)((kFmRawBufs + b) * kFmBarBytes); };
+    auto PF = [&](int b) { return bars + (unsigned)((2 * kFmRawBufs + b) * kFmBarBytes); };
+    auto PE = [&](int b) { return bars + (unsigned)((2 * kFmRawBufs + 2 + b) * kFmBarBytes); };
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int b = 0; b < 2; b++) {
+        for (int b = 0; b < kFmRawBufs; b++) {
             mbar_init(RF(b), 1);
             mbar_init(RE(b), kFmCvtWarps);
+        }
+        for (int b = 0; b < 2; b++) {
             mbar_init(PF(b), kFmCvtWarps);
             mbar_init(PE(b), kFmMmaWarps);
-            mbar_init(OF(b), kFmMmaWarps);
-            mbar_init(OE(b), kFmCvtWarps);
         }
         mbar_fence_init();
     }
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kFmThreads, 1) fir_mma_kernel(const FirMmaArgs
         }
         const int kbw = ((16 * warp * G::M) / G::L) / 2;            // window start of this block, in plane words
         const int frag_off = g * G::PW + kbw + 2 * t;               // row g, frames kb + 4t ..
-        const int col = 16 * warp + 2 * t;
+        const int col = 16 * warp + 2 * t;                          // first output column this lane owns
         int it = 0;
         for (i64 tile = tile0; tile < a.tile_hi; tile += stride, it++) {
             const int b = it & 1;
@@ -262,24 +262,36 @@ __global__ void __launch_bounds__(kFmThreads, 1) fir_mma_kernel(const FirMmaArgs
             fir_mma_block<IN_RATE>(phv, plo, breg, d12, d34);
             __syncwarp();
             if (lane == 0) mbar_arrive(PE(b));                      // planes[b] may be refilled
-            mbar_wait(OE(b), ph ^ 1u);                              // staging tile b drained (passes on first use)
-            int16_t* ot = otile0 + (size_t)b * (kFmRT * kFmOutPitch);
+            // ---- epilogue: d[0],d[1] = run g, outputs 2t, 2t+1 of an 8-output half; d[2],d[3] = run g + 8 ----
+            const i64 m_run = ((i64)tile * kFmRT + g) * kFmNout + col;          // first output this lane owns in run g
+            u64 e_lo = 0, e_hi = 0;                                              // sum of squares of this lane's outputs (runs g, g+8)
 #pragma unroll
             for (int nt = 0; nt < 2; nt++) {
-                // d[0],d[1]: run g, outputs 2t, 2t+1 of this 8-output half; d[2],d[3]: run g + 8
                 const float sc12 = 1.0f / 64.0f, sc34 = 1.0f / 8192.0f;
                 const int q0 = quant_s16(fmaf(d12[nt][0], sc12, d34[nt][0] * sc34));
                 const int q1 = quant_s16(fmaf(d12[nt][1], sc12, d34[nt][1] * sc34));
                 const int q2 = quant_s16(fmaf(d12[nt][2], sc12, d34[nt][2] * sc34));
                 const int q3 = quant_s16(fmaf(d12[nt][3], sc12, d34[nt][3] * sc34));
-                *(unsigned*)(ot + g * kFmOutPitch + col + 8 * nt) = (unsigned)(q0 & 0xffff) | ((unsigned)q1 << 16);
-                *(unsigned*)(ot + (g + 8) * kFmOutPitch + col + 8 * nt) = (unsigned)(q2 & 0xffff) | ((unsigned)q3 << 16);
+                if (a.out_s16) {
+                    *(unsigned*)(a.out_s16 + m_run + 8 * nt) = (unsigned)(q0 & 0xffff) | ((unsigned)q1 << 16);
+                    *(unsigned*)(a.out_s16 + m_run + 8 * kFmNout + 8 * nt) = (unsigned)(q2 & 0xffff) | ((unsigned)q3 << 16);
+                }
+                e_lo += (u64)(unsigned)(q0 * q0) + (u64)(unsigned)(q1 * q1);
+                e_hi += (u64)(unsigned)(q2 * q2) + (u64)(unsigned)(q3 * q3);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(OF(b));
+            // the 16 outputs of (run, block) are one millisecond: reduce over the 4 lanes t = 0..3 that share a run
+            e_lo += __shfl_xor_sync(0xffffffffu, e_lo, 1);
+            e_hi += __shfl_xor_sync(0xffffffffu, e_hi, 1);
+            e_lo += __shfl_xor_sync(0xffffffffu, e_lo, 2);
+            e_hi += __shfl_xor_sync(0xffffffffu, e_hi, 2);
+            if (a.energy && t == 0) {
+                const i64 ms = ((i64)tile * kFmRT + g) * kFmBlocks + warp;
+                a.energy[ms] = e_lo;
+                a.energy[ms + 8 * kFmBlocks] = e_hi;
+            }
         }
     } else {
-        // ============================ converter / copy-out warps (and the TMA issuer) ============================
+        // ============================ converter warps (and the TMA issuer) ============================
         const int ctid = tid - kFmMmaWarps * 32;
         auto issue = [&](i64 tile, int b) {
             // raw span of the tile: frames [tile*RT*S - CENTER - AL, +RAW_BYTES/4), 16-byte aligned at both ends
@@ -292,52 +304,31 @@ __global__ void __launch_bounds__(kFmThreads, 1) fir_mma_kernel(const FirMmaArgs
                 bulk_load(smem_addr(raw0 + (size_t)b * G::RAW_BYTES + off), src + off, (unsigned)nb, RF(b));
             }
         };
-        // copy-out of one staged tile: coalesced 16-byte stores + per-millisecond energy of the quantised samples
-        auto copy_out = [&](i64 tile, int b) {
-            const int16_t* ot = otile0 + (size_t)b * (kFmRT * kFmOutPitch);
-            const i64 m_tile = (i64)tile * kFmRT * kFmNout;
-#pragma unroll
-            for (int id = ctid; id < kFmRT * (kFmNout / 8); id += kFmCvtThreads) {   // 320 items: whole warps in every trip
-                const int n = id / (kFmNout / 8), c = id - n * (kFmNout / 8);
-                const uint4 v = *(const uint4*)(ot + n * kFmOutPitch + 8 * c);
-                const i64 m = m_tile + (i64)n * kFmNout + 8 * c;
-                if (a.out_s16) *(uint4*)(a.out_s16 + m) = v;
-                const unsigned w[4] = {v.x, v.y, v.z, v.w};
-                u64 e = 0;
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int s0 = (int)(short)(w[j] & 0xffff), s1 = (int)(short)(w[j] >> 16);
-                    e += (u64)(unsigned)(s0 * s0) + (u64)(unsigned)(s1 * s1);
-                }
-                e += __shfl_xor_sync(0xffffffffu, e, 1);                             // the other half of the millisecond
-                if (a.energy && (c & 1) == 0) a.energy[m >> 4] = e;
-            }
-        };
-        static_assert((kFmRT * (kFmNout / 8)) % 32 == 0 && kFmCvtThreads % 32 == 0, "copy-out trips must be whole warps");
-
         if (ctid == 0) {
-            if (tile0 < a.tile_hi) issue(tile0, 0);
-            if (tile0 + stride < a.tile_hi) issue(tile0 + stride, 1);
+            for (int r = 0; r < kFmRawBufs; r++)
+                if (tile0 + r * stride < a.tile_hi) issue(tile0 + r * stride, r);
         }
+        int rb = 0;                 // raw ring slot of this tile
+        unsigned rph = 0;           // its phase parity
         int it = 0;
         i64 tile = tile0;
         for (; tile < a.tile_hi; tile += stride, it++) {
             const int b = it & 1;
             const unsigned ph = (unsigned)((it >> 1) & 1);
-            mbar_wait(RF(b), ph);                                   // raw frames landed
+            mbar_wait(RF(rb), rph);                                 // raw frames landed
             mbar_wait(PE(b), ph ^ 1u);                              // planes[b] released by the MMA warps (passes on first use)
-            // ---- raw s16 stereo -> hv / lo f16 planes.  pair q = tid + 192 j of the tile <-> row n = q / PAIRS_ROW,
+            // ---- raw s16 stereo -> hv / lo f16 planes.  pair q = ctid + 192 j of the tile <-> row n = q / PAIRS_ROW,
             //      columns 2kp, 2kp+1 (kp = q % PAIRS_ROW); for a fixed trip j the row is n0(j) or n0(j)+1.
             {
-                const unsigned* rawt = (const unsigned*)(raw0 + (size_t)b * G::RAW_BYTES) + G::AL + 2 * ctid;
+                const unsigned* rawt = (const unsigned*)(raw0 + (size_t)rb * G::RAW_BYTES) + G::AL + 2 * ctid;
                 unsigned* plt = planes0 + (size_t)b * (2 * G::PLANE_WORDS) + ctid;
 #pragma unroll
-                for (int j0 = 0; j0 < G::CVT_TRIPS; j0 += 4) {
-                    unsigned r0[4], r1[4];
-                    int po[4];
-                    bool ok[4];
+                for (int j0 = 0; j0 < G::CVT_TRIPS; j0 += kCvtIlp) {
+                    unsigned r0[kCvtIlp], r1[kCvtIlp];
+                    int po[kCvtIlp];
+                    bool ok[kCvtIlp];
 #pragma unroll
-                    for (int e = 0; e < 4; e++) {
+                    for (int e = 0; e < kCvtIlp; e++) {
                         const int j = j0 + e;
                         const int qbase = kFmCvtThreads * j;                           // q = qbase + ctid
                         const int n0 = qbase / G::PAIRS_ROW;
@@ -351,7 +342,7 @@ __global__ void __launch_bounds__(kFmThreads, 1) fir_mma_kernel(const FirMmaArgs
                         r1[e] = ok[e] ? rawt[ro + 1] : 0u;
                     }
 #pragma unroll
-                    for (int e = 0; e < 4; e++) {
+                    for (int e = 0; e < kCvtIlp; e++) {
                         // u = L + R + 65536 in [0, 131070]: u >> 7 = hv + 512, u & 127 = lo
                         const unsigned u0 = (unsigned)__dp2a_lo((int)r0[e], 0x0101, 65536);
                         const unsigned u1 = (unsigned)__dp2a_lo((int)r1[e], 0x0101, 65536);
@@ -365,25 +356,13 @@ __global__ void __launch_bounds__(kFmThreads, 1) fir_mma_kernel(const FirMmaArgs
                 }
             }
             __syncwarp();
-            if (lane == 0) { mbar_arrive(PF(b)); mbar_arrive(RE(b)); }
-            // refill raw[b] with the tile two steps ahead once every converter warp has released it
-            if (ctid == 0 && tile + 2 * stride < a.tile_hi) {
-                mbar_wait(RE(b), ph);
-                issue(tile + 2 * stride, b);
+            if (lane == 0) { mbar_arrive(PF(b)); mbar_arrive(RE(rb)); }
+            // refill this ring slot with the tile kFmRawBufs steps ahead once every converter warp has released it
+            if (ctid == 0 && tile + kFmRawBufs * stride < a.tile_hi) {
+                mbar_wait(RE(rb), rph);
+                issue(tile + kFmRawBufs * stride, rb);
             }
-            // copy-out of the previous tile (its MMAs ran while this tile was being converted)
-            if (it >= 1) {
-                const int pb = (it - 1) & 1;
-                mbar_wait(OF(pb), (unsigned)(((it - 1) >> 1) & 1));
-                copy_out(tile - stride, pb);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(OE(pb));
-            }
-        }
-        if (it >= 1) {
-            const int pb = (it - 1) & 1;
-            mbar_wait(OF(pb), (unsigned)(((it - 1) >> 1) & 1));
-            copy_out(tile - stride, pb);
+            if (++rb == kFmRawBufs) { rb = 0; rph ^= 1u; }
         }
     }
 }

@@ -430,9 +430,13 @@ __global__ void __launch_bounds__(256) mel_floor_kernel(LogMelParams p) {
         const i64 t = tile * LM_FRAMES + lane;
         if (t >= T) continue;
         float* q = p.out + (size_t)b * (size_t)n_mels * (size_t)T + t;
-        for (int m = 0; m < n_mels; m++, q += T) {
-            const float v = *q;
-            if (v < floor_v) *q = floor_v;
+        for (int m0 = 0; m0 < n_mels; m0 += 8, q += 8 * T) {       // n_mels is 80 or 128: whole groups of 8 loads in flight
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) v[e] = q[(size_t)e * (size_t)T];
+#pragma unroll
+            for (int e = 0; e < 8; e++)
+                if (v[e] < floor_v) q[(size_t)e * (size_t)T] = floor_v;
         }
     }
 }
