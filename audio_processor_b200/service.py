@@ -17,7 +17,7 @@ from typing import List, Optional, Tuple, Union
 
 import numpy as np
 
-from . import ops, wavio, whisper_audio
+from . import _abi, ops, wavio, whisper_audio
 
 
 class AudioFrontend:
@@ -100,10 +100,95 @@ class AudioFrontend:
                      keep_silence=self.keep_silence, seek_step=self.seek_step)
         return r.pcm, r.mel, r.kept
 
+    def stream(self, n_in: int, in_rate: int, channels: int = 2, dtype=None, padding: int = 0, depth: int = 2) -> "ClipStream":
+        """pipelined submit()/result() front-end for many same-shaped clips (uploads overlap kernels and downloads)"""
+        return ClipStream(self, n_in, in_rate, channels, dtype, padding, depth)
+
     def _to_device(self, pcm):
         torch = ops.require_cuda()
         t = torch.from_numpy(np.ascontiguousarray(pcm)) if isinstance(pcm, np.ndarray) else pcm
         return t.to(self.device if self.device is not None else "cuda", non_blocking=True)
+
+
+class ClipStream:
+    """Pipelined host -> device -> host front-end for a stream of same-shaped clips (what a job worker pool feeds).
+
+    ``submit(host_pcm)`` enqueues the H2D copy, the whole device path and the D2H of the info block on dedicated
+    streams and returns a ticket at once; ``result(ticket)`` returns (trimmed int16 PCM, log-mel, kept ms ranges) as
+    views of pinned host buffers.  With ``depth`` clips in flight the upload of clip i+1 overlaps the kernels and the
+    download of clip i (PCIe is full duplex), so steady-state throughput is bounded by the larger transfer, not the sum.
+    Results stay valid until ``depth`` further clips have been submitted."""
+
+    def __init__(self, frontend: "AudioFrontend", n_in: int, in_rate: int, channels: int = 2, dtype=None, padding: int = 0,
+                 depth: int = 2):
+        torch = ops.require_cuda()
+        self.torch, self.fe, self.depth = torch, frontend, int(depth)
+        dtype = torch.int16 if dtype is None else dtype
+        dev = torch.device(frontend.device if frontend.device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.dev, self.in_rate = dev, int(in_rate)
+        shape = (int(n_in),) if channels == 1 else (int(n_in), int(channels))
+        self.s_h2d, self.s_run, self.s_info, self.s_d2h = (torch.cuda.Stream(device=dev) for _ in range(4))
+        self.slots = []
+        for _ in range(self.depth):
+            plan = ops.PipelinePlan(int(n_in), in_rate, channels, dtype, n_mels=frontend.n_mels, padding=padding, device=dev)
+            self.slots.append(dict(
+                plan=plan, dev_in=torch.empty(shape, dtype=dtype, device=dev),
+                h_info=torch.empty(_abi.INFO_LEN, dtype=torch.int64).pin_memory(),
+                h_pcm=torch.empty(plan.n16 + 64, dtype=torch.int16).pin_memory(),
+                h_mel=torch.empty(plan.n_mels * max(plan.t_cap, 1), dtype=torch.float32).pin_memory(),
+                h_kept=torch.empty((plan.cap, 2), dtype=torch.int32).pin_memory(),
+                ev_in=torch.cuda.Event(), ev_run=torch.cuda.Event(), ev_info=torch.cuda.Event(), ev_out=torch.cuda.Event(),
+                busy=False))
+        self.n_submitted = 0
+
+    def submit(self, host_pcm) -> int:
+        torch, fe = self.torch, self.fe
+        t = torch.from_numpy(np.ascontiguousarray(host_pcm)) if isinstance(host_pcm, np.ndarray) else host_pcm
+        ticket = self.n_submitted
+        sl = self.slots[ticket % self.depth]
+        if sl["busy"]:
+            raise RuntimeError("ClipStream: collect result(ticket) of the clip that used this slot before submitting more")
+        with torch.cuda.stream(self.s_h2d):
+            sl["dev_in"].copy_(t, non_blocking=True)
+            sl["ev_in"].record()
+        with torch.cuda.stream(self.s_run):
+            self.s_run.wait_event(sl["ev_in"])
+            sl["plan"].run(sl["dev_in"], trim=fe.strip_silence, min_silence_len=fe.min_silence_len,
+                           silence_thresh=fe.silence_thresh, keep_silence=fe.keep_silence, seek_step=fe.seek_step)
+            sl["ev_run"].record()
+        with torch.cuda.stream(self.s_info):          # own stream: a later clip's info copy must not queue ahead of this clip's download
+            self.s_info.wait_event(sl["ev_run"])
+            sl["h_info"].copy_(sl["plan"].info, non_blocking=True)
+            sl["ev_info"].record()
+        sl["busy"] = True
+        self.n_submitted += 1
+        return ticket
+
+    def result(self, ticket: int):
+        torch = self.torch
+        sl = self.slots[ticket % self.depth]
+        sl["ev_info"].synchronize()
+        info = sl["h_info"].tolist()
+        if info[_abi.INFO_OVERFLOW]:
+            raise RuntimeError(f"more than cap={sl['plan'].cap} silence ranges; raise `cap`")
+        n_keep, T, nk = int(info[_abi.INFO_N_KEEP]), int(info[_abi.INFO_N_FRAMES]), int(info[_abi.INFO_N_KEPT])
+        plan = sl["plan"]
+        with torch.cuda.stream(self.s_d2h):
+            sl["h_pcm"][:n_keep].copy_(plan.pcm[:n_keep], non_blocking=True)
+            sl["h_mel"][: plan.n_mels * T].copy_(plan.mel[: plan.n_mels * T], non_blocking=True)
+            sl["h_kept"][:nk].copy_(plan.kept[:nk], non_blocking=True)
+            sl["ev_out"].record()
+        sl["ev_out"].synchronize()
+        sl["busy"] = False
+        return sl["h_pcm"][:n_keep], sl["h_mel"][: plan.n_mels * T].view(plan.n_mels, T), sl["h_kept"][:nk].tolist()
+
+    def bytes_per_clip(self, ticket: int):
+        """(h2d, d2h) bytes moved for a collected ticket — for benchmarks"""
+        sl = self.slots[ticket % self.depth]
+        info = sl["h_info"].tolist()
+        plan = sl["plan"]
+        return (sl["dev_in"].numel() * sl["dev_in"].element_size(),
+                8 * _abi.INFO_LEN + 2 * int(info[_abi.INFO_N_KEEP]) + 4 * plan.n_mels * int(info[_abi.INFO_N_FRAMES]) + 8 * int(info[_abi.INFO_N_KEPT]))
 
 
 def remap_time(t_trimmed_s: float, kept_ms: List[List[int]]) -> float:

@@ -383,32 +383,48 @@ def run_b200(args):
             hin = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in inputs]
             for h, t in zip(hin, inputs):
                 h.copy_(t)
-            n16cap = [p.n16 + 64 for p in plans]
-            hpcm = [torch.empty(c, dtype=torch.int16).pin_memory() for c in n16cap]
-            hmel = [torch.empty(n_mels * (c // 160 + 1), dtype=torch.float32).pin_memory() for c in n16cap]
+            # the public pipelined API: ClipStream.submit() uploads + runs, result() downloads trimmed PCM + mel + tables
+            # into pinned host buffers; depth 2 keeps the next upload in flight while the previous clip is collected
+            cs = fe.stream(int(inputs[0].shape[0]), in_rate, ch, inputs[0].dtype, padding=0, depth=2)
+            pending = []
 
             def e2e_step():
                 bi = bo = 0
-                for h, hp, hm in zip(hin, hpcm, hmel):
-                    pcm, mel, kept = fe.process_pcm(h, in_rate)           # H2D + kernels + D2H of the segment table
-                    hp[: pcm.numel()].copy_(pcm, non_blocking=True)
-                    hm[: mel.numel()].copy_(mel.reshape(-1), non_blocking=True)
-                    bi += h.numel() * 2
-                    bo += pcm.numel() * 2 + mel.numel() * 4 + 8 * len(kept) + 8 * _abi.INFO_LEN
-                torch.cuda.synchronize()
+                for h in hin:
+                    pending.append(cs.submit(h))
+                    if len(pending) > 1:
+                        tk = pending.pop(0)
+                        cs.result(tk)
+                        b1, b2 = cs.bytes_per_clip(tk)
+                        bi += b1; bo += b2
                 return bi, bo
+
+            last = {}
+
+            def e2e_drain():
+                while pending:
+                    tk = pending.pop(0)
+                    cs.result(tk)
+                    last["tk"] = tk
             e2e_audio_h = audio_h
         for _ in range(3):
             bi, bo = e2e_step()
+        if not logmel_only:
+            e2e_drain()                # the timed region starts with nothing in flight
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            bi, bo = e2e_step()
+            bi, bo = e2e_step()        # every step: one upload submitted and one finished clip downloaded per clip of the step
+        if not logmel_only:
+            e2e_drain()                # ... and the clips still in flight are collected inside the timed region
         barrier()
         dt_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        if not logmel_only:
+            b1, b2 = cs.bytes_per_clip(last["tk"])
+            bi, bo = b1 * len(hin), b2 * len(hin)
         e2e = {"value": sum_over_ranks(e2e_audio_h) * e2e_steps / (dt_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(bi),
                "d2h_bytes_per_step": int(bo), "ms_per_step": dt_ms / e2e_steps, "steps": e2e_steps,
-               "api": "whisper_audio.log_mel_spectrogram(host)" if logmel_only else "AudioFrontend.process_pcm(host pcm)"}
+               "api": "whisper_audio.log_mel_spectrogram(host)" if logmel_only else "AudioFrontend.stream(...).submit(host pcm) / result(): 2 clips in flight"}
     t_load1 = time.time()
     clocks = sampler.stop(t_load0, t_load1) if sampler else None
 

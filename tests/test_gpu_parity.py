@@ -321,3 +321,26 @@ def test_pipeline_full_hour_properties(ops, T):
     # the two floors differ (slice max vs whole-clip max): compare where neither side is clamped
     mask = (refm > refm.max() - 1.9) & (sub > float(mel.max()) - 1.9)
     assert mask.mean() > 0.5 and np.abs(sub - refm)[mask].max() <= MEL_TOL
+
+
+def test_clip_stream_pipelined_api(ops, T):
+    """ClipStream.submit()/result(): same results as the one-shot pipeline, with two clips in flight"""
+    from audio_processor_b200 import synth
+    from audio_processor_b200.service import AudioFrontend
+    fe = AudioFrontend(min_silence_len=1000, silence_thresh=-40, keep_silence=200)
+    clips = [synth.synth_clip(40 + i, 44100, 2, 12.0, 0.3, device="cpu") for i in range(4)]
+    cs = fe.stream(int(clips[0].shape[0]), 44100, 2, clips[0].dtype, depth=2)
+    got, pending = [], []
+    for c in clips:
+        pending.append(cs.submit(c.pin_memory()))
+        if len(pending) > 1:
+            pcm, mel, kept = cs.result(pending.pop(0))
+            got.append((pcm.clone(), mel.clone(), kept))
+    while pending:
+        pcm, mel, kept = cs.result(pending.pop(0))
+        got.append((pcm.clone(), mel.clone(), kept))
+    for c, (pcm, mel, kept) in zip(clips, got):
+        r = ops.pipeline(c.cuda(), 44100, n_mels=80, min_silence_len=1000, silence_thresh=-40, keep_silence=200)
+        assert kept == r.kept and T.equal(pcm, r.pcm.cpu()) and T.equal(mel, r.mel.cpu())
+    with pytest.raises(RuntimeError):
+        cs.submit(clips[0]); cs.submit(clips[1]); cs.submit(clips[2])      # third clip would overwrite an uncollected slot
