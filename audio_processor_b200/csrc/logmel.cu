@@ -188,20 +188,32 @@ static inline void cp_async_drain() {}
 constexpr int LM_PAIRS = LM_TILE / 2;                                   // 2680 sample pairs per tile
 constexpr int LM_PRE = (LM_PAIRS + LM_THREADS - 1) / LM_THREADS;        // 17 pairs per thread
 
-template <int NM>
-__global__ void __launch_bounds__(LM_THREADS, 2) stft_mel_kernel(LogMelParams p) {
+// shared-memory footprint: the s16 variant keeps the tile as raw sample pairs (half the bytes) and both variants put the
+// power spectra into the exchange buffer once it has been consumed => 67 KB (s16: 3 CTAs per SM) / 78 KB (f32: 2)
+template <int FMT> struct LmSmem {
+    static constexpr int TILE_WORDS = ((FMT == B2A_FMT_S16 ? (LM_TILE / 2 + (LM_TILE / kHop + 2)) : LM_TILE_WORDS) + 3) / 4 * 4;   // keeps the buffers behind it 16-byte aligned
+    static constexpr int HOPW = FMT == B2A_FMT_S16 ? (kHop / 2 + 1) : LM_HOPW;      // words between frames (81: odd, conflict free)
+    static constexpr int WORDS = TILE_WORDS + 2 * LM_FRAMES * LM_EXP + kNFFT + 2 * 200 + 2 * 202 + 8;
+    static constexpr int CTAS = FMT == B2A_FMT_S16 ? 3 : 2;
+};
+
+template <int NM, int FMT>
+__global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel(LogMelParams p) {
+    using SM = LmSmem<FMT>;
+    constexpr bool S16 = FMT == B2A_FMT_S16;
     B2A_DYN_SMEM(smem_raw);
-    float* s_tile = (float*)smem_raw;                                   // LM_TILE_WORDS
-    float2* s_ex = (float2*)(s_tile + LM_TILE_WORDS);                   // LM_FRAMES * LM_EXP complex
-    float* s_P = (float*)(s_ex + LM_FRAMES * LM_EXP);                   // LM_FRAMES * LM_PP
-    float* s_win = s_P + LM_FRAMES * LM_PP;                             // 400
+    float* s_tile = (float*)smem_raw;                                   // SM::TILE_WORDS (f32 samples, or s16 sample pairs)
+    unsigned* s_tile16 = (unsigned*)smem_raw;
+    float2* s_ex = (float2*)(s_tile + SM::TILE_WORDS);                  // LM_FRAMES * LM_EXP complex
+    float* s_P = (float*)s_ex;                                          // LM_FRAMES * LM_PP, reuses the exchange buffer
+    float* s_win = (float*)(s_ex + LM_FRAMES * LM_EXP);                 // 400
     float2* s_tw200 = (float2*)(s_win + kNFFT);                         // 200
     float2* s_tw400 = s_tw200 + 200;                                    // 201 (+1 pad)
     float* s_red = (float*)(s_tw400 + 202);                             // 8
 
     const int tid = threadIdx.x;
     const LogMelTables* tab = p.tab;
-    for (int i = tid; i < kNFFT; i += LM_THREADS) s_win[i] = tab->win[i];
+    for (int i = tid; i < kNFFT; i += LM_THREADS) s_win[i] = tab->win[i] * (S16 ? (1.0f / 32768.0f) : 1.0f);   // s16 tile holds raw integers
     for (int i = tid; i < 200; i += LM_THREADS) s_tw200[i] = tab->tw200[i];
     for (int i = tid; i < kNBins; i += LM_THREADS) s_tw400[i] = tab->tw400[i];
 
@@ -214,14 +226,15 @@ __global__ void __launch_bounds__(LM_THREADS, 2) stft_mel_kernel(LogMelParams p)
 
     const int u = tid >> 5, f = tid & 31;        // role (warp-uniform), frame within the tile
     const int k1a = u, k1b = (u == 0) ? 5 : 10 - u;
-    const float* ps = s_tile + LM_HOPW * f + 2 * u;          // + 40 n1 + 10 j + 2 (n1 / 4)
+    const float* ps = s_tile + LM_HOPW * f + 2 * u;          // f32 tile: + 40 n1 + 10 j + 2 (n1 / 4)
+    const unsigned* ps16 = s_tile16 + SM::HOPW * f + u;       // s16 tile (words = sample pairs): + 20 n1 + 5 j + (n1 / 4)
     const float* pw = s_win + 2 * u;                         // + 40 n1 + 10 j
     const float2* pt = s_tw200 + 10 * u;                     // + 50 j + k1
     float2* pex_w = s_ex + LM_EXP * f + u;                   // + 20 k1 + 5 j
     const float2* pex_a = s_ex + LM_EXP * f + 20 * k1a;      // + n2
     const float2* pex_b = s_ex + LM_EXP * f + 20 * k1b;
     float* pP = s_P + LM_PP * f;
-    const int elem = p.fmt == B2A_FMT_S16 ? 2 : 4;
+    const int elem = S16 ? 2 : 4;
 
     float run_max = -3.0e38f;
     i64 prev_slot = -1;                          // tile_min slot of the previous work item (written one barrier later)
@@ -236,7 +249,7 @@ __global__ void __launch_bounds__(LM_THREADS, 2) stft_mel_kernel(LogMelParams p)
         r.row = (const char*)p.audio + (size_t)b * (size_t)p.row_stride * elem;
         r.q0 = tile * (LM_FRAMES * kHop) - 200;
         const bool interior = r.q0 >= 0 && r.q0 + LM_TILE <= n_act && ((((uintptr_t)(r.row + r.q0 * elem)) & 7) == 0);
-        r.mode = interior ? (p.fmt == B2A_FMT_S16 ? 1 : 2) : 0;
+        r.mode = interior ? (S16 ? 1 : 2) : 0;
         return r;
     };
     // generic tile load: padded-domain index q = q0 + i, reflect at both ends, zeros past n_act
@@ -245,9 +258,15 @@ __global__ void __launch_bounds__(LM_THREADS, 2) stft_mel_kernel(LogMelParams p)
             i64 q = sc.q0 + i;
             if (q < 0) q = -q;
             if (q >= ltot) q = 2 * (ltot - 1) - q;
-            float v = 0.0f;
-            if (q >= 0 && q < n_act) v = load_sample(sc.row, p.fmt, q);
-            s_tile[i + LM_SKEW * (i / kHop)] = v;
+            if (S16) {
+                short v = 0;
+                if (q >= 0 && q < n_act) v = ((const short*)sc.row)[q];
+                ((short*)s_tile16)[i + 2 * (i / kHop)] = v;                     // one word of skew per hop
+            } else {
+                float v = 0.0f;
+                if (q >= 0 && q < n_act) v = ((const float*)sc.row)[q];
+                s_tile[i + LM_SKEW * (i / kHop)] = v;
+            }
         }
     };
     // pair pr (samples 2pr, 2pr+1) lives at word 2pr + LM_SKEW * (pr / 80) of the skewed tile
@@ -255,9 +274,7 @@ __global__ void __launch_bounds__(LM_THREADS, 2) stft_mel_kernel(LogMelParams p)
 #pragma unroll
         for (int i = 0; i < LM_PRE; i++) {
             const int pr = tid + LM_THREADS * i;
-            if (pr < LM_PAIRS)
-                *(float2*)(s_tile + 2 * pr + LM_SKEW * (pr / 80)) =
-                    make_float2((float)(short)(pre[i] & 0xffff) * (1.0f / 32768.0f), (float)(short)(pre[i] >> 16) * (1.0f / 32768.0f));
+            if (pr < LM_PAIRS) s_tile16[pr + pr / 80] = pre[i];                    // raw pair, converted where it is used
         }
     };
     auto fetch_s16_pairs = [&](const Src& sc, unsigned (&pre)[LM_PRE]) {
@@ -309,7 +326,13 @@ __global__ void __launch_bounds__(LM_THREADS, 2) stft_mel_kernel(LogMelParams p)
             cpx x[10], y[10];
 #pragma unroll
             for (int n1 = 0; n1 < 10; n1++) {
-                const float2 xv = *(const float2*)(ps + 10 * j + 40 * n1 + LM_SKEW * (n1 / 4));
+                float2 xv;
+                if (S16) {
+                    const unsigned w = ps16[5 * j + 20 * n1 + n1 / 4];
+                    xv = make_float2((float)(short)(w & 0xffff), (float)(short)(w >> 16));
+                } else {
+                    xv = *(const float2*)(ps + 10 * j + 40 * n1 + LM_SKEW * (n1 / 4));
+                }
                 const float2 wv = *(const float2*)(pw + 10 * j + 40 * n1);
                 x[n1].r = xv.x * wv.x;
                 x[n1].i = xv.y * wv.y;
@@ -334,13 +357,14 @@ __global__ void __launch_bounds__(LM_THREADS, 2) stft_mel_kernel(LogMelParams p)
         {
             cpx za[20], zb[20];
             {
-                cpx x[20];
+                cpx xa[20], xb[20];
 #pragma unroll
-                for (int n2 = 0; n2 < 20; n2++) { const float2 v = pex_a[n2]; x[n2] = {v.x, v.y}; }
-                dft20(x, za);
+                for (int n2 = 0; n2 < 20; n2++) { const float2 v = pex_a[n2]; xa[n2] = {v.x, v.y}; }
 #pragma unroll
-                for (int n2 = 0; n2 < 20; n2++) { const float2 v = pex_b[n2]; x[n2] = {v.x, v.y}; }
-                dft20(x, zb);
+                for (int n2 = 0; n2 < 20; n2++) { const float2 v = pex_b[n2]; xb[n2] = {v.x, v.y}; }
+                __syncthreads();   // the exchange buffer is consumed: the power spectra may overwrite it
+                dft20(xa, za);
+                dft20(xb, zb);
             }
             if (u != 0) {
                 // Z[k] = za[j] (k = u+10j),  Z[200-k] = zb[19-j]
@@ -446,10 +470,7 @@ __global__ void logmel_init_kernel(int* gmax_key, int n) {
     if (i < n) gmax_key[i] = float_to_key(-3.0e38f);
 }
 
-static size_t logmel_smem_bytes() {
-    size_t words = (size_t)LM_TILE_WORDS + 2 * (size_t)LM_FRAMES * LM_EXP + (size_t)LM_FRAMES * LM_PP + kNFFT + 2 * 200 + 2 * 202 + 8;
-    return words * 4;
-}
+template <int FMT> static size_t logmel_smem_bytes() { return (size_t)LmSmem<FMT>::WORDS * 4; }
 
 static i64 logmel_tiles_cap(i64 n, i64 padding) {
     i64 T = (n + padding) / kHop;
@@ -488,13 +509,16 @@ int logmel_launch(const void* d_audio, int fmt, i64 batch, i64 n, i64 row_stride
     int nkeys = (int)batch;
     auto kinit = logmel_init_kernel;
     B2A_LAUNCH(kinit, (nkeys + 255) / 256, 256, 0, stream, p.gmax_key, nkeys);
-    size_t smem = logmel_smem_bytes();
-    auto k4 = n_mels == 80 ? stft_mel_kernel<80> : stft_mel_kernel<128>;
+    const bool s16 = fmt == B2A_FMT_S16;
+    size_t smem = s16 ? logmel_smem_bytes<B2A_FMT_S16>() : logmel_smem_bytes<B2A_FMT_F32>();
+    auto k4 = n_mels == 80 ? (s16 ? stft_mel_kernel<80, B2A_FMT_S16> : stft_mel_kernel<80, B2A_FMT_F32>)
+                           : (s16 ? stft_mel_kernel<128, B2A_FMT_S16> : stft_mel_kernel<128, B2A_FMT_F32>);
     {
         cudaError_t e = cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // idempotent, cheap
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(stft_mel)");
     }
-    i64 grid = work < 148 * 2 ? work : 148 * 2;   // persistent: 2 CTAs per SM (shared-memory bound)
+    const i64 resident = 148 * (s16 ? LmSmem<B2A_FMT_S16>::CTAS : LmSmem<B2A_FMT_F32>::CTAS);   // persistent: every CTA resident
+    i64 grid = work < resident ? work : resident;
     B2A_LAUNCH(k4, (unsigned)grid, LM_THREADS, smem, stream, p);
     B2A_CHECK_LAUNCH("stft_mel_kernel");
     i64 grid5 = (work + 7) / 8 < 148 * 8 ? (work + 7) / 8 : 148 * 8;     // 8 warps per block, one tile per warp
