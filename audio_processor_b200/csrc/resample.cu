@@ -68,11 +68,37 @@ __global__ void __launch_bounds__(256) resample_generic_kernel(GenericParams p) 
         float a0 = 0.f, a1 = 0.f;
         const i64 base = idx - p.center;
         int i = 0;
-        for (; i + 1 < p.taps; i += 2) {
-            a0 = fmaf(generic_sample(p, base + i), h[i], a0);
-            a1 = fmaf(generic_sample(p, base + i + 1), h[i + 1], a1);
+        if (base >= 0 && base + p.taps <= p.n_in) {
+            // interior window: no edge extension, plain strided loads, four taps in flight per accumulator pair
+            float b0 = 0.f, b1 = 0.f;
+            if (p.fmt == B2A_FMT_S16 && p.channels == 2 && (((uintptr_t)p.in) & 3) == 0) {
+                const int* s = (const int*)p.in + base;            // one 32-bit word per stereo frame
+                for (; i + 3 < p.taps; i += 4) {
+                    a0 = fmaf((float)__dp2a_lo(s[i], 0x0101, 0), h[i], a0);
+                    a1 = fmaf((float)__dp2a_lo(s[i + 1], 0x0101, 0), h[i + 1], a1);
+                    b0 = fmaf((float)__dp2a_lo(s[i + 2], 0x0101, 0), h[i + 2], b0);
+                    b1 = fmaf((float)__dp2a_lo(s[i + 3], 0x0101, 0), h[i + 3], b1);
+                }
+                for (; i < p.taps; i++) a0 = fmaf((float)__dp2a_lo(s[i], 0x0101, 0), h[i], a0);
+                a0 = ((a0 + b0) + (a1 + b1)) * (1.0f / 65536.0f);   // exact power-of-two scale of 0.5*(L+R)/32768
+                a1 = 0.f;
+            } else {
+                for (; i + 3 < p.taps; i += 4) {
+                    a0 = fmaf(generic_sample(p, base + i), h[i], a0);
+                    a1 = fmaf(generic_sample(p, base + i + 1), h[i + 1], a1);
+                    b0 = fmaf(generic_sample(p, base + i + 2), h[i + 2], b0);
+                    b1 = fmaf(generic_sample(p, base + i + 3), h[i + 3], b1);
+                }
+                for (; i < p.taps; i++) a0 = fmaf(generic_sample(p, base + i), h[i], a0);
+                a0 += b0; a1 += b1;
+            }
+        } else {
+            for (; i + 1 < p.taps; i += 2) {
+                a0 = fmaf(generic_sample(p, base + i), h[i], a0);
+                a1 = fmaf(generic_sample(p, base + i + 1), h[i + 1], a1);
+            }
+            if (i < p.taps) a0 = fmaf(generic_sample(p, base + i), h[i], a0);
         }
-        if (i < p.taps) a0 = fmaf(generic_sample(p, base + i), h[i], a0);
         const float y = a0 + a1;
         q = quant_s16(y * 32768.0f);
         if (p.out_s16) p.out_s16[m] = (int16_t)q;

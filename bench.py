@@ -55,6 +55,16 @@ WORKLOADS = {
 
 
 # ----------------------------------------------------------------------------------------------- utils
+def measured_traffic(workload: str, kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json), or None"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)[workload][kernel]
+        return int(t["read"]) + int(t["write"])
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -466,7 +476,7 @@ def run_b200(args):
             "stages_ms": {k: round(v, 4) for k, v in stages.items()},
             "roofline": {"bound": "hbm", "kernel": roof["kernel"], "achieved": roof["bytes"] / (roof["ms"] * 1e-3) / 1e9,
                          "peak": peak, "unit": "GB/s", "frac": roof["bytes"] / (roof["ms"] * 1e-3) / 1e9 / peak,
-                         "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_launch": int(roof["bytes"]),
+                         "peak_source": peak_src, "traffic": measured_traffic(args.workload, roof["kernel"]), "algorithmic_bytes_per_launch": int(roof["bytes"]),
                          "kernel_ms": roof["ms"],
                          "pipeline_algorithmic_bytes_per_step": int(abytes),
                          "pipeline_achieved": abytes / (ms_step * 1e-3) / 1e9,
