@@ -17,10 +17,11 @@
 //    transposes through shared memory (pitch 201 complex per frame: conflict free), then the radix-20 butterflies
 //    (4x5 prime-factor) of output residues {u, 10-u} mod 10 — so the real-FFT unpack pairs (k, 200-k) stay inside
 //    one thread.  The unpack produces 4|X|^2 (16 flops per conjugate pair); the 1/4 lives in the mel weights.
-//  * mel projection: warp g owns a contiguous group of mels (balanced by non-zero weights), lane = frame.  The
-//    sparse filterbank is compile-time data (mel_tables_gen.inc): fully unrolled, each weight an FFMA immediate,
-//    each power bin loaded once from shared memory (pitch 203: conflict free).  log10, running max/min and the
-//    [n_mels][T] store follow; a warp stores 32 consecutive frames of one mel = one 128-byte line.
+//  * mel projection: warp g owns a contiguous group of mels (balanced by cost), lane = frame.  The sparse filterbank
+//    (mel_tables_gen.inc) is staged in shared memory as packed descriptors + zero-padded weight quads and walked by a
+//    small loop shared by all warps (16-byte broadcast loads of weights, conflict-free loads of the power bins at
+//    pitch 203) — the fully unrolled immediate-weight form was 24-48 % slower on instruction fetch.  log10, running
+//    max/min and the [n_mels][T] store follow; a warp stores 32 consecutive frames of one mel = one 128-byte line.
 //  * K5 applies Whisper's global floor in place and skips tiles whose minimum is already above it.
 #include "b2a_tables.cuh"
 
@@ -40,7 +41,6 @@ constexpr int LM_PP = 203;                          // power-spectrum pitch per 
 #define B2A_MEL_TABLES_INCLUDED
 #include "mel_tables_gen.inc"
 #endif
-template <int NM> __device__ __forceinline__ float mel_w(int idx) { return NM == 80 ? kMelW80[idx] : kMelW128[idx]; }
 
 struct cpx { float r, i; };
 __device__ __forceinline__ cpx cadd(cpx a, cpx b) { return {a.r + b.r, a.i + b.i}; }
@@ -147,31 +147,45 @@ __device__ __forceinline__ float load_sample(const void* audio, int fmt, i64 idx
     return ((const float*)audio)[idx];
 }
 
-// ---- mel projection of one frame for the mels [M, M1) of a warp's group: compile-time sparse filterbank ----
-// lmax / lmin track log2(mel) over the group (converted once per tile by the caller); only the store is predicated
-template <int NM, int M, int M1>
-struct MelLoop {
-    __device__ static __forceinline__ void run(const float* __restrict__ Pf, float* __restrict__ ocol, size_t Tstride, bool valid,
-                                               float& lmax, float& lmin) {
-        constexpr int st = MelC<NM>::start[M], ln = MelC<NM>::len[M];
-        float acc = 0.0f;
+// ---- mel projection of one frame for the mels [m0, m1) of a warp's group, table driven ----
+// The sparse filterbank sits in shared memory: pack[m] = first bin | quads << 8 | first weight quad << 12, weights padded
+// with zeros to whole quads (one 16-byte broadcast load per 4 taps).  The code is the same few dozen instructions for
+// every warp and every mel: the fully unrolled immediate-weight form measured 24 % (80 mels) to 48 % (128 mels) slower
+// because five warps x 5 different 4-6 KB bodies overflow the instruction cache (profiles/r01_logmel_icache.md).
+// lmax / lmin track log2(mel) over the group (converted once per tile by the caller); only the store is predicated.
+template <int NQ>
+__device__ __forceinline__ float mel_dot(const float4* __restrict__ w4, const float* __restrict__ pf) {
+    float acc = 0.0f;
 #pragma unroll
-        for (int j = 0; j < ln; j++) acc = fmaf(mel_w<NM>(M * kMelMaxWidth + j), Pf[st + j], acc);
+    for (int q = 0; q < NQ; q++) {
+        const float4 w = w4[q];
+        acc = fmaf(w.x, pf[4 * q], acc);
+        acc = fmaf(w.y, pf[4 * q + 1], acc);
+        acc = fmaf(w.z, pf[4 * q + 2], acc);
+        acc = fmaf(w.w, pf[4 * q + 3], acc);
+    }
+    return acc;
+}
+__device__ __forceinline__ void mel_group(const unsigned* __restrict__ s_pack, const float4* __restrict__ s_flat4, int m0, int m1,
+                                          const float* __restrict__ Pf, float* __restrict__ ocol, size_t Tstride, bool valid,
+                                          float& lmax, float& lmin) {
+    ocol += (size_t)m0 * Tstride;
+#pragma unroll 1
+    for (int m = m0; m < m1; m++, ocol += Tstride) {
+        const unsigned pk = s_pack[m];
+        const float* pf = Pf + (pk & 0xffu);
+        const float4* w4 = s_flat4 + (pk >> 12);
+        const int nq = (int)((pk >> 8) & 0xfu);
+        float acc;
+        if (nq == 1) acc = mel_dot<1>(w4, pf);
+        else if (nq == 2) acc = mel_dot<2>(w4, pf);
+        else if (nq == 3) acc = mel_dot<3>(w4, pf);
+        else acc = mel_dot<4>(w4, pf);
         const float l2 = __log2f(fmaxf(acc, 1e-10f));
         lmax = fmaxf(lmax, l2);
         lmin = fminf(lmin, l2);
         if (valid) *ocol = fmaf(l2 * 0.30102999566398120f, 0.25f, 1.0f);      // (log10 + 4) / 4, same roundings as Whisper's two steps
-        MelLoop<NM, M + 1, M1>::run(Pf, ocol + Tstride, Tstride, valid, lmax, lmin);
     }
-};
-template <int NM, int M1>
-struct MelLoop<NM, M1, M1> {
-    __device__ static __forceinline__ void run(const float*, float*, size_t, bool, float&, float&) {}
-};
-template <int NM, int G>
-__device__ __forceinline__ void mel_group(const float* __restrict__ Pf, float* __restrict__ ocol, size_t Tstride, bool valid,
-                                          float& lmax, float& lmin) {
-    MelLoop<NM, MelC<NM>::group[G], MelC<NM>::group[G + 1]>::run(Pf, ocol + (size_t)MelC<NM>::group[G] * Tstride, Tstride, valid, lmax, lmin);
 }
 
 #ifndef B2A_EMU
@@ -193,7 +207,7 @@ constexpr int LM_PRE = (LM_PAIRS + LM_THREADS - 1) / LM_THREADS;        // 17 pa
 template <int FMT> struct LmSmem {
     static constexpr int TILE_WORDS = ((FMT == B2A_FMT_S16 ? (LM_TILE / 2 + (LM_TILE / kHop + 2)) : LM_TILE_WORDS) + 3) / 4 * 4;   // keeps the buffers behind it 16-byte aligned
     static constexpr int HOPW = FMT == B2A_FMT_S16 ? (kHop / 2 + 1) : LM_HOPW;      // words between frames (81: odd, conflict free)
-    static constexpr int WORDS = TILE_WORDS + 2 * LM_FRAMES * LM_EXP + kNFFT + 2 * 200 + 2 * 202 + 8;
+    static constexpr int WORDS = TILE_WORDS + 2 * LM_FRAMES * LM_EXP + kNFFT + 2 * 200 + 2 * 202 + 8 + kMelFlatN128 + kMelMaxMels;
     static constexpr int CTAS = FMT == B2A_FMT_S16 ? 3 : 2;
 };
 
@@ -210,12 +224,17 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
     float2* s_tw200 = (float2*)(s_win + kNFFT);                         // 200
     float2* s_tw400 = s_tw200 + 200;                                    // 201 (+1 pad)
     float* s_red = (float*)(s_tw400 + 202);                             // 8
+    float4* s_flat4 = (float4*)(s_red + 8);                             // padded mel weights (<= kMelFlatN128 floats, 16-byte aligned)
+    unsigned* s_pack = (unsigned*)(s_flat4 + kMelFlatN128 / 4);          // n_mels packed filter descriptors
 
     const int tid = threadIdx.x;
     const LogMelTables* tab = p.tab;
     for (int i = tid; i < kNFFT; i += LM_THREADS) s_win[i] = tab->win[i] * (S16 ? (1.0f / 32768.0f) : 1.0f);   // s16 tile holds raw integers
     for (int i = tid; i < 200; i += LM_THREADS) s_tw200[i] = tab->tw200[i];
     for (int i = tid; i < kNBins; i += LM_THREADS) s_tw400[i] = tab->tw400[i];
+    for (int i = tid; i < (NM == 80 ? kMelFlatN80 : kMelFlatN128); i += LM_THREADS) ((float*)s_flat4)[i] = NM == 80 ? kMelFlat80[i] : kMelFlat128[i];
+    for (int i = tid; i < NM; i += LM_THREADS) s_pack[i] = NM == 80 ? kMelPack80[i] : kMelPack128[i];
+    for (int i = tid; i < LM_FRAMES * LM_EXP; i += LM_THREADS) s_ex[i] = make_float2(0.0f, 0.0f);   // padded taps may read slots no stage writes
 
     i64 n_act = p.n;
     if (p.d_n) { n_act = *p.d_n; if (n_act > p.n) n_act = p.n; if (n_act < 0) n_act = 0; }
@@ -235,6 +254,11 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
     const float2* pex_b = s_ex + LM_EXP * f + 20 * k1b;
     float* pP = s_P + LM_PP * f;
     const int elem = S16 ? 2 : 4;
+    // this warp's group of mels (balanced by cost at table-generation time)
+    constexpr int kG0 = MelC<NM>::group[0], kG1 = MelC<NM>::group[1], kG2 = MelC<NM>::group[2], kG3 = MelC<NM>::group[3],
+                  kG4 = MelC<NM>::group[4], kG5 = MelC<NM>::group[5];
+    const int mg0 = u == 0 ? kG0 : u == 1 ? kG1 : u == 2 ? kG2 : u == 3 ? kG3 : kG4;
+    const int mg1 = u == 0 ? kG1 : u == 1 ? kG2 : u == 2 ? kG3 : u == 3 ? kG4 : kG5;
 
     float run_max = -3.0e38f;
     i64 prev_slot = -1;                          // tile_min slot of the previous work item (written one barrier later)
@@ -404,13 +428,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
             const bool valid = t < T;
             float* ocol = p.out + (size_t)b * (size_t)NM * (size_t)T + (valid ? t : 0);
             float lmax = -3.0e38f, lmin = 3.0e38f;
-            switch (u) {
-                case 0: mel_group<NM, 0>(pP, ocol, (size_t)T, valid, lmax, lmin); break;
-                case 1: mel_group<NM, 1>(pP, ocol, (size_t)T, valid, lmax, lmin); break;
-                case 2: mel_group<NM, 2>(pP, ocol, (size_t)T, valid, lmax, lmin); break;
-                case 3: mel_group<NM, 3>(pP, ocol, (size_t)T, valid, lmax, lmin); break;
-                default: mel_group<NM, 4>(pP, ocol, (size_t)T, valid, lmax, lmin); break;
-            }
+            mel_group(s_pack, s_flat4, mg0, mg1, pP, ocol, (size_t)T, valid, lmax, lmin);
             if (valid) run_max = fmaxf(run_max, lmax * 0.30102999566398120f);
             // per-tile minimum (lets mel_floor skip tiles that need no clamping): published after the next barrier
             lmin = warp_reduce_min_f(valid ? lmin : 3.0e38f);
