@@ -41,6 +41,13 @@ constexpr int LM_PP = 203;                          // power-spectrum pitch per 
 #define B2A_MEL_TABLES_INCLUDED
 #include "mel_tables_gen.inc"
 #endif
+// compile-time access to MelC<NM>::seg[G][q] from device code (the constexpr arrays themselves have no device storage)
+template <int NM, int G> struct MelSeg {
+    __host__ __device__ static constexpr int v(int q) {
+        constexpr int s0 = MelC<NM>::seg[G][0], s1 = MelC<NM>::seg[G][1], s2 = MelC<NM>::seg[G][2], s3 = MelC<NM>::seg[G][3], s4 = MelC<NM>::seg[G][4];
+        return q == 0 ? s0 : q == 1 ? s1 : q == 2 ? s2 : q == 3 ? s3 : s4;
+    }
+};
 
 struct cpx { float r, i; };
 __device__ __forceinline__ cpx cadd(cpx a, cpx b) { return {a.r + b.r, a.i + b.i}; }
@@ -147,45 +154,46 @@ __device__ __forceinline__ float load_sample(const void* audio, int fmt, i64 idx
     return ((const float*)audio)[idx];
 }
 
-// ---- mel projection of one frame for the mels [m0, m1) of a warp's group, table driven ----
-// The sparse filterbank sits in shared memory: pack[m] = first bin | quads << 8 | first weight quad << 12, weights padded
-// with zeros to whole quads (one 16-byte broadcast load per 4 taps).  The code is the same few dozen instructions for
-// every warp and every mel: the fully unrolled immediate-weight form measured 24 % (80 mels) to 48 % (128 mels) slower
-// because five warps x 5 different 4-6 KB bodies overflow the instruction cache (profiles/r01_logmel_icache.md).
-// lmax / lmin track log2(mel) over the group (converted once per tile by the caller); only the store is predicated.
+// ---- mel projection of one frame for a warp's group of mels, table driven ----
+// The sparse filterbank sits in shared memory: desc[m] = {byte offset of the first power bin, byte offset of the first
+// weight quad}, weights padded with zeros to whole quads (one 16-byte broadcast load per 4 taps) and the quad count made
+// non-decreasing in m, so a group is at most four runs of constant quad count: loops without a per-mel branch.  The code
+// is the same few dozen instructions for every warp: the fully unrolled immediate-weight form measured 24 % (80 mels) to
+// 48 % (128 mels) slower because five warps x 5 different 4-6 KB bodies overflow the instruction cache
+// (profiles/r01_logmel_icache.md).  lmax / lmin track log2(mel) over the group (converted once per tile by the caller);
+// only the store is predicated.
 template <int NQ>
-__device__ __forceinline__ float mel_dot(const float4* __restrict__ w4, const float* __restrict__ pf) {
-    float acc = 0.0f;
-#pragma unroll
-    for (int q = 0; q < NQ; q++) {
-        const float4 w = w4[q];
-        acc = fmaf(w.x, pf[4 * q], acc);
-        acc = fmaf(w.y, pf[4 * q + 1], acc);
-        acc = fmaf(w.z, pf[4 * q + 2], acc);
-        acc = fmaf(w.w, pf[4 * q + 3], acc);
-    }
-    return acc;
-}
-__device__ __forceinline__ void mel_group(const unsigned* __restrict__ s_pack, const float4* __restrict__ s_flat4, int m0, int m1,
-                                          const float* __restrict__ Pf, float* __restrict__ ocol, size_t Tstride, bool valid,
-                                          float& lmax, float& lmin) {
-    ocol += (size_t)m0 * Tstride;
+__device__ __forceinline__ void mel_run(const uint2* __restrict__ s_desc, const char* __restrict__ s_flat, int m0, int m1,
+                                        const char* __restrict__ Pf, float*& ocol, size_t Tstride, bool valid, float& lmax, float& lmin) {
 #pragma unroll 1
     for (int m = m0; m < m1; m++, ocol += Tstride) {
-        const unsigned pk = s_pack[m];
-        const float* pf = Pf + (pk & 0xffu);
-        const float4* w4 = s_flat4 + (pk >> 12);
-        const int nq = (int)((pk >> 8) & 0xfu);
-        float acc;
-        if (nq == 1) acc = mel_dot<1>(w4, pf);
-        else if (nq == 2) acc = mel_dot<2>(w4, pf);
-        else if (nq == 3) acc = mel_dot<3>(w4, pf);
-        else acc = mel_dot<4>(w4, pf);
-        const float l2 = __log2f(fmaxf(acc, 1e-10f));
+        const uint2 d = s_desc[m];
+        const float* pf = (const float*)(Pf + d.x);
+        const float4* w4 = (const float4*)(s_flat + d.y);
+        float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            const float4 w = w4[q];
+            a0 = fmaf(w.x, pf[4 * q], a0);
+            a1 = fmaf(w.y, pf[4 * q + 1], a1);
+            a0 = fmaf(w.z, pf[4 * q + 2], a0);
+            a1 = fmaf(w.w, pf[4 * q + 3], a1);
+        }
+        const float l2 = __log2f(fmaxf(a0 + a1, 1e-10f));
         lmax = fmaxf(lmax, l2);
         lmin = fminf(lmin, l2);
         if (valid) *ocol = fmaf(l2 * 0.30102999566398120f, 0.25f, 1.0f);      // (log10 + 4) / 4, same roundings as Whisper's two steps
     }
+}
+// seg[q]: first mel of the group with more than q quads (seg[0] = group start, seg[4] = group end)
+__device__ __forceinline__ void mel_group(const uint2* __restrict__ s_desc, const char* __restrict__ s_flat, const int (&seg)[5],
+                                          const float* __restrict__ Pf, float* ocol, size_t Tstride, bool valid,
+                                          float& lmax, float& lmin) {
+    ocol += (size_t)seg[0] * Tstride;
+    mel_run<1>(s_desc, s_flat, seg[0], seg[1], (const char*)Pf, ocol, Tstride, valid, lmax, lmin);
+    mel_run<2>(s_desc, s_flat, seg[1], seg[2], (const char*)Pf, ocol, Tstride, valid, lmax, lmin);
+    mel_run<3>(s_desc, s_flat, seg[2], seg[3], (const char*)Pf, ocol, Tstride, valid, lmax, lmin);
+    mel_run<4>(s_desc, s_flat, seg[3], seg[4], (const char*)Pf, ocol, Tstride, valid, lmax, lmin);
 }
 
 #ifndef B2A_EMU
@@ -207,7 +215,7 @@ constexpr int LM_PRE = (LM_PAIRS + LM_THREADS - 1) / LM_THREADS;        // 17 pa
 template <int FMT> struct LmSmem {
     static constexpr int TILE_WORDS = ((FMT == B2A_FMT_S16 ? (LM_TILE / 2 + (LM_TILE / kHop + 2)) : LM_TILE_WORDS) + 3) / 4 * 4;   // keeps the buffers behind it 16-byte aligned
     static constexpr int HOPW = FMT == B2A_FMT_S16 ? (kHop / 2 + 1) : LM_HOPW;      // words between frames (81: odd, conflict free)
-    static constexpr int WORDS = TILE_WORDS + 2 * LM_FRAMES * LM_EXP + kNFFT + 2 * 200 + 2 * 202 + 8 + kMelFlatN128 + kMelMaxMels;
+    static constexpr int WORDS = TILE_WORDS + 2 * LM_FRAMES * LM_EXP + kNFFT + 2 * 200 + 2 * 202 + 8 + kMelFlatN128 + 2 * kMelMaxMels;
     static constexpr int CTAS = FMT == B2A_FMT_S16 ? 3 : 2;
 };
 
@@ -225,7 +233,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
     float2* s_tw400 = s_tw200 + 200;                                    // 201 (+1 pad)
     float* s_red = (float*)(s_tw400 + 202);                             // 8
     float4* s_flat4 = (float4*)(s_red + 8);                             // padded mel weights (<= kMelFlatN128 floats, 16-byte aligned)
-    unsigned* s_pack = (unsigned*)(s_flat4 + kMelFlatN128 / 4);          // n_mels packed filter descriptors
+    uint2* s_desc = (uint2*)(s_flat4 + kMelFlatN128 / 4);                // n_mels filter descriptors
 
     const int tid = threadIdx.x;
     const LogMelTables* tab = p.tab;
@@ -233,7 +241,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
     for (int i = tid; i < 200; i += LM_THREADS) s_tw200[i] = tab->tw200[i];
     for (int i = tid; i < kNBins; i += LM_THREADS) s_tw400[i] = tab->tw400[i];
     for (int i = tid; i < (NM == 80 ? kMelFlatN80 : kMelFlatN128); i += LM_THREADS) ((float*)s_flat4)[i] = NM == 80 ? kMelFlat80[i] : kMelFlat128[i];
-    for (int i = tid; i < NM; i += LM_THREADS) s_pack[i] = NM == 80 ? kMelPack80[i] : kMelPack128[i];
+    for (int i = tid; i < 2 * NM; i += LM_THREADS) ((unsigned*)s_desc)[i] = NM == 80 ? kMelDesc80[i] : kMelDesc128[i];
     for (int i = tid; i < LM_FRAMES * LM_EXP; i += LM_THREADS) s_ex[i] = make_float2(0.0f, 0.0f);   // padded taps may read slots no stage writes
 
     i64 n_act = p.n;
@@ -255,10 +263,11 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
     float* pP = s_P + LM_PP * f;
     const int elem = S16 ? 2 : 4;
     // this warp's group of mels (balanced by cost at table-generation time)
-    constexpr int kG0 = MelC<NM>::group[0], kG1 = MelC<NM>::group[1], kG2 = MelC<NM>::group[2], kG3 = MelC<NM>::group[3],
-                  kG4 = MelC<NM>::group[4], kG5 = MelC<NM>::group[5];
-    const int mg0 = u == 0 ? kG0 : u == 1 ? kG1 : u == 2 ? kG2 : u == 3 ? kG3 : kG4;
-    const int mg1 = u == 0 ? kG1 : u == 1 ? kG2 : u == 2 ? kG3 : u == 3 ? kG4 : kG5;
+    int mseg[5];
+#pragma unroll
+    for (int q = 0; q < 5; q++) {
+            mseg[q] = u == 0 ? MelSeg<NM, 0>::v(q) : u == 1 ? MelSeg<NM, 1>::v(q) : u == 2 ? MelSeg<NM, 2>::v(q) : u == 3 ? MelSeg<NM, 3>::v(q) : MelSeg<NM, 4>::v(q);
+    }
 
     float run_max = -3.0e38f;
     i64 prev_slot = -1;                          // tile_min slot of the previous work item (written one barrier later)
@@ -428,7 +437,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
             const bool valid = t < T;
             float* ocol = p.out + (size_t)b * (size_t)NM * (size_t)T + (valid ? t : 0);
             float lmax = -3.0e38f, lmin = 3.0e38f;
-            mel_group(s_pack, s_flat4, mg0, mg1, pP, ocol, (size_t)T, valid, lmax, lmin);
+            mel_group(s_desc, (const char*)s_flat4, mseg, pP, ocol, (size_t)T, valid, lmax, lmin);
             if (valid) run_max = fmaxf(run_max, lmax * 0.30102999566398120f);
             // per-tile minimum (lets mel_floor skip tiles that need no clamping): published after the next barrier
             lmin = warp_reduce_min_f(valid ? lmin : 3.0e38f);

@@ -4,6 +4,7 @@
 // the real-FFT unpack (|X|^2 = 0.25 * |2X|^2), an exact power-of-two scale.  Mels are split into 5 groups (one per
 // warp of the kernel) balanced by the kernel's cost model (quads of taps + per-mel epilogue).
 #include <cstdio>
+#include <algorithm>
 #include <vector>
 #include "../audio_processor_b200/csrc/mel_design.h"
 
@@ -21,7 +22,7 @@ static int emit(FILE* f, int nm) {
         if (first < 0) { first = 0; last = -1; }
         start[m] = first; len[m] = last - first + 1;
         if (len[m] > kWidth) { fprintf(stderr, "mel %d wider than %d bins\n", m, kWidth); return 1; }
-        total += 9 * ((len[m] + 3) / 4) + 20;      // kernel cost model: 9 instructions per quad of taps + 20 per mel
+        total += 9 * ((len[m] + 3) / 4) + 14;      // kernel cost model: 9 instructions per quad of taps + 14 per mel
     }
     fprintf(f, "// %d mels: sparse slaney filterbank, weights x 0.25\n", nm);
     fprintf(f, "template <> struct MelC<%d> {\n    static constexpr int start[%d] = {", nm, nm);
@@ -33,25 +34,48 @@ static int emit(FILE* f, int nm) {
     int bounds[kGroups + 1]; bounds[0] = 0; bounds[kGroups] = nm;
     int acc = 0, g = 1;
     for (int m = 0; m < nm && g < kGroups; m++) {
-        acc += 9 * ((len[m] + 3) / 4) + 20;
+        acc += 9 * ((len[m] + 3) / 4) + 14;
         if (acc * kGroups >= total * g) bounds[g++] = m + 1;
     }
     for (; g < kGroups; g++) bounds[g] = nm;
     fprintf(f, "    static constexpr int group[%d] = {", kGroups + 1);
     for (int i = 0; i <= kGroups; i++) fprintf(f, "%d, ", bounds[i]);
+    fprintf(f, "};\n    static constexpr int seg[%d][5] = {", kGroups);
+    {
+        std::vector<int> q2(nm);
+        int prev = 1;
+        for (int m = 0; m < nm; m++) { q2[m] = std::max(prev, (len[m] + 3) / 4); prev = q2[m]; }
+        for (int g2 = 0; g2 < kGroups; g2++) {
+            fprintf(f, "{");
+            for (int q = 0; q <= 4; q++) {
+                int m = bounds[g2];
+                while (m < bounds[g2 + 1] && q2[m] <= q) m++;
+                fprintf(f, "%d, ", q == 4 ? bounds[g2 + 1] : m);
+            }
+            fprintf(f, "}, ");
+        }
+    }
     fprintf(f, "};\n};\n");
-    // table-driven form for the kernel's mel loop: weights flattened, every filter padded with zeros to a multiple of 4
-    // (one 16-byte load per 4 taps); pack[m] = first bin | quads << 8 | first weight quad << 12
+    // table-driven form for the kernel's mel loop: weights flattened, every filter padded with zeros to whole quads of
+    // taps (one 16-byte load per 4 taps); quads[m] is made non-decreasing in m (filters widen with frequency; a narrower
+    // straggler is padded), so each warp's group is a few runs of constant quad count = loops without a per-mel branch.
+    // desc[m] = {byte offset of the first power bin, byte offset of the first weight quad}; seg[g][q] = first mel of
+    // group g with more than q quads (seg[g][0] = group start, seg[g][4] = group end).
+    std::vector<int> quads(nm);
+    {
+        int prev = 1;
+        for (int m = 0; m < nm; m++) { quads[m] = std::max(prev, (len[m] + 3) / 4); prev = quads[m]; }
+    }
     {
         std::vector<float> flat;
-        std::vector<unsigned> pack(nm);
+        std::vector<unsigned> desc(2 * nm);
         for (int m = 0; m < nm; m++) {
-            const int quads = (len[m] + 3) / 4;
-            pack[m] = (unsigned)start[m] | ((unsigned)quads << 8) | ((unsigned)(flat.size() / 4) << 12);
-            for (int j = 0; j < 4 * quads; j++) flat.push_back(j < len[m] ? 0.25f * filt[(size_t)m * kBins + start[m] + j] : 0.0f);
+            desc[2 * m] = (unsigned)start[m] * 4u;
+            desc[2 * m + 1] = (unsigned)flat.size() * 4u;
+            for (int j = 0; j < 4 * quads[m]; j++) flat.push_back(j < len[m] ? 0.25f * filt[(size_t)m * kBins + start[m] + j] : 0.0f);
         }
-        fprintf(f, "static __device__ const unsigned kMelPack%d[%d] = {", nm, nm);
-        for (int m = 0; m < nm; m++) fprintf(f, "0x%xu,%s", pack[m], (m % 10 == 9) ? "\n" : " ");
+        fprintf(f, "static __device__ const unsigned kMelDesc%d[%d] = {", nm, 2 * nm);
+        for (int m = 0; m < 2 * nm; m++) fprintf(f, "%uu,%s", desc[m], (m % 10 == 9) ? "\n" : " ");
         fprintf(f, "};\nconstexpr int kMelFlatN%d = %d;\nstatic __device__ const float kMelFlat%d[%d] = {\n", nm, (int)flat.size(), nm, (int)flat.size());
         for (size_t i = 0; i < flat.size(); i++) fprintf(f, "%.9ef,%s", flat[i], (i % 4 == 3) ? "\n" : " ");
         fprintf(f, "};\n");
