@@ -11,6 +11,6 @@ for wl in cfg2 cfg1 cfg4 cfg3; do
 done
 timeout 300 python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/plain_${TAG}.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KRE" -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_launches_${TAG}.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'fir_mma_kernel|stft_mel_kernel|cover_kernel' -s 6 -c 3 -o gpurun_out/prof_${TAG} -f python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_full_${TAG}.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"fir_mma_kernel|stft_mel_kernel|cover_kernel|compact_kernel" -s 9 -c 9 -o gpurun_out/prof_${TAG} -f python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_full_${TAG}.log 2>&1
 tail -3 gpurun_out/ncu_full_${TAG}.log
 ls -la gpurun_out
