@@ -2,7 +2,7 @@
 
 The reference shells out to ffmpeg for every container (app/services/audio_processor.py:912-923) and
 whisper re-reads the 16-bit WAV it wrote.  In this tier only PCM WAV is decoded on the host (16-bit
-int, 32-bit float, WAVE_FORMAT_EXTENSIBLE wrappers of those); compressed inputs are out of scope
+and 24-bit int, 32-bit float, WAVE_FORMAT_EXTENSIBLE wrappers of those); compressed inputs are out of scope
  and raise.
 """
 from __future__ import annotations
@@ -49,8 +49,14 @@ def read_wav(path: str) -> Tuple[np.ndarray, int]:
         a = np.frombuffer(payload, dtype="<i2", count=len(payload) // 2)
     elif tag == WAVE_FORMAT_IEEE_FLOAT and bits == 32:
         a = np.frombuffer(payload, dtype="<f4", count=len(payload) // 4)
+    elif tag == WAVE_FORMAT_PCM and bits == 24:
+        # packed little-endian s24 -> float32 in [-1, 1) (exact: 24 bits fit the f32 significand); goes down the float path
+        raw = np.frombuffer(payload, dtype=np.uint8, count=(len(payload) // 3) * 3).reshape(-1, 3).astype(np.int32)
+        v = raw[:, 0] | (raw[:, 1] << 8) | (raw[:, 2] << 16)
+        v = np.where(v >= (1 << 23), v - (1 << 24), v)
+        a = (v.astype(np.float32) / np.float32(1 << 23)).astype(np.float32)
     else:
-        raise UnsupportedAudio(f"{path}: WAV format tag {tag} / {bits} bits is not supported (s16 and f32 only)")
+        raise UnsupportedAudio(f"{path}: WAV format tag {tag} / {bits} bits is not supported (s16, s24 and f32 only)")
     if ch > 1:
         a = a[: (len(a) // ch) * ch].reshape(-1, ch)
     return np.ascontiguousarray(a), int(rate)

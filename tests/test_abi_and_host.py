@@ -98,6 +98,28 @@ def test_wav_roundtrip_and_errors(tmp_path):
     bad.write_bytes(b"\x00\x00\x00\x20ftypM4A ")
     with pytest.raises(wavio.UnsupportedAudio):
         wavio.read_wav(str(bad))
+    # packed 24-bit PCM (stereo) inside a WAVE_FORMAT_EXTENSIBLE header, with a LIST chunk before the data
+    import struct
+    v = np.array([[0, 1], [-1, 8388607], [-8388608, 123456], [-654321, 42]], dtype=np.int32)
+    payload = b"".join(struct.pack("<i", int(t))[:3] for t in v.reshape(-1))
+    fmt = struct.pack("<HHIIHH", 0xFFFE, 2, 48000, 48000 * 6, 6, 24) + struct.pack("<HHI", 22, 24, 3) + struct.pack("<H", 1) + b"\x00" * 14
+    body = b"WAVE" + b"fmt " + struct.pack("<I", len(fmt)) + fmt + b"LIST" + struct.pack("<I", 4) + b"INFO" + b"data" + struct.pack("<I", len(payload)) + payload
+    p24 = tmp_path / "c.wav"
+    p24.write_bytes(b"RIFF" + struct.pack("<I", len(body)) + body)
+    a, sr = wavio.read_wav(str(p24))
+    assert sr == 48000 and a.dtype == np.float32 and a.shape == (4, 2) and np.array_equal(a, (v / 8388608.0).astype(np.float32))
+
+
+def test_mel_segments_follow_transcribe_windows():
+    """whisper.transcribe slices [n_mels, 3000]-frame windows out of a mel computed with padding=N_SAMPLES"""
+    import torch
+    from audio_processor_b200 import whisper_audio as wa
+    content = 7321
+    mel = torch.arange(2 * (content + wa.N_FRAMES), dtype=torch.float32).view(2, -1)
+    segs = list(wa.mel_segments(mel))
+    assert [s for s, _ in segs] == [0, 3000, 6000] and all(tuple(m.shape) == (2, 3000) for _, m in segs)
+    assert torch.equal(segs[1][1], mel[:, 3000:6000])
+    assert torch.equal(segs[2][1][:, :1321], mel[:, 6000:7321]) and float(segs[2][1][:, 1321:].abs().sum()) == 0.0
 
 
 def test_segment_standin_matches_pydub_restatement():
