@@ -316,6 +316,18 @@ def run_b200(args):
     value = total_audio_h * args.steps / (ms_total / 1e3)
     abytes = algo_bytes()
 
+    # ---- the one collective of the design: gather the per-clip segment tables (KBs) over NCCL, outside the timed region ----
+    gathered = None
+    if not logmel_only:
+        from audio_processor_b200 import sharding
+        tables = []
+        for p in plans:
+            nk = int(p.info[_abi.INFO_N_KEPT].item())
+            tables.append(p.kept[:nk].cpu().tolist())
+        ids = [rank * clips + i for i in range(clips)]
+        allt = sharding.gather_segment_tables(ids, tables, cap=plans[0].cap, device=dev)
+        gathered = {"clips": len(allt), "segments": int(sum(len(t) for _, t in allt))}
+
     # ---- per-stage device times (same stream, CUDA events) -> the dominant kernel for the roofline ----
     stages = {}
 
@@ -483,6 +495,8 @@ def run_b200(args):
                          "pipeline_frac": abytes / (ms_step * 1e-3) / 1e9 / peak},
             "clocks": clocks,
         }
+        if gathered is not None:
+            out["segment_tables_gathered"] = gathered
         if e2e is not None:
             out["e2e"] = e2e
         if cpu is not None:
