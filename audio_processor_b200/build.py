@@ -3,8 +3,8 @@
     python -m audio_processor_b200.build            # incremental
     python -m audio_processor_b200.build --force
 
-The tap-table header csrc/fir_taps_gen.inc is regenerated from tools/gen_fir_taps.cpp
-(the same double-precision design code the runtime uses, csrc/fir_design.h).
+The mel table header csrc/mel_tables_gen.inc is regenerated from tools/gen_mel_tables.cpp
+(the same double-precision design code the runtime uses, csrc/mel_design.h).
 """
 from __future__ import annotations
 
@@ -21,8 +21,8 @@ OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libb2a.so")
 
 SOURCES = [
-    "b2a_host.cu", "logmel.cu", "silence.cu", "resample.cu", "pipeline.cu", "fir_fast_dispatch.cu",
-    "fir_mma_44100.cu", "fir_mma_48000.cu", "fir_fast_44100_s16x1.cu", "fir_fast_48000_s16x1.cu",
+    "b2a_host.cu", "logmel.cu", "silence.cu", "resample.cu", "pipeline.cu", "fir_dispatch.cu",
+    "fir_mma_44100.cu", "fir_mma_48000.cu",
 ]
 
 NVCC_FLAGS = [
@@ -47,18 +47,6 @@ def _deps_mtime() -> float:
     return m
 
 
-def gen_taps(force: bool = False) -> None:
-    out = os.path.join(CSRC, "fir_taps_gen.inc")
-    src = os.path.join(ROOT, "tools", "gen_fir_taps.cpp")
-    dep = max(os.path.getmtime(src), os.path.getmtime(os.path.join(CSRC, "fir_design.h")))
-    if not force and os.path.exists(out) and os.path.getmtime(out) >= dep:
-        return
-    os.makedirs(OBJ, exist_ok=True)
-    exe = os.path.join(OBJ, "gen_fir_taps")
-    subprocess.run(["g++", "-O2", "-o", exe, src], check=True)
-    subprocess.run([exe, out], check=True)
-
-
 def gen_mel(force: bool = False) -> None:
     """csrc/mel_tables_gen.inc from tools/gen_mel_tables.cpp (+ csrc/mel_design.h, the design the runtime also uses)."""
     out = os.path.join(CSRC, "mel_tables_gen.inc")
@@ -75,7 +63,6 @@ def gen_mel(force: bool = False) -> None:
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
-    gen_taps(force)
     gen_mel(force)
     dep_m = _deps_mtime()
     jobs = []

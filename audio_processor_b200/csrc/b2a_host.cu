@@ -35,7 +35,7 @@ int cuda_fail(cudaError_t e, const char* what) {
     return B2A_ECUDA;
 }
 
-// resampler design lives in fir_design.h (shared with tools/gen_fir_taps.cpp)
+// resampler design lives in fir_design.h
 static long long gcd_ll(long long a, long long b) { return b2a_design::gcd_ll(a, b); }
 
 void design_resampler_host(int in_rate, int out_rate, int* L_out, int* M_out, int* taps_out, float** h_taps_out) {
@@ -133,7 +133,7 @@ const ResampleDesign* get_resample_design(int in_rate, int out_rate) {
 // B[f][n] = 2^12 * tap[phase(J)][kb + 16 s + f - (J M)/L],  J = 16 b + 8 nt + n  (zero outside the filter).
 template <int IN_RATE>
 static void build_fir_mma_table(const float* taps /*[L][TAPS]*/, std::vector<uint2>& out) {
-    using G = FirMmaGeom<IN_RATE>;
+    using G = FirMmaGeom<IN_RATE, 2>;       // tap geometry does not depend on the channel count
     out.assign((size_t)kFmBlocks * G::KS * 2 * 2 * 32, make_uint2(0u, 0u));
     for (int b = 0; b < kFmBlocks; b++)
         for (int s = 0; s < G::KS; s++)

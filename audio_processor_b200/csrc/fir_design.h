@@ -4,8 +4,8 @@
 //   ffmpeg -ar 16000 -ac 1 -c:a pcm_s16le      (/root/reference/app/services/audio_processor.py:912-920)
 // with no resampler options => filter_size 32, phase_shift 10, exact_rational, cutoff 0.97,
 // Kaiser window beta 9.  See SURVEY.md A.1 and oracle/resample_oracle.py (float64 restatement,
-// pinned against the real library).  Header-only so that the build-time tap-table generator
-// (tools/gen_fir_taps.cpp) and the runtime library produce bit-identical float taps.
+// pinned against the real library).  Header-only: the runtime library builds the float taps (and from them the tensor-core filter tables) once per
+// rate pair.
 #pragma once
 #include <cmath>
 #include <cstdlib>

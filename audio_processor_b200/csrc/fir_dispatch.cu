@@ -1,0 +1,21 @@
+// fir_dispatch.cu — picks the tensor-core FIR instantiation for a (rate, format, channels) triple.
+#include "fir_mma.cuh"
+
+namespace b2a {
+
+int fir_mma_run_44100(int channels, const void*, i64, int16_t*, u64*, FirMmaPlan*, cudaStream_t);
+int fir_mma_run_48000(int channels, const void*, i64, int16_t*, u64*, FirMmaPlan*, cudaStream_t);
+
+// returns 1 if the tensor-core kernel was launched (plan filled), 0 if this input has no fast path, <0 on error.
+// s16 input at the two named rates only; the pre-quantisation float output and every other case use the
+// table-driven kernel in resample.cu.
+int fir_fast_dispatch(int in_rate, int fmt, int channels, const void* d_in, i64 n_in, int16_t* d_out_s16, float* d_out_f32,
+                      u64* d_energy, FirMmaPlan* plan, cudaStream_t stream) {
+    plan->out_lo = plan->out_hi = 0;
+    if (fmt != B2A_FMT_S16 || d_out_f32 || (channels != 1 && channels != 2)) return 0;
+    if (in_rate == 44100) return fir_mma_run_44100(channels, d_in, n_in, d_out_s16, d_energy, plan, stream);
+    if (in_rate == 48000) return fir_mma_run_48000(channels, d_in, n_in, d_out_s16, d_energy, plan, stream);
+    return 0;
+}
+
+}  // namespace b2a

@@ -1,4 +1,4 @@
-// fir_mma.cuh — fused s16-stereo decode + downmix + polyphase FIR as a banded-Toeplitz product on the tensor
+// fir_mma.cuh — fused s16 decode (stereo or mono) + downmix + polyphase FIR as a banded-Toeplitz product on the tensor
 // cores (sm_100a), for the two named rate pairs (44.1 kHz and 48 kHz -> 16 kHz).
 //
 // Replaces libswresample's swr_convert inner loop behind the reference's
@@ -20,7 +20,7 @@
 // Within a k-step the 16 k-slots are permuted so that lane t owns frames 4t..4t+3: an A fragment row is one
 // 8-byte shared-memory load (the filter table is built with the same permutation).
 //
-// Exactness.  The window value is v = L + R (17-bit integer; the output is sum(t * v) / 2).  v = 128 * hv + lo
+// Exactness.  The window value is v = L + R (stereo) or 2 x (mono): a 17-bit integer; the output is sum(t * v) / 2.  v = 128 * hv + lo
 // with hv in [-512, 511] and lo in [0, 127]: both exact in f16.  Taps are scaled by 2^12 and split T = T_hi + T_lo
 // (f16 each, |T - T_hi - T_lo| <= 2^-22 |T|).  All four cross terms are accumulated in f32:
 //     out = 2^-6 * (T_hi + T_lo) . hv  +  2^-13 * (T_hi + T_lo) . lo
@@ -61,7 +61,7 @@ constexpr int kFmRawBufs = 4;           // raw-tile ring: TMA loads are issued t
 constexpr int kCvtIlp = 8;              // frame pairs in flight per converter thread
 constexpr int kFmBarBytes = 16;         // one mbarrier slot (8 bytes on the GPU; the emulation keeps counters in 16)
 
-template <int IN_RATE>
+template <int IN_RATE, int CH>
 struct FirMmaGeom {
     using TR = FirMmaTraits<IN_RATE>;
     static constexpr int L = TR::L, M = TR::M, TAPS = TR::TAPS, KS = TR::KS, P = TR::P;
@@ -70,10 +70,11 @@ struct FirMmaGeom {
     static constexpr int kb(int b) { return (16 * b * M) / L; }     // window start of block b (frames from the row origin)
     static constexpr int PC = kb(kFmBlocks - 1) + 16 * KS;          // columns actually read by the MMAs (540 / 592)
     static constexpr int PW = P / 2;                                // words per plane row
-    static constexpr int CENTER_BYTES16 = (CENTER * 4 + 15) / 16 * 16;
-    static constexpr int AL = (CENTER_BYTES16 - CENTER * 4) / 4;    // frames the raw tile starts early (16-byte alignment)
+    static constexpr int FB = 2 * CH;                               // bytes per input frame (s16 samples)
+    static constexpr int CENTER_BYTES16 = (CENTER * FB + 15) / 16 * 16;
+    static constexpr int AL = (CENTER_BYTES16 - CENTER * FB) / FB;  // frames the raw tile starts early (16-byte alignment)
     static constexpr int RAWF = (kFmRT - 1) * S + PC;               // frames a tile's rows touch
-    static constexpr int RAW_BYTES = ((AL + RAWF) * 4 + 15) / 16 * 16;
+    static constexpr int RAW_BYTES = ((AL + RAWF) * FB + 15) / 16 * 16;
     static constexpr int PLANE_WORDS = kFmRT * PW;                  // one plane (hv or lo) of one tile
     static constexpr int PLANES_BYTES = 2 * PLANE_WORDS * 4;        // hv + lo
     static constexpr int NBARS = 2 * kFmRawBufs + 4;
@@ -92,7 +93,7 @@ struct FirMmaGeom {
             }
         return 16 * s < hi && 16 * s + 16 > lo;
     }
-    static_assert((kFmRT * S * 4) % 16 == 0, "tile pitch must keep 16-byte alignment");
+    static_assert((kFmRT * S * FB) % 16 == 0 && (CENTER_BYTES16 - CENTER * FB) % FB == 0, "tile pitch / lead-in must keep 16-byte alignment");
     static_assert(P % 4 == 0 && (PW % 32 == 8 || PW % 32 == 24), "plane pitch must make 8-byte fragment loads conflict free");
     static_assert(P >= PC && PC % 2 == 0, "row must hold every column the MMAs read");
     static_assert(16 * KS >= ((15 * M) / L + 1) + TAPS, "K must cover the widest window of a block");
@@ -100,7 +101,7 @@ struct FirMmaGeom {
 };
 
 struct FirMmaArgs {
-    const unsigned char* in;     // raw interleaved s16 stereo frames
+    const unsigned char* in;     // raw interleaved s16 frames (stereo or mono)
     int16_t* out_s16;            // nullable
     u64* energy;                 // nullable
     const uint2* btab;           // [block][KS][nt][term][lane] B fragments (taps), see build_fir_mma_table
@@ -176,7 +177,7 @@ template <int IN_RATE>
 __device__ __forceinline__ void fir_mma_block(const unsigned* __restrict__ phv, const unsigned* __restrict__ plo,
                                               const uint2 (&breg)[FirMmaTraits<IN_RATE>::KS][2][2],
                                               float (&d12)[2][4], float (&d34)[2][4]) {
-    using G = FirMmaGeom<IN_RATE>;
+    using G = FirMmaGeom<IN_RATE, 2>;      // plane geometry does not depend on the channel count
 #pragma unroll
     for (int s = 0; s < G::KS; s++) {
         // lane t owns frames 4t..4t+3 of the k-step: word 0 = k-slots (2t, 2t+1), word 1 = k-slots (2t+8, 2t+9)
@@ -199,9 +200,9 @@ __device__ __forceinline__ void fir_mma_block(const unsigned* __restrict__ phv, 
     }
 }
 
-template <int IN_RATE>
+template <int IN_RATE, int CH>
 __global__ void __launch_bounds__(kFmThreads, 1) fir_mma_kernel(const FirMmaArgs a) {
-    using G = FirMmaGeom<IN_RATE>;
+    using G = FirMmaGeom<IN_RATE, CH>;
     B2A_DYN_SMEM(smem);
     unsigned char* raw0 = smem;                                                  // [kFmRawBufs][RAW_BYTES]
     unsigned* planes0 = (unsigned*)(smem + kFmRawBufs * G::RAW_BYTES);           // [2][hv plane | lo plane]
@@ -295,7 +296,7 @@ __global__ void __launch_bounds__(kFmThreads, 1) fir_mma_kernel(const FirMmaArgs
         const int ctid = tid - kFmMmaWarps * 32;
         auto issue = [&](i64 tile, int b) {
             // raw span of the tile: frames [tile*RT*S - CENTER - AL, +RAW_BYTES/4), 16-byte aligned at both ends
-            const unsigned char* src = a.in + ((i64)tile * kFmRT * G::S - G::CENTER - G::AL) * 4;
+            const unsigned char* src = a.in + ((i64)tile * kFmRT * G::S - G::CENTER - G::AL) * G::FB;
             mbar_expect_tx(RF(b), (unsigned)G::RAW_BYTES);
             constexpr int PIECE = 16384;
 #pragma unroll 1
@@ -320,7 +321,8 @@ __global__ void __launch_bounds__(kFmThreads, 1) fir_mma_kernel(const FirMmaArgs
             // ---- raw s16 stereo -> hv / lo f16 planes.  pair q = ctid + 192 j of the tile <-> row n = q / PAIRS_ROW,
             //      columns 2kp, 2kp+1 (kp = q % PAIRS_ROW); for a fixed trip j the row is n0(j) or n0(j)+1.
             {
-                const unsigned* rawt = (const unsigned*)(raw0 + (size_t)rb * G::RAW_BYTES) + G::AL + 2 * ctid;
+                const unsigned* rawt = (const unsigned*)(raw0 + (size_t)rb * G::RAW_BYTES) + G::AL + 2 * ctid;             // stereo: one word per frame
+                const unsigned short* rawm = (const unsigned short*)(raw0 + (size_t)rb * G::RAW_BYTES) + G::AL + 2 * ctid;  // mono
                 unsigned* plt = planes0 + (size_t)b * (2 * G::PLANE_WORDS) + ctid;
 #pragma unroll
                 for (int j0 = 0; j0 < G::CVT_TRIPS; j0 += kCvtIlp) {
@@ -338,14 +340,19 @@ __global__ void __launch_bounds__(kFmThreads, 1) fir_mma_kernel(const FirMmaArgs
                         // raw frame index = n*S + 2*kp = 2q + n*(S - 2*PAIRS_ROW);  plane word = n*PW + kp = q + n*(PW - PAIRS_ROW)
                         const int ro = 2 * qbase + (n0 + (up ? 1 : 0)) * (G::S - 2 * G::PAIRS_ROW);
                         po[e] = qbase + (n0 + (up ? 1 : 0)) * (G::PW - G::PAIRS_ROW);
-                        r0[e] = ok[e] ? rawt[ro] : 0u;
-                        r1[e] = ok[e] ? rawt[ro + 1] : 0u;
+                        if (CH == 2) {
+                            r0[e] = ok[e] ? rawt[ro] : 0u;
+                            r1[e] = ok[e] ? rawt[ro + 1] : 0u;
+                        } else {
+                            r0[e] = ok[e] ? (unsigned)rawm[ro] : 0u;
+                            r1[e] = ok[e] ? (unsigned)rawm[ro + 1] : 0u;
+                        }
                     }
 #pragma unroll
                     for (int e = 0; e < kCvtIlp; e++) {
-                        // u = L + R + 65536 in [0, 131070]: u >> 7 = hv + 512, u & 127 = lo
-                        const unsigned u0 = (unsigned)__dp2a_lo((int)r0[e], 0x0101, 65536);
-                        const unsigned u1 = (unsigned)__dp2a_lo((int)r1[e], 0x0101, 65536);
+                        // u = v + 65536 in [0, 131070] with v = L + R (stereo) or 2 x (mono): u >> 7 = hv + 512, u & 127 = lo
+                        const unsigned u0 = CH == 2 ? (unsigned)__dp2a_lo((int)r0[e], 0x0101, 65536) : (unsigned)(2 * (int)(short)r0[e] + 65536);
+                        const unsigned u1 = CH == 2 ? (unsigned)__dp2a_lo((int)r1[e], 0x0101, 65536) : (unsigned)(2 * (int)(short)r1[e] + 65536);
                         const unsigned whv = ((u1 >> 7) << 16) + ((u0 >> 7) + 0x64006400u);       // f16 bits of 1024 + hv + 512
                         const unsigned wlo = ((u1 & 127u) << 16) + ((u0 & 127u) + 0x64006400u);   // f16 bits of 1024 + lo
                         if (ok[e]) {
@@ -374,9 +381,9 @@ struct FirMmaPlan {
 
 const uint2* get_fir_mma_table(int in_rate);   // device table for the current device (b2a_host.cu); nullptr + error on failure
 
-template <int IN_RATE>
+template <int IN_RATE, int CH>
 static inline int fir_mma_launch(const void* d_in, i64 n_in, int16_t* d_out_s16, u64* d_energy, FirMmaPlan* plan, cudaStream_t stream) {
-    using G = FirMmaGeom<IN_RATE>;
+    using G = FirMmaGeom<IN_RATE, CH>;
     plan->out_lo = plan->out_hi = 0;
     // tile t reads frames [t*RT*S - CENTER - AL, that + RAW_BYTES/4): t >= 1 keeps the start inside the clip; the first
     // 16 runs (reflect head) and the tail go to the table-driven kernel
@@ -386,7 +393,7 @@ static inline int fir_mma_launch(const void* d_in, i64 n_in, int16_t* d_out_s16,
     if (tile_hi <= tile_lo) return 0;
     const uint2* tab = get_fir_mma_table(IN_RATE);
     if (!tab) return B2A_ECUDA;
-    auto k = fir_mma_kernel<IN_RATE>;
+    auto k = fir_mma_kernel<IN_RATE, CH>;
     static bool attr_done = false;    // idempotent; a benign race only repeats the call
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES);

@@ -1,18 +1,18 @@
 // resample.cu — conversion to 16 kHz mono s16: dispatch, generic/edge kernel, same-rate passthrough.
 //
 // Replaces the libswresample work behind convert_to_wav (app/services/audio_processor.py:901-930,
-// ffmpeg command :912-920).  Fast paths (resample_fast.cuh) cover 44.1 kHz and 48 kHz s16 input; this
+// ffmpeg command :912-920).  The tensor-core fast path (fir_mma.cuh) covers 44.1 kHz and 48 kHz s16 input; this
 // file holds the table-driven kernel used for (a) the head/tail outputs whose windows need
 // libswresample's reflect / symmetric edge extension, (b) every other rate pair and float input,
 // and the same-rate paths (identity, (L+R+1)>>1 stereo s16 downmix, float quantisation).
 #include "b2a_tables.cuh"
-#include "resample_fast.cuh"
+#include "fir_mma.cuh"
 
 namespace b2a {
 
-// fast-path launchers live in their own translation units (long, fully unrolled kernels)
-int fir_fast_dispatch(int in_rate, int fmt, int channels, const void* d_in, i64 n_in, i64 n_out, int16_t* d_out_s16,
-                      float* d_out_f32, u64* d_energy, FirFastPlan* plan, cudaStream_t stream);
+// tensor-core fast path (fir_mma.cuh), instantiated in its own translation units
+int fir_fast_dispatch(int in_rate, int fmt, int channels, const void* d_in, i64 n_in, int16_t* d_out_s16, float* d_out_f32,
+                      u64* d_energy, FirMmaPlan* plan, cudaStream_t stream);
 
 struct GenericParams {
     const void* in;
@@ -184,12 +184,12 @@ int resample_launch(const void* d_in, int fmt, int channels, int in_rate, i64 n_
     if (n_in < des->taps) { set_error("resample: input shorter than the %d-tap filter is unsupported", des->taps); return B2A_EUNSUPPORTED; }
 
     // fast path for the named rate pairs (needs 16-byte aligned buffers)
-    FirFastPlan plan;
-    plan.set_first = plan.set_count = 0; plan.out_lo = plan.out_hi = 0; plan.energy_atomic = false;
+    FirMmaPlan plan;
+    plan.out_lo = plan.out_hi = 0;
     const bool aligned = ((((uintptr_t)d_in) | ((uintptr_t)d_out_s16) | ((uintptr_t)d_out_f32) | ((uintptr_t)d_energy)) & 15) == 0;
     bool fast = false;
     if (aligned && out_rate == 16000) {
-        int rc = fir_fast_dispatch(in_rate, fmt, channels, d_in, n_in, n_out, d_out_s16, d_out_f32, d_energy, &plan, stream);
+        int rc = fir_fast_dispatch(in_rate, fmt, channels, d_in, n_in, d_out_s16, d_out_f32, d_energy, &plan, stream);
         if (rc < 0) return rc;
         fast = rc > 0;
     }
@@ -200,12 +200,12 @@ int resample_launch(const void* d_in, int fmt, int channels, int in_rate, i64 n_
     p.L = des->L; p.M = des->M; p.taps = des->taps; p.center = des->center; p.taps_dev = des->d_taps;
     p.out_s16 = d_out_s16; p.out_f32 = d_out_f32; p.energy = d_energy; p.spm = spm; p.n_energy = n_energy;
     p.energy_atomic = 0;
-    if (plan.set_count > 0) { p.lo0 = 0; p.hi0 = plan.out_lo; p.lo1 = plan.out_hi; p.hi1 = n_out; }
+    if (plan.out_hi > plan.out_lo) { p.lo0 = 0; p.hi0 = plan.out_lo; p.lo1 = plan.out_hi; p.hi1 = n_out; }
     else { p.lo0 = 0; p.hi0 = n_out; p.lo1 = p.hi1 = n_out; }
     const bool direct = spm > 0 && spm <= 32 && (32 % spm) == 0;
     if (d_energy && !direct) {
         // (the fast path zeroes the table itself when it accumulates atomically)
-        if (plan.set_count == 0) cudaMemsetAsync(d_energy, 0, (size_t)n_energy * 8, stream);
+        cudaMemsetAsync(d_energy, 0, (size_t)n_energy * 8, stream);     // only for output rates whose millisecond is not a power-of-two count (no fast path there)
         p.energy_atomic = 1;
     }
     // cover the zero-extended tail of the last millisecond too

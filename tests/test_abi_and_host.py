@@ -56,13 +56,13 @@ def test_host_only_entry_points_match_the_oracle():
     assert lib.b2a_mel_filters(64, None, 0) < 0 and b"bad argument" in lib.b2a_last_error()
 
 
-def test_generated_tap_table_is_current():
-    """csrc/fir_taps_gen.inc must be what tools/gen_fir_taps.cpp emits (immediates == runtime design)."""
-    exe = os.path.join(ROOT, "audio_processor_b200", "_build", "gen_fir_taps_test")
+def test_generated_mel_table_is_current():
+    """csrc/mel_tables_gen.inc must be what tools/gen_mel_tables.cpp emits (kernel tables == runtime design)."""
+    exe = os.path.join(ROOT, "audio_processor_b200", "_build", "gen_mel_tables_test")
     os.makedirs(os.path.dirname(exe), exist_ok=True)
-    subprocess.run(["g++", "-O2", "-o", exe, os.path.join(ROOT, "tools", "gen_fir_taps.cpp")], check=True)
+    subprocess.run(["g++", "-O2", "-o", exe, os.path.join(ROOT, "tools", "gen_mel_tables.cpp")], check=True)
     out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
-    assert out == open(os.path.join(ROOT, "audio_processor_b200", "csrc", "fir_taps_gen.inc")).read()
+    assert out == open(os.path.join(ROOT, "audio_processor_b200", "csrc", "mel_tables_gen.inc")).read()
 
 
 def test_product_path_has_no_cpu_fallback():

@@ -132,14 +132,15 @@ def test_emu_pipeline(emu):
     assert np.abs(r2["mel"] - wl.log_mel_spectrogram(full.astype(np.float32) / 32768.0, 128, padding=1600).numpy()).max() <= 1e-4
 
 
-@pytest.mark.parametrize("rate,tile_frames", [(44100, 7056), (48000, 7680)])
-def test_emu_fir_pipeline_many_tiles_per_cta(emu, rate, tile_frames, monkeypatch):
+@pytest.mark.parametrize("rate,tile_frames,ch", [(44100, 7056, 2), (48000, 7680, 2), (44100, 7056, 1), (48000, 7680, 1)])
+def test_emu_fir_pipeline_many_tiles_per_cta(emu, rate, tile_frames, ch, monkeypatch):
     """the tensor-core FIR's producer/consumer pipeline (mbarrier phases, raw-buffer refills two tiles ahead, deferred
     copy-out) with only 2 persistent CTAs, i.e. 5-6 tiles per CTA — the steady state of the real grid"""
     monkeypatch.setenv("B2A_FIR_GRID", "2")
     rng = np.random.default_rng(rate)
     n = tile_frames * 11 + 999
-    x = (rng.standard_normal((n, 2)) * 6000).clip(-32768, 32767).astype(np.int16)
+    x = (rng.standard_normal((n, ch)) * 6000).clip(-32768, 32767).astype(np.int16)
+    x = x[:, 0].copy() if ch == 1 else x
     y, en = emu.resample(x, rate, want_energy=True)
     assert len(y) == ro.out_len(n, rate, 16000)
     assert np.abs(y.astype(int) - ro.convert(x, rate).astype(int)).max() <= 1
