@@ -106,6 +106,8 @@ struct FirMmaArgs {
     u64* energy;                 // nullable
     const uint2* btab;           // [block][KS][nt][term][lane] B fragments (taps), see build_fir_mma_table
     i64 tile_lo, tile_hi;        // tiles [tile_lo, tile_hi) are produced (tile t = runs [t*RT, (t+1)*RT))
+    int phases;                  // profiling aid (env B2A_FIR_PHASES, tools/fir_phase_probe.py): bit 0 convert, bit 1 k-steps,
+                                 // bit 2 epilogue; 7 = the product, anything else gives wrong results on purpose
 };
 
 // ---- primitives (GPU: PTX; TEST-ONLY emulation: tests/emu) -------------------------------------------------
@@ -260,10 +262,11 @@ __global__ void __launch_bounds__(kFmThreads, 1) fir_mma_kernel(const FirMmaArgs
 #pragma unroll
                 for (int e = 0; e < 4; e++) { d12[nt][e] = 0.f; d34[nt][e] = 0.f; }
             mbar_wait(PF(b), ph);
-            fir_mma_block<IN_RATE>(phv, plo, breg, d12, d34);
+            if (a.phases & 2) fir_mma_block<IN_RATE>(phv, plo, breg, d12, d34);
             __syncwarp();
             if (lane == 0) mbar_arrive(PE(b));                      // planes[b] may be refilled
             // ---- epilogue: d[0],d[1] = run g, outputs 2t, 2t+1 of an 8-output half; d[2],d[3] = run g + 8 ----
+            if (!(a.phases & 4)) continue;
             const i64 m_run = ((i64)tile * kFmRT + g) * kFmNout + col;          // first output this lane owns in run g
             u64 e_lo = 0, e_hi = 0;                                              // sum of squares of this lane's outputs (runs g, g+8)
 #pragma unroll
@@ -320,7 +323,7 @@ __global__ void __launch_bounds__(kFmThreads, 1) fir_mma_kernel(const FirMmaArgs
             mbar_wait(PE(b), ph ^ 1u);                              // planes[b] released by the MMA warps (passes on first use)
             // ---- raw s16 stereo -> hv / lo f16 planes.  pair q = ctid + 192 j of the tile <-> row n = q / PAIRS_ROW,
             //      columns 2kp, 2kp+1 (kp = q % PAIRS_ROW); for a fixed trip j the row is n0(j) or n0(j)+1.
-            {
+            if (a.phases & 1) {
                 const unsigned* rawt = (const unsigned*)(raw0 + (size_t)rb * G::RAW_BYTES) + G::AL + 2 * ctid;             // stereo: one word per frame
                 const unsigned short* rawm = (const unsigned short*)(raw0 + (size_t)rb * G::RAW_BYTES) + G::AL + 2 * ctid;  // mono
                 unsigned* plt = planes0 + (size_t)b * (2 * G::PLANE_WORDS) + ctid;
@@ -403,6 +406,8 @@ static inline int fir_mma_launch(const void* d_in, i64 n_in, int16_t* d_out_s16,
     FirMmaArgs a;
     a.in = (const unsigned char*)d_in; a.out_s16 = d_out_s16; a.energy = d_energy; a.btab = tab;
     a.tile_lo = tile_lo; a.tile_hi = tile_hi;
+    a.phases = 7;
+    if (const char* ph = getenv("B2A_FIR_PHASES")) a.phases = atoi(ph);      // profiling only
     const i64 tiles = tile_hi - tile_lo;
     unsigned grid = (unsigned)(tiles < 148 ? tiles : 148);                   // persistent: one CTA per SM
     if (const char* gs = getenv("B2A_FIR_GRID")) {                           // test knob: few CTAs => many tiles per CTA
