@@ -344,3 +344,20 @@ def test_clip_stream_pipelined_api(ops, T):
         assert kept == r.kept and T.equal(pcm, r.pcm.cpu()) and T.equal(mel, r.mel.cpu())
     with pytest.raises(RuntimeError):
         cs.submit(clips[0]); cs.submit(clips[1]); cs.submit(clips[2])      # third clip would overwrite an uncollected slot
+
+
+def test_pipeline_degenerate_clips(ops, T):
+    """all-silent clip (nothing kept, empty mel), and a clip shorter than one FIR tile (table-driven kernel only)"""
+    from oracle import pydub_silence as ps, resample_oracle as ro, whisper_logmel as wl
+    quiet = T.zeros((44100 * 3, 2), dtype=T.int16, device="cuda")
+    r = ops.pipeline(quiet, 44100, n_mels=80, min_silence_len=1000, silence_thresh=-40, keep_silence=200)
+    assert r.kept == [] and r.nonsilent == [] and r.n_keep == 0 and r.n_frames == 0 and tuple(r.mel.shape) == (80, 0)
+    rng = np.random.default_rng(17)
+    short = (rng.standard_normal((44100 // 2, 2)) * 4000).astype(np.int16)          # 0.5 s: below min_silence_len, all kept
+    r = ops.pipeline(short, 44100, n_mels=80, min_silence_len=1000, silence_thresh=-40, keep_silence=200)
+    y = ro.convert(short, 44100)
+    pcm = r.pcm.cpu().numpy()
+    assert r.kept == ps.kept_ranges_fast(pcm if len(pcm) == len(y) else y, 16000, 1000, -40, 200, 1)
+    assert abs(len(pcm) - len(y)) <= 16 and np.abs(pcm[:len(y) - 16].astype(int) - y[:len(y) - 16].astype(int)).max() <= 1
+    ref = wl.log_mel_spectrogram(pcm.astype(np.float32) / 32768.0, 80).numpy()
+    assert np.abs(r.mel.cpu().numpy() - ref).max() <= MEL_TOL
