@@ -203,3 +203,29 @@ def remap_time(t_trimmed_s: float, kept_ms: List[List[int]]) -> float:
             return (s + (t_ms - acc)) / 1000.0
         acc += d
     return (kept_ms[-1][1] / 1000.0) if kept_ms else t_trimmed_s
+
+
+def remap_segments(segments, kept_ms: List[List[int]]):
+    """Vectorised remap for Whisper's result: every ``{"start": s, "end": e, ...}`` of ``asr_result["segments"]`` (times on
+    the silence-stripped timeline) gets original-recording times, so the speaker-overlap loop of the reference
+    (audio_processor.py:1114-1145) compares like with like.  Returns new dicts; the input is not modified."""
+    if not kept_ms:
+        return [dict(s) for s in segments]
+    k = np.asarray(kept_ms, dtype=np.float64)
+    dur = k[:, 1] - k[:, 0]
+    acc_end = np.cumsum(dur)                       # trimmed-timeline end of every kept range (ms)
+    acc_start = acc_end - dur
+
+    def one(t_s: float) -> float:
+        t_ms = float(t_s) * 1000.0
+        i = int(np.searchsorted(acc_end, t_ms, side="left"))
+        if i >= len(k):
+            return float(k[-1, 1]) / 1000.0
+        return float(k[i, 0] + (t_ms - acc_start[i])) / 1000.0
+
+    out = []
+    for seg in segments:
+        d = dict(seg)
+        d["start"], d["end"] = one(seg["start"]), one(seg["end"])
+        out.append(d)
+    return out

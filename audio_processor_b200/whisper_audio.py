@@ -92,16 +92,17 @@ def log_mel_spectrogram(audio: Union[str, np.ndarray, "object"], n_mels: int = 8
     return ops.log_mel(audio, n_mels=n_mels, padding=padding)
 
 
-def mel_segments(mel, n_frames: int = N_FRAMES):
+def mel_segments(mel, n_frames: int = N_FRAMES, dtype=None):
     """The 30-second windows ``whisper.transcribe`` feeds the encoder: ``mel[:, seek:seek + n_frames]`` for
     seek = 0, n_frames, ... over the content frames, each zero-padded to ``n_frames`` by pad_or_trim (transcribe computes
     the mel with ``padding=N_SAMPLES`` and treats the last N_FRAMES as padding; pass such a mel here).  Yields
-    (seek, segment) with segment [n_mels, n_frames] on the mel's device, no host round trip."""
+    (seek, segment) with segment [n_mels, n_frames] on the mel's device (optionally cast to ``dtype``), no host round trip."""
     content_frames = int(mel.shape[-1]) - N_FRAMES
     seek = 0
     while seek < content_frames:
         size = min(n_frames, content_frames - seek)
-        yield seek, pad_or_trim(mel[:, seek:seek + size], n_frames)
+        seg = pad_or_trim(mel[:, seek:seek + size], n_frames)
+        yield seek, (seg.to(dtype) if dtype is not None else seg)      # e.g. torch.float16 for an fp16 encoder
         seek += size
 
 

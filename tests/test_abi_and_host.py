@@ -147,6 +147,17 @@ def test_remap_time_and_sharding():
     assert counts.tolist() == [2, 0] and padded[0, :2].tolist() == [[0, 5], [7, 9]]
 
 
+def test_remap_segments_matches_scalar_remap():
+    from audio_processor_b200.service import remap_segments, remap_time
+    kept = [[0, 3093], [4907, 8000], [9000, 9500]]
+    segs = [{"start": 0.0, "end": 1.5, "text": "a"}, {"start": 3.0, "end": 3.2, "text": "b"}, {"start": 6.1, "end": 6.6, "text": "c"}]
+    out = remap_segments(segs, kept)
+    for a, b in zip(segs, out):
+        assert abs(b["start"] - remap_time(a["start"], kept)) < 1e-9 and abs(b["end"] - remap_time(a["end"], kept)) < 1e-9
+        assert b["text"] == a["text"]
+    assert abs(out[1]["end"] - (4.907 + (3.2 - 3.093))) < 1e-9 and remap_segments(segs, []) == segs
+
+
 def test_synth_recipe():
     from audio_processor_b200 import synth
     x = synth.synth_clip(2, 16000, 1, 30.0, 0.3)
