@@ -397,11 +397,15 @@ static inline int fir_mma_launch(const void* d_in, i64 n_in, int16_t* d_out_s16,
     const uint2* tab = get_fir_mma_table(IN_RATE);
     if (!tab) return B2A_ECUDA;
     auto k = fir_mma_kernel<IN_RATE, CH>;
-    static bool attr_done = false;    // idempotent; a benign race only repeats the call
-    if (!attr_done) {
+    // the dynamic shared-memory opt-in is a per-device function attribute: remember which devices have it
+    // (idempotent; a benign race only repeats the call)
+    static unsigned long long attr_mask = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !((attr_mask >> dev) & 1ull)) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fir_mma_kernel)");
-        attr_done = true;
+        if (dev >= 0 && dev < 64) attr_mask |= 1ull << dev;
     }
     FirMmaArgs a;
     a.in = (const unsigned char*)d_in; a.out_s16 = d_out_s16; a.energy = d_energy; a.btab = tab;

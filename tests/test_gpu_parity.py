@@ -361,3 +361,16 @@ def test_pipeline_degenerate_clips(ops, T):
     assert abs(len(pcm) - len(y)) <= 16 and np.abs(pcm[:len(y) - 16].astype(int) - y[:len(y) - 16].astype(int)).max() <= 1
     ref = wl.log_mel_spectrogram(pcm.astype(np.float32) / 32768.0, 80).numpy()
     assert np.abs(r.mel.cpu().numpy() - ref).max() <= MEL_TOL
+
+
+def test_second_device_in_one_process(ops, T):
+    """per-device table caches and kernel attributes: the same process drives cuda:1 after cuda:0 (needs 2 GPUs)"""
+    if T.cuda.device_count() < 2:
+        pytest.skip("single-GPU box")
+    from audio_processor_b200 import synth
+    x0 = synth.synth_clip(7, 44100, 2, 10.0, 0.3, device="cuda:0")
+    r0 = ops.pipeline(x0, 44100, n_mels=80, min_silence_len=1000, silence_thresh=-40, keep_silence=200)
+    with T.cuda.device(1):
+        x1 = x0.to("cuda:1")
+        r1 = ops.pipeline(x1, 44100, n_mels=80, min_silence_len=1000, silence_thresh=-40, keep_silence=200)
+        assert r1.kept == r0.kept and T.equal(r1.pcm.cpu(), r0.pcm.cpu()) and T.equal(r1.mel.cpu(), r0.mel.cpu())
