@@ -13,6 +13,7 @@
 #include "b2a_tables.cuh"
 #include "f16_bits.h"
 #include "fir_mma.cuh"
+#include "fir_umma.cuh"
 #include "fir_design.h"
 #include "mel_design.h"
 
@@ -178,6 +179,57 @@ const uint2* get_fir_mma_table(int in_rate) {
     if (e == cudaSuccess) e = cudaMemcpy(d, h.data(), h.size() * sizeof(uint2), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cuda_fail(e, "FIR table upload"); return nullptr; }
     g_fir_mma[key] = d;
+    return d;
+}
+
+
+// ---- filter bank of the tcgen05 FIR (fir_umma.cuh) as UMMA B operand tiles ---------------------------------------
+// [block b][k-step s] -> one [N = 32][K = 16] f16 tile in the canonical no-swizzle K-major layout
+// (element (n, k) at (n / 8) * 256 + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2 bytes): rows 0-15 = T_hi, rows 16-31 =
+// T_lo of output J = 16 b + n % 16, column k <-> plane column kbp(b) + 16 s + k, i.e.
+// T = 2^12 * tap[phase(J)][kbp(b) + 16 s + k - (J DEC) / L]  (zero outside the filter).
+template <int IN_RATE>
+static void build_fir_umma_table(const float* taps /*[L][TAPS]*/, std::vector<unsigned char>& out) {
+    using G = FirUmmaGeom<IN_RATE>;
+    out.assign((size_t)G::B_BYTES, 0);
+    for (int b = 0; b < G::BBLOCKS; b++)
+        for (int s = 0; s < G::KS; s++)
+            for (int n = 0; n < 32; n++)
+                for (int k = 0; k < 16; k++) {
+                    const int J = 16 * b + (n & 15);
+                    const int BJ = (J * G::DEC) / G::L, ph = (J * G::DEC) % G::L;
+                    const int i = G::kbp(b) + 16 * s + k - BJ;
+                    float T = 0.0f;
+                    if (i >= 0 && i < G::TAPS) T = taps[(size_t)ph * G::TAPS + i] * (float)(1 << kFmTapShift);
+                    const uint16_t hi = b2a_f16::f32_to_f16(T);
+                    const uint16_t lo = b2a_f16::f32_to_f16(T - b2a_f16::f16_to_f32(hi));
+                    const uint16_t v = n < 16 ? hi : lo;
+                    const size_t off = ((size_t)b * G::KS + s) * kFuBTile + (n / 8) * kFuBSbo + (k / 8) * kFuBLbo + (n % 8) * 16 + (k % 8) * 2;
+                    memcpy(&out[off], &v, 2);
+                }
+}
+
+static std::map<std::pair<int, int>, const uint4*> g_fir_umma;   // (device, in_rate)
+
+const uint4* get_fir_umma_table(int in_rate) {
+    const ResampleDesign* des = get_resample_design(in_rate, kSampleRate);
+    if (!des) return nullptr;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { cuda_fail(e, "cudaGetDevice"); return nullptr; }
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto key = std::make_pair(dev, in_rate);
+    auto it = g_fir_umma.find(key);
+    if (it != g_fir_umma.end()) return it->second;
+    std::vector<unsigned char> h;
+    if (in_rate == 44100) build_fir_umma_table<44100>(des->h_taps, h);
+    else if (in_rate == 48000) build_fir_umma_table<48000>(des->h_taps, h);
+    else { set_error("no tcgen05 FIR table for %d Hz", in_rate); return nullptr; }
+    uint4* d = nullptr;
+    e = cudaMalloc((void**)&d, h.size());
+    if (e == cudaSuccess) e = cudaMemcpy(d, h.data(), h.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cuda_fail(e, "FIR table upload"); return nullptr; }
+    g_fir_umma[key] = d;
     return d;
 }
 

@@ -5,14 +5,25 @@ namespace b2a {
 
 int fir_mma_run_44100(int channels, const void*, i64, int16_t*, u64*, FirMmaPlan*, cudaStream_t);
 int fir_mma_run_48000(int channels, const void*, i64, int16_t*, u64*, FirMmaPlan*, cudaStream_t);
+int fir_umma_run_44100(const void*, i64, int16_t*, u64*, FirMmaPlan*, cudaStream_t);
+int fir_umma_run_48000(const void*, i64, int16_t*, u64*, FirMmaPlan*, cudaStream_t);
 
 // returns 1 if the tensor-core kernel was launched (plan filled), 0 if this input has no fast path, <0 on error.
 // s16 input at the two named rates only; the pre-quantisation float output and every other case use the
-// table-driven kernel in resample.cu.
+// table-driven kernel in resample.cu.  Clips too short for a 128-run tile of the tcgen05 kernel fall back to the
+// 16-run tiles of the mma.sync kernel.
 int fir_fast_dispatch(int in_rate, int fmt, int channels, const void* d_in, i64 n_in, int16_t* d_out_s16, float* d_out_f32,
                       u64* d_energy, FirMmaPlan* plan, cudaStream_t stream) {
     plan->out_lo = plan->out_hi = 0;
     if (fmt != B2A_FMT_S16 || d_out_f32 || (channels != 1 && channels != 2)) return 0;
+    // stereo: tcgen05 kernel (fir_umma.cuh); B2A_FIR_IMPL=mma selects the legacy mma.sync kernel (A/B profiling only)
+    static const bool legacy = [] { const char* e = getenv("B2A_FIR_IMPL"); return e && e[0] == 'm'; }();
+    if (channels == 2 && !legacy) {
+        int rc = 0;
+        if (in_rate == 44100) rc = fir_umma_run_44100(d_in, n_in, d_out_s16, d_energy, plan, stream);
+        else if (in_rate == 48000) rc = fir_umma_run_48000(d_in, n_in, d_out_s16, d_energy, plan, stream);
+        if (rc != 0) return rc;                       // launched, or failed; 0 = clip shorter than one 128-run tile
+    }
     if (in_rate == 44100) return fir_mma_run_44100(channels, d_in, n_in, d_out_s16, d_energy, plan, stream);
     if (in_rate == 48000) return fir_mma_run_48000(channels, d_in, n_in, d_out_s16, d_energy, plan, stream);
     return 0;

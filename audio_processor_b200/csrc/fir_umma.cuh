@@ -1,0 +1,473 @@
+// fir_umma.cuh — fused s16 stereo decode + downmix + polyphase FIR on the 5th-generation tensor cores
+// (tcgen05.mma, accumulators in TMEM), sm_100a, for the two named rate pairs (44.1 kHz and 48 kHz -> 16 kHz).
+//
+// Replaces libswresample's swr_convert inner loop behind the reference's
+//   ffmpeg -ar 16000 -ac 1 -c:a pcm_s16le   (app/services/audio_processor.py:912-923).
+//
+// Same banded-Toeplitz formulation and the same exact f16 splits as fir_mma.cuh (the legacy mma.sync kernel, still
+// used for mono input), re-laid for tcgen05:
+//   run   = 160 consecutive outputs = 10 blocks of 16 (one block = one millisecond at 16 kHz); a run consumes S input
+//           frames (441 / 480), so 128 consecutive runs are 128 rows that share one filter matrix per block;
+//   block b of 128 runs:  D[128 x 32] = X[128 x 16 KS] * [T_hi | T_lo][16 KS x 32]
+//           X = (hv + lo / 128) with v = L + R = 128 hv + lo  (two f16 planes, both exact, accumulated into the same D),
+//           T = 2^12 taps split T_hi + T_lo (f16 each); columns 0-15 hold the T_hi partial sums of the 16 outputs,
+//           columns 16-31 the T_lo ones; the epilogue adds the two and scales by 2^-6.
+//   => 2 KS tcgen05.mma (M128 N32 K16, kind::f16, f32 accumulate) per block, issued by one thread.
+//
+// Shared memory cannot hold a tile's planes (128 rows x 544 frames x 4 B = 278 KB) next to the 92 KB filter bank, and a
+// raw tile (226 KB) does not fit either, so the planes are a COLUMN RING: 4 pieces of 64 columns for all 128 rows
+// (+ one mirrored chunk so that a K=16 operand never straddles the wrap).  Converter warps read the input straight
+// from global memory (16-byte loads, a half-warp covers 256 contiguous bytes of one row), realign by the row's
+// frame offset (441 r is not a multiple of 4 frames), split into the two planes and store them in the canonical
+// no-swizzle K-major layout the MMA reads: [chunk of 8 columns][row][16 B], chunk pitch LBO = 2064 B (128 rows x
+// 16 B + 16 B of padding that spreads the stores over the banks), 8-row groups SBO = 128 B apart.  Layout, descriptor
+// fields and the TMEM accumulator layout (lane = row, column = n) are pinned on hardware by tools/probes/umma_probe.cu.
+//
+// Roles (416 threads, one persistent CTA per SM), coupled only by mbarriers:
+//   warps 0-3   epilogue: warp q owns TMEM lanes 32q..32q+31 (thread = run): tcgen05.ld 32 columns, add the two
+//               halves, round half-to-even + clip to s16 (swr audioconvert), two 16-byte stores, and the exact uint64
+//               sum of squares of the millisecond for the silence detector;
+//   warp  4     TMEM allocation; lane 0 issues every tcgen05.mma and the tcgen05.commit arrivals that release ring
+//               pieces back to the converters and hand accumulators to the epilogue (ring of 4 accumulators);
+//   warps 5-12  converters (global -> registers -> planes), one piece prefetched in registers.
+#pragma once
+#include "fir_mma.cuh"
+
+namespace b2a {
+
+constexpr int kFuRT = 128;                 // runs per tile = UMMA M
+constexpr int kFuPiece = 64;               // columns per ring piece
+constexpr int kFuLbo = kFuRT * 16 + 16;    // bytes between consecutive chunks of a plane
+constexpr int kFuSbo = 128;                // bytes between 8-row groups inside a chunk
+constexpr int kFuEpiWarps = 4;
+constexpr int kFuCvtWarps = 8;
+constexpr int kFuMmaWarp = 4;              // warp 4 issues the MMAs; warps 5-7 only pad its warpgroup (setmaxnreg is per warpgroup)
+constexpr int kFuCvtWarp0 = 8;             // converters = warpgroups 2 and 3
+constexpr int kFuThreads = (kFuCvtWarp0 + kFuCvtWarps) * 32;
+constexpr int kFuRegsEpi = 72, kFuRegsMma = 24, kFuRegsCvt = 208;   // 128 (72 + 24 + 2 x 208) = 65536 registers
+constexpr int kFuRowPairs = kFuRT / 2 / kFuCvtWarps;            // row pairs per converter warp and piece (4)
+constexpr int kFuDSlots = 4;               // accumulator ring
+constexpr int kFuDCols = 32;               // TMEM columns per accumulator: [T_hi sums | T_lo sums]
+constexpr int kFuTmemCols = kFuDSlots * kFuDCols;               // 128 (power of two >= 32)
+constexpr int kFuBTile = 32 * 16 * 2;      // one [N = 32][K = 16] f16 operand tile
+constexpr int kFuBLbo = 128, kFuBSbo = 256;                     // B tile: [n group of 8][k chunk][8 rows][16 B]
+constexpr unsigned kFuIdesc = (1u << 4) | ((unsigned)(kFuDCols >> 3) << 17) | ((unsigned)(kFuRT >> 4) << 24);   // f16 x f16 -> f32, K-major, N = 32, M = 128
+
+template <int IN_RATE>
+struct FirUmmaGeom {
+    using TR = FirMmaTraits<IN_RATE>;
+    static constexpr int L = TR::L, DEC = TR::M, TAPS = TR::TAPS;
+    static constexpr int CENTER = (TAPS - 1) / 2;
+    static constexpr int S = kFmNout * DEC / L;                          // input frames per run (441 / 480)
+    static constexpr int kb(int b) { return (16 * b * DEC) / L; }        // exact window start of block b (column of the row)
+    static constexpr int kbp(int b) { return kb(b) & ~7; }               // rounded down to a chunk
+    static constexpr int window() {                                      // columns a block's window must span from kbp(b)
+        int w = 0;
+        for (int b = 0; b < kFmBlocks; b++)
+            for (int j = 0; j < 16; j++) {
+                const int e = ((16 * b + j) * DEC) / L - kbp(b) + TAPS;
+                w = e > w ? e : w;
+            }
+        return w;
+    }
+    static constexpr int KS = (window() + 15) / 16;                      // k-steps per block (9 / 10)
+    static constexpr int COLS = kbp(kFmBlocks - 1) + 16 * KS;            // columns of a row the MMAs read
+    static constexpr int PIECES = (COLS + kFuPiece - 1) / kFuPiece;      // ring pieces per tile (9 / 10)
+    // one phase (48 kHz: L = 1) and chunk-aligned block windows => every block has the same filter matrix
+    static constexpr bool SHARED_B = (L == 1) && (kb(1) % 8 == 0);
+    static constexpr int BBLOCKS = SHARED_B ? 1 : kFmBlocks;
+    static constexpr int B_BYTES = BBLOCKS * KS * kFuBTile;
+    // ring: 4 pieces next to the 92 KB filter bank of 44.1 kHz; 6 where the bank is one shared 10 KB matrix (48 kHz,
+    // whose 160-column windows span 4 pieces)
+    static constexpr int RING_PIECES = SHARED_B ? 6 : 4;
+    static constexpr int RING_CHUNKS = RING_PIECES * kFuPiece / 8;       // chunks of 8 columns (+ 1 mirror of chunk 0)
+    static constexpr int PLANE_BYTES = (RING_CHUNKS + 1) * kFuLbo;
+    static constexpr int NBARS = 2 * RING_PIECES + 2 * kFuDSlots;
+    static constexpr int SMEM_BYTES = 2 * PLANE_BYTES + B_BYTES + NBARS * kFmBarBytes + 16;
+    static constexpr int piece_last(int b) { return (kbp(b) + 16 * KS - 1) / kFuPiece; }                       // last piece block b reads
+    static constexpr int pieces_free_after(int b) { return b + 1 < kFmBlocks ? kbp(b + 1) / kFuPiece : PIECES; }  // pieces no later block reads
+    static constexpr int max_span() {
+        int m = 0;
+        for (int b = 0; b < kFmBlocks; b++) { const int s = piece_last(b) - kbp(b) / kFuPiece + 1; m = s > m ? s : m; }
+        return m;
+    }
+    static_assert(max_span() < RING_PIECES, "a block window must leave one ring piece for the converters to run ahead");
+    static_assert(SMEM_BYTES <= 232448, "shared-memory budget (227 KB per CTA)");
+    static_assert((S * kFuRT * 4) % 16 == 0, "a tile advances the input by whole 16-byte quads");
+};
+
+struct FirUmmaArgs {
+    const unsigned char* in;     // interleaved s16 stereo frames
+    int16_t* out_s16;            // nullable
+    u64* energy;                 // nullable
+    const uint4* btab;           // filter bank as UMMA B tiles, see build_fir_umma_table
+    i64 run0;                    // first run of tile 0 (>= 1 so that every window starts inside the clip)
+    i64 tile_lo, tile_hi;        // tiles [tile_lo, tile_hi): tile t = runs [run0 + 128 t, +128)
+};
+
+// ---- primitives (GPU: PTX; TEST-ONLY emulation: tests/emu) -------------------------------------------------
+#ifndef B2A_EMU
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(saddr_t slot, unsigned cols) {      // whole warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(unsigned base, unsigned cols) {   // whole warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
+}
+// shared-memory matrix descriptor, SWIZZLE_NONE, K-major: start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | version 1 << 46
+__device__ __forceinline__ unsigned long long umma_desc(saddr_t addr, unsigned lbo, unsigned sbo) {
+    return (unsigned long long)((addr >> 4) & 0x3fffu) | ((unsigned long long)((lbo >> 4) & 0x3fffu) << 16) |
+           ((unsigned long long)((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+// D[tmem] (+)= A[smem] * B[smem], M = 128, N = 32, K = 16, one thread issues
+__device__ __forceinline__ void umma_f16(unsigned d_tmem, saddr_t a, unsigned a_lbo, unsigned a_sbo, saddr_t b, unsigned b_lbo, unsigned b_sbo,
+                                         unsigned idesc, unsigned accumulate) {
+    const unsigned long long da = umma_desc(a, a_lbo, a_sbo), db = umma_desc(b, b_lbo, b_sbo);
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on the mbarrier once every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(saddr_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 TMEM columns of this warp's 32 lanes (thread = lane) -> registers; waits for the data
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned hfma2_bits(unsigned a, unsigned b, unsigned c) {
+    unsigned r;
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+// round half-to-even and saturate to int16 in one conversion (libswresample: lrintf + av_clip_int16)
+__device__ __forceinline__ int quant_s16_sat(float v) {
+    short q;
+    asm("cvt.rni.sat.s16.f32 %0, %1;" : "=h"(q) : "f"(v));
+    return (int)q;
+}
+template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::evict_last.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+#else
+static float g_emu_tmem[128][512];
+static inline void fence_proxy_async() {}
+static inline void tc_fence_before() {}
+static inline void tc_fence_after() {}
+static inline void tmem_alloc(saddr_t slot, unsigned) { *(unsigned*)slot = 0u; }
+static inline void tmem_dealloc(unsigned, unsigned) {}
+static inline void umma_f16(unsigned d_tmem, saddr_t a, unsigned a_lbo, unsigned a_sbo, saddr_t b, unsigned b_lbo, unsigned b_sbo,
+                            unsigned idesc, unsigned accumulate) {
+    const int n_dim = (int)((idesc >> 17) & 0x3fu) * 8, col0 = (int)(d_tmem & 0xffffu);
+    for (int row = 0; row < 128; row++)
+        for (int n = 0; n < n_dim; n++) {
+            float acc = accumulate ? g_emu_tmem[row][col0 + n] : 0.0f;
+            for (int k = 0; k < 16; k++) {
+                const unsigned short av = *(const unsigned short*)(a + (size_t)(k / 8) * a_lbo + (size_t)(row / 8) * a_sbo + (row % 8) * 16 + (k % 8) * 2);
+                const unsigned short bv = *(const unsigned short*)(b + (size_t)(k / 8) * b_lbo + (size_t)(n / 8) * b_sbo + (n % 8) * 16 + (k % 8) * 2);
+                acc += emu::f16_to_f32(av) * emu::f16_to_f32(bv);
+            }
+            g_emu_tmem[row][col0 + n] = acc;
+        }
+}
+static inline void umma_commit(saddr_t bar) { mbar_arrive(bar); }
+static inline void tmem_ld32(unsigned taddr, unsigned (&r)[32]) {
+    const int lane0 = (int)(taddr >> 16), col0 = (int)(taddr & 0xffffu);
+    for (int j = 0; j < 32; j++) r[j] = __float_as_uint(g_emu_tmem[lane0 + emu_lane()][col0 + j]);
+}
+static inline unsigned hfma2_bits(unsigned a, unsigned b, unsigned c) {
+    auto one = [](unsigned short x, unsigned short y, unsigned short z) {
+        return (unsigned)emu::f32_to_f16((float)((double)emu::f16_to_f32(x) * (double)emu::f16_to_f32(y) + (double)emu::f16_to_f32(z)));
+    };
+    return one((unsigned short)(a & 0xffff), (unsigned short)(b & 0xffff), (unsigned short)(c & 0xffff)) |
+           (one((unsigned short)(a >> 16), (unsigned short)(b >> 16), (unsigned short)(c >> 16)) << 16);
+}
+static inline int quant_s16_sat(float v) { return quant_s16(v); }
+template <int N> static inline void reg_dealloc() {}
+template <int N> static inline void reg_alloc() {}
+static inline uint4 ldg_stream(const uint4* p) { return *p; }
+#endif
+
+// ---- converter role ------------------------------------------------------------------------------------------
+// Warp cw owns the rows of residue class c = cw & 3 (row = c + 4 j): j in [8 g, 8 g + 8) with g = cw >> 2, as 4 row
+// pairs: half-warp h of row pair i converts row c + 4 (8 g + h) + 8 i, lane q (of 16) the piece's columns 4q..4q+3.
+// Those columns are frames f0 + 4q .. +3 with f0 = 4 G0 + SH, SH the same for the whole class: words SH..3 of quad
+// G0 + q and words 0..SH-1 of quad G0 + q + 1.  For SH > 0 lane q loads quad G0 + q + 1 and takes the 4 - SH words of
+// the quad before it from lane q - 1; lane 0 takes them from lane 15's quad of the PREVIOUS piece (kept in `old`), so
+// no quad is loaded twice.  Two register sets alternate and every register quad is refilled with the piece two ahead
+// the moment it is consumed: 48-64 KB of loads are in flight per SM without a shared-memory staging ring.
+template <int W> __device__ __forceinline__ unsigned quad_word(const uint4& v) { return W == 0 ? v.x : W == 1 ? v.y : W == 2 ? v.z : v.w; }
+
+template <int IN_RATE, int SH>
+__device__ __forceinline__ void fir_umma_convert(const FirUmmaArgs& a, unsigned char* ring, saddr_t pf0, saddr_t pe0, int cw, int lane,
+                                                 i64 tile0, i64 stride, int n_tiles) {
+    using G = FirUmmaGeom<IN_RATE>;
+    constexpr int NW = SH == 0 ? 0 : 4 - SH;                  // words taken from the previous quad
+    constexpr int ROWQ = 8 * G::S / 4;                        // quads between rows 8 apart
+    constexpr unsigned KHV = 65536u + (0x6400u << 7);         // dp2a bias: (u >> 7) = f16 bits of 1024 + (hv + 512), u & 127 = lo
+    const int h = lane >> 4, q = lane & 15;
+    const int row0 = (cw & 3) + 4 * (2 * kFuRowPairs * (cw >> 2) + h);
+    auto qptr = [&](i64 tile) {                                // this lane's quad of piece 0 of the tile (row row0)
+        const i64 run = a.run0 + tile * kFuRT + row0;
+        return (const uint4*)a.in + (((run * G::S - G::CENTER) >> 2) + (SH ? 1 : 0) + q);
+    };
+    const int total = n_tiles * G::PIECES;
+    if (total == 0) return;
+    uint4 set[2][kFuRowPairs];
+    unsigned old[kFuRowPairs][NW ? NW : 1];
+    // load cursor: piece l_P (= piece being converted + 2 in the steady state)
+    i64 l_tile = tile0;
+    int l_p = 0, l_P = 0;
+    const uint4* lp = qptr(l_tile);
+    auto advance_load = [&]() {
+        l_P++;
+        lp += kFuPiece / 4;
+        if (++l_p == G::PIECES) { l_p = 0; l_tile += stride; lp = qptr(l_tile); }
+    };
+    // convert cursor
+    i64 c_tile = tile0;
+    int c_p = 0, c_P = 0, slot = 0;
+    unsigned pe_parity = 1;                                    // passes on first use of a slot
+    // converts the piece held in `cur` and refills each register quad with the piece two ahead as soon as it is consumed
+    auto step = [&](uint4 (&cur)[kFuRowPairs]) {
+        mbar_wait(pe0 + (unsigned)(slot * kFmBarBytes), pe_parity);      // MMAs done with the old contents of the slot
+        if (SH != 0 && c_p == 0) {
+            // first piece of a tile: new rows, the quad before the piece comes from memory (lane 15 only)
+            const uint4* cp = qptr(c_tile);
+#pragma unroll
+            for (int i = 0; i < kFuRowPairs; i++) {
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (q == 15) v = ldg_stream(cp - 16 + i * ROWQ);
+                if (NW > 0) old[i][0] = SH == 1 ? v.y : SH == 2 ? v.z : v.w;
+                if (NW > 1) old[i][1] = SH == 1 ? v.z : v.w;
+                if (NW > 2) old[i][2] = v.w;
+            }
+        }
+        unsigned char* dst0 = ring + (size_t)(slot * (kFuPiece / 8) + (q >> 1)) * kFuLbo + (q & 1) * 8 + row0 * 16;
+        const bool refill = l_P < total;
+#pragma unroll
+        for (int i = 0; i < kFuRowPairs; i++) {
+            const uint4 v = cur[i];
+            unsigned f[4];
+            if (SH == 0) { f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
+            else {
+                const unsigned cw_[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int w = 0; w < NW; w++) {
+                    const unsigned x = cw_[SH + w];                          // word SH + w of this lane's quad
+                    f[w] = __shfl_sync(0xffffffffu, q == 15 ? old[i][w] : x, (q + 15) & 15, 16);
+                    old[i][w] = x;                                           // lane 15: handed to lane 0 in the next piece
+                }
+#pragma unroll
+                for (int w = NW; w < 4; w++) f[w] = cw_[w - NW];
+            }
+            const unsigned u0 = (unsigned)__dp2a_lo((int)f[0], 0x0101, (int)KHV), u1 = (unsigned)__dp2a_lo((int)f[1], 0x0101, (int)KHV);
+            const unsigned u2 = (unsigned)__dp2a_lo((int)f[2], 0x0101, (int)KHV), u3 = (unsigned)__dp2a_lo((int)f[3], 0x0101, (int)KHV);
+            const unsigned hva = hsub2_bits(((u1 >> 7) << 16) + (u0 >> 7), 0x66006600u);       // (1024 + hv + 512) - 1536
+            const unsigned hvb = hsub2_bits(((u3 >> 7) << 16) + (u2 >> 7), 0x66006600u);
+            const unsigned loa = hfma2_bits((((u1 & 127u) << 16) | (u0 & 127u)) | 0x64006400u, 0x20002000u, 0xC800C800u);   // (1024 + lo) / 128 - 8
+            const unsigned lob = hfma2_bits((((u3 & 127u) << 16) | (u2 & 127u)) | 0x64006400u, 0x20002000u, 0xC800C800u);
+            unsigned char* d = dst0 + i * 128;
+            *(uint2*)d = make_uint2(hva, hvb);
+            *(uint2*)(d + G::PLANE_BYTES) = make_uint2(loa, lob);
+            if (slot == 0 && q < 2) {                                         // mirror of ring chunk 0 behind the last chunk
+                *(uint2*)(d + (size_t)G::RING_CHUNKS * kFuLbo) = make_uint2(hva, hvb);
+                *(uint2*)(d + (size_t)G::RING_CHUNKS * kFuLbo + G::PLANE_BYTES) = make_uint2(loa, lob);
+            }
+            if (refill) cur[i] = ldg_stream(lp + i * ROWQ);                   // (the asm's memory clobber keeps it behind the stores)
+        }
+        advance_load();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pf0 + (unsigned)(slot * kFmBarBytes));
+        c_P++;
+        if (++slot == G::RING_PIECES) { slot = 0; pe_parity ^= 1u; }
+        if (++c_p == G::PIECES) { c_p = 0; c_tile += stride; }
+    };
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        if (l_P < total) {
+#pragma unroll
+            for (int i = 0; i < kFuRowPairs; i++) set[k][i] = ldg_stream(lp + i * ROWQ);
+        }
+        advance_load();
+    }
+    while (true) {
+        step(set[0]);
+        if (c_P >= total) break;
+        step(set[1]);
+        if (c_P >= total) break;
+    }
+}
+
+template <int IN_RATE>
+__global__ void __launch_bounds__(kFuThreads, 1) fir_umma_kernel(const FirUmmaArgs a) {
+    using G = FirUmmaGeom<IN_RATE>;
+    B2A_DYN_SMEM(smem);
+    unsigned char* ring = smem;                                   // [plane hv | plane lo][RING_CHUNKS + 1][kFuLbo]
+    unsigned char* btab = smem + 2 * G::PLANE_BYTES;               // [BBLOCKS][KS][kFuBTile]
+    const saddr_t bars = smem_addr(btab + G::B_BYTES);
+    unsigned* tmem_slot = (unsigned*)(btab + G::B_BYTES + G::NBARS * kFmBarBytes);
+    // barrier slots: PF piece full (converters -> MMA), PE piece free (MMA commit -> converters),
+    //                DF accumulator full (MMA commit -> epilogue), DE accumulator drained (epilogue -> MMA)
+    auto PF = [&](int s) { return bars + (unsigned)((0 + s) * kFmBarBytes); };
+    auto PE = [&](int s) { return bars + (unsigned)((G::RING_PIECES + s) * kFmBarBytes); };
+    auto DF = [&](int s) { return bars + (unsigned)((2 * G::RING_PIECES + s) * kFmBarBytes); };
+    auto DE = [&](int s) { return bars + (unsigned)((2 * G::RING_PIECES + kFuDSlots + s) * kFmBarBytes); };
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    for (int i = tid; i < G::B_BYTES / 16; i += kFuThreads) ((uint4*)btab)[i] = a.btab[i];
+    fence_proxy_async();                                          // the tensor core reads shared memory through the async proxy
+    if (tid == 0) {
+        for (int s = 0; s < G::RING_PIECES; s++) { mbar_init(PF(s), kFuCvtWarps); mbar_init(PE(s), 1); }
+        for (int s = 0; s < kFuDSlots; s++) { mbar_init(DF(s), 1); mbar_init(DE(s), kFuEpiWarps); }
+        mbar_fence_init();
+    }
+    if (warp == kFuMmaWarp) tmem_alloc(smem_addr(tmem_slot), kFuTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem = *tmem_slot;
+
+    const i64 tile0 = a.tile_lo + blockIdx.x;
+    const i64 stride = gridDim.x;
+    const int n_tiles = tile0 < a.tile_hi ? (int)((a.tile_hi - tile0 + stride - 1) / stride) : 0;
+
+    if (warp < kFuEpiWarps) {
+        // ===================================== epilogue: thread = run =====================================
+        reg_dealloc<kFuRegsEpi>();
+        const int row = warp * 32 + lane;
+        int n = 0;                                                // accumulator counter
+        for (int it = 0; it < n_tiles; it++) {
+            const i64 run = a.run0 + (tile0 + it * stride) * kFuRT + row;
+#pragma unroll 1
+            for (int b = 0; b < kFmBlocks; b++, n++) {
+                const int ds = n % kFuDSlots;
+                mbar_wait(DF(ds), (unsigned)((n / kFuDSlots) & 1));
+                tc_fence_after();
+                unsigned r[32];
+                tmem_ld32(tmem + ((unsigned)(warp * 32) << 16) + (unsigned)(ds * kFuDCols), r);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(DE(ds));               // the accumulator may be overwritten
+                unsigned w[8];
+                u64 e = 0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int q0 = quant_s16_sat((__uint_as_float(r[2 * j]) + __uint_as_float(r[16 + 2 * j])) * (1.0f / 64.0f));
+                    const int q1 = quant_s16_sat((__uint_as_float(r[2 * j + 1]) + __uint_as_float(r[16 + 2 * j + 1])) * (1.0f / 64.0f));
+                    w[j] = (unsigned)(q0 & 0xffff) | ((unsigned)q1 << 16);
+                    e += (u64)((unsigned)(q0 * q0) + (unsigned)(q1 * q1));    // two squares fit 32 bits (<= 2^31)
+                }
+                if (a.out_s16) {
+                    uint4* dst = (uint4*)(a.out_s16 + run * kFmNout + 16 * b);
+                    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                }
+                if (a.energy) a.energy[run * kFmBlocks + b] = e;  // the block's 16 outputs are exactly one millisecond
+            }
+        }
+    } else if (warp < kFuCvtWarp0) {
+        // ===================================== MMA issuer (one thread) =====================================
+        reg_dealloc<kFuRegsMma>();
+        if (warp == kFuMmaWarp && lane == 0) {
+            const saddr_t ring_s = smem_addr(ring), btab_s = smem_addr(btab);
+            int ready = 0, freed = 0, n = 0;                      // pieces known full / released, accumulator counter
+            for (int it = 0; it < n_tiles; it++) {
+                const int piece0 = it * G::PIECES;                // global piece counter of the tile's piece 0
+#pragma unroll 1
+                for (int b = 0; b < kFmBlocks; b++, n++) {
+                    const int need = piece0 + G::piece_last(b) + 1;
+                    for (; ready < need; ready++) mbar_wait(PF(ready % G::RING_PIECES), (unsigned)((ready / G::RING_PIECES) & 1));
+                    const int ds = n % kFuDSlots;
+                    mbar_wait(DE(ds), (unsigned)(((n / kFuDSlots) & 1) ^ 1));      // passes on first use
+                    tc_fence_after();
+                    const unsigned d_tmem = tmem + (unsigned)(ds * kFuDCols);
+                    const int chunk0 = piece0 * (kFuPiece / 8) + G::kbp(b) / 8;     // global chunk index of the window start
+                    const saddr_t bt = btab_s + (unsigned)((G::SHARED_B ? 0 : b) * G::KS * kFuBTile);
+#pragma unroll
+                    for (int s = 0; s < G::KS; s++) {
+                        // the last ring chunk pairs with the mirror of chunk 0 stored right behind it
+                        const saddr_t ahv = ring_s + (unsigned)(((chunk0 + 2 * s) % G::RING_CHUNKS) * kFuLbo);
+                        umma_f16(d_tmem, ahv, kFuLbo, kFuSbo, bt + (unsigned)(s * kFuBTile), kFuBLbo, kFuBSbo, kFuIdesc, s > 0 ? 1u : 0u);
+                        umma_f16(d_tmem, ahv + G::PLANE_BYTES, kFuLbo, kFuSbo, bt + (unsigned)(s * kFuBTile), kFuBLbo, kFuBSbo, kFuIdesc, 1u);
+                    }
+                    umma_commit(DF(ds));
+                    const int free_to = piece0 + G::pieces_free_after(b);
+                    for (; freed < free_to; freed++) umma_commit(PE(freed % G::RING_PIECES));
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ============================ converters: global -> registers -> planes ============================
+        reg_alloc<kFuRegsCvt>();
+        const int cw = warp - kFuCvtWarp0;
+        // the frame offset of a row against the 16-byte grid depends on the row only through row % 4: a warp owns rows
+        // of one residue class, so the realignment is a compile-time constant of its code path
+        const int sh = (int)(((a.run0 + (cw & 3)) * G::S - G::CENTER) & 3);
+        if (sh == 0) fir_umma_convert<IN_RATE, 0>(a, ring, PF(0), PE(0), cw, lane, tile0, stride, n_tiles);
+        else if (sh == 1) fir_umma_convert<IN_RATE, 1>(a, ring, PF(0), PE(0), cw, lane, tile0, stride, n_tiles);
+        else if (sh == 2) fir_umma_convert<IN_RATE, 2>(a, ring, PF(0), PE(0), cw, lane, tile0, stride, n_tiles);
+        else fir_umma_convert<IN_RATE, 3>(a, ring, PF(0), PE(0), cw, lane, tile0, stride, n_tiles);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kFuMmaWarp) tmem_dealloc(tmem, kFuTmemCols);
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+const uint4* get_fir_umma_table(int in_rate);   // device table for the current device (b2a_host.cu); nullptr + error on failure
+
+template <int IN_RATE>
+static inline int fir_umma_launch(const void* d_in, i64 n_in, int16_t* d_out_s16, u64* d_energy, FirMmaPlan* plan, cudaStream_t stream) {
+    using G = FirUmmaGeom<IN_RATE>;
+    plan->out_lo = plan->out_hi = 0;
+    // tile t = runs [1 + 128 t, +128): run >= 1 keeps every window start inside the clip.  The converters read whole
+    // pieces plus one quad: frames up to S run - CENTER + 64 PIECES + 3 of the tile's last row must exist.
+    const i64 run0 = 1;
+    const i64 last_need = (i64)G::CENTER * -1 + (i64)kFuPiece * G::PIECES + 4;             // relative to S * run of the last row
+    // largest T with S (run0 + 128 T - 1) + last_need <= n_in
+    const i64 room = n_in - last_need - (i64)G::S * (run0 - 1);
+    const i64 tiles = room >= (i64)G::S * kFuRT ? room / ((i64)G::S * kFuRT) : 0;
+    if (tiles <= 0) return 0;
+    const uint4* tab = get_fir_umma_table(IN_RATE);
+    if (!tab) return B2A_ECUDA;
+    auto k = fir_umma_kernel<IN_RATE>;
+    static unsigned long long attr_mask = 0;                     // per-device opt-in, see fir_mma_launch
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !((attr_mask >> dev) & 1ull)) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fir_umma_kernel)");
+        if (dev >= 0 && dev < 64) attr_mask |= 1ull << dev;
+    }
+    FirUmmaArgs a;
+    a.in = (const unsigned char*)d_in; a.out_s16 = d_out_s16; a.energy = d_energy; a.btab = tab;
+    a.run0 = run0; a.tile_lo = 0; a.tile_hi = tiles;
+    unsigned grid = (unsigned)(tiles < 148 ? tiles : 148);       // persistent: one CTA per SM
+    if (const char* gs = getenv("B2A_FIR_GRID")) {               // test knob: few CTAs => many tiles per CTA
+        const int gv = atoi(gs);
+        if (gv > 0 && (unsigned)gv < grid) grid = (unsigned)gv;
+    }
+    B2A_LAUNCH(k, grid, kFuThreads, G::SMEM_BYTES, stream, a);
+    B2A_CHECK_LAUNCH("fir_umma_kernel");
+    plan->out_lo = run0 * kFmNout;
+    plan->out_hi = (run0 + tiles * kFuRT) * kFmNout;
+    return 1;
+}
+
+}  // namespace b2a
