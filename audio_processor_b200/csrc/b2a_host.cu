@@ -184,29 +184,32 @@ const uint2* get_fir_mma_table(int in_rate) {
 
 
 // ---- filter bank of the tcgen05 FIR (fir_umma.cuh) as UMMA B operand tiles ---------------------------------------
-// [block b][k-step s] -> one [N = 32][K = 16] f16 tile in the canonical no-swizzle K-major layout
+// [class c][block b][k-step s] -> one [N = 32][K = 16] f16 tile in the canonical no-swizzle K-major layout
 // (element (n, k) at (n / 8) * 256 + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2 bytes): rows 0-15 = T_hi, rows 16-31 =
-// T_lo of output J = 16 b + n % 16, column k <-> plane column kbp(b) + 16 s + k, i.e.
-// T = 2^12 * tap[phase(J)][kbp(b) + 16 s + k - (J DEC) / L]  (zero outside the filter).
+// T_lo of output J = 16 b + n % 16.  Plane column j of a class-c row is input frame S run - CENTER - shift(c) + j, so
+// column k of the tile (j = kbp(b) + 16 s + k) carries
+// T = 2^12 * tap[phase(J)][j - shift(c) - (J DEC) / L]  (zero outside the filter).
 template <int IN_RATE>
 static void build_fir_umma_table(const float* taps /*[L][TAPS]*/, std::vector<unsigned char>& out) {
     using G = FirUmmaGeom<IN_RATE>;
-    out.assign((size_t)G::B_BYTES, 0);
-    for (int b = 0; b < G::BBLOCKS; b++)
-        for (int s = 0; s < G::KS; s++)
-            for (int n = 0; n < 32; n++)
-                for (int k = 0; k < 16; k++) {
-                    const int J = 16 * b + (n & 15);
-                    const int BJ = (J * G::DEC) / G::L, ph = (J * G::DEC) % G::L;
-                    const int i = G::kbp(b) + 16 * s + k - BJ;
-                    float T = 0.0f;
-                    if (i >= 0 && i < G::TAPS) T = taps[(size_t)ph * G::TAPS + i] * (float)(1 << kFmTapShift);
-                    const uint16_t hi = b2a_f16::f32_to_f16(T);
-                    const uint16_t lo = b2a_f16::f32_to_f16(T - b2a_f16::f16_to_f32(hi));
-                    const uint16_t v = n < 16 ? hi : lo;
-                    const size_t off = ((size_t)b * G::KS + s) * kFuBTile + (n / 8) * kFuBSbo + (k / 8) * kFuBLbo + (n % 8) * 16 + (k % 8) * 2;
-                    memcpy(&out[off], &v, 2);
-                }
+    out.assign((size_t)kFuClasses * G::B_BYTES, 0);
+    for (int c = 0; c < kFuClasses; c++)
+        for (int b = 0; b < G::BBLOCKS; b++)
+            for (int s = 0; s < G::KS; s++)
+                for (int n = 0; n < 32; n++)
+                    for (int k = 0; k < 16; k++) {
+                        const int J = 16 * b + (n & 15);
+                        const int BJ = (J * G::DEC) / G::L, ph = (J * G::DEC) % G::L;
+                        const int i = G::kbp(b) + 16 * s + k - G::shift(kFuRun0, c) - BJ;
+                        float T = 0.0f;
+                        if (i >= 0 && i < G::TAPS) T = taps[(size_t)ph * G::TAPS + i] * (float)(1 << kFmTapShift);
+                        const uint16_t hi = b2a_f16::f32_to_f16(T);
+                        const uint16_t lo = b2a_f16::f32_to_f16(T - b2a_f16::f16_to_f32(hi));
+                        const uint16_t v = n < 16 ? hi : lo;
+                        const size_t off = (size_t)c * G::B_BYTES + ((size_t)b * G::KS + s) * kFuBTile + (n / 8) * kFuBSbo + (k / 8) * kFuBLbo +
+                                           (n % 8) * 16 + (k % 8) * 2;
+                        memcpy(&out[off], &v, 2);
+                    }
 }
 
 static std::map<std::pair<int, int>, const uint4*> g_fir_umma;   // (device, in_rate)

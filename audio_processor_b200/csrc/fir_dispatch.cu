@@ -3,8 +3,8 @@
 
 namespace b2a {
 
-int fir_mma_run_44100(int channels, const void*, i64, int16_t*, u64*, FirMmaPlan*, cudaStream_t);
-int fir_mma_run_48000(int channels, const void*, i64, int16_t*, u64*, FirMmaPlan*, cudaStream_t);
+int fir_mma_run_44100(int channels, const void*, i64, int16_t*, u64*, FirMmaPlan*, cudaStream_t, i64 first_tile);
+int fir_mma_run_48000(int channels, const void*, i64, int16_t*, u64*, FirMmaPlan*, cudaStream_t, i64 first_tile);
 int fir_umma_run_44100(const void*, i64, int16_t*, u64*, FirMmaPlan*, cudaStream_t);
 int fir_umma_run_48000(const void*, i64, int16_t*, u64*, FirMmaPlan*, cudaStream_t);
 
@@ -16,17 +16,30 @@ int fir_fast_dispatch(int in_rate, int fmt, int channels, const void* d_in, i64 
                       u64* d_energy, FirMmaPlan* plan, cudaStream_t stream) {
     plan->out_lo = plan->out_hi = 0;
     if (fmt != B2A_FMT_S16 || d_out_f32 || (channels != 1 && channels != 2)) return 0;
-    // stereo: tcgen05 kernel (fir_umma.cuh); B2A_FIR_IMPL=mma selects the legacy mma.sync kernel (A/B profiling only)
+    // stereo: tcgen05 kernel (fir_umma.cuh) over whole 512-run spans, then the mma.sync kernel (16-run tiles) over what is
+    // left behind the last span; B2A_FIR_IMPL=mma selects the mma.sync kernel alone (A/B profiling only)
     static const bool legacy = [] { const char* e = getenv("B2A_FIR_IMPL"); return e && e[0] == 'm'; }();
+    i64 first_tile = 1;
+    FirMmaPlan head;
+    head.out_lo = head.out_hi = 0;
     if (channels == 2 && !legacy) {
         int rc = 0;
-        if (in_rate == 44100) rc = fir_umma_run_44100(d_in, n_in, d_out_s16, d_energy, plan, stream);
-        else if (in_rate == 48000) rc = fir_umma_run_48000(d_in, n_in, d_out_s16, d_energy, plan, stream);
-        if (rc != 0) return rc;                       // launched, or failed; 0 = clip shorter than one 128-run tile
+        if (in_rate == 44100) rc = fir_umma_run_44100(d_in, n_in, d_out_s16, d_energy, &head, stream);
+        else if (in_rate == 48000) rc = fir_umma_run_48000(d_in, n_in, d_out_s16, d_energy, &head, stream);
+        if (rc < 0) return rc;
+        if (rc > 0) first_tile = head.out_hi / (kFmRT * kFmNout);          // span ends are multiples of 16 runs
     }
-    if (in_rate == 44100) return fir_mma_run_44100(channels, d_in, n_in, d_out_s16, d_energy, plan, stream);
-    if (in_rate == 48000) return fir_mma_run_48000(channels, d_in, n_in, d_out_s16, d_energy, plan, stream);
-    return 0;
+    int rc = 0;
+    if (in_rate == 44100) rc = fir_mma_run_44100(channels, d_in, n_in, d_out_s16, d_energy, plan, stream, first_tile);
+    else if (in_rate == 48000) rc = fir_mma_run_48000(channels, d_in, n_in, d_out_s16, d_energy, plan, stream, first_tile);
+    if (rc < 0) return rc;
+    if (head.out_hi > head.out_lo) {
+        // outputs [head.out_lo, head.out_hi) came from the tcgen05 kernel, [plan->out_lo, plan->out_hi) (if any) follow directly
+        plan->out_lo = head.out_lo;
+        if (rc == 0) plan->out_hi = head.out_hi;
+        return 1;
+    }
+    return rc;
 }
 
 }  // namespace b2a

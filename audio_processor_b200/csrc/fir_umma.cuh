@@ -16,26 +16,38 @@
 //
 // Shared memory cannot hold a tile's planes (128 rows x 544 frames x 4 B = 278 KB) next to the 92 KB filter bank, and a
 // raw tile (226 KB) does not fit either, so the planes are a COLUMN RING: 4 pieces of 64 columns for all 128 rows
-// (+ one mirrored chunk so that a K=16 operand never straddles the wrap).  Converter warps read the input straight
-// from global memory (16-byte loads, a half-warp covers 256 contiguous bytes of one row), realign by the row's
-// frame offset (441 r is not a multiple of 4 frames), split into the two planes and store them in the canonical
-// no-swizzle K-major layout the MMA reads: [chunk of 8 columns][row][16 B], chunk pitch LBO = 2064 B (128 rows x
-// 16 B + 16 B of padding that spreads the stores over the banks), 8-row groups SBO = 128 B apart.  Layout, descriptor
-// fields and the TMEM accumulator layout (lane = row, column = n) are pinned on hardware by tools/probes/umma_probe.cu.
+// (+ one mirrored chunk so that a K=16 operand never straddles the wrap), stored in the canonical no-swizzle K-major
+// layout the MMA reads: [chunk of 8 columns][row][16 B], chunk pitch LBO = 2064 B (128 rows x 16 B + 16 B of padding
+// that spreads the stores over the banks), 8-row groups SBO = 128 B apart.  Layout, descriptor fields and the TMEM
+// accumulator layout (lane = row, column = n) are pinned on hardware by tools/probes/umma_probe.cu.
 //
-// Roles (416 threads, one persistent CTA per SM), coupled only by mbarriers:
+// Alignment.  A run is 441 frames = 1764 bytes, so consecutive runs sit at four different offsets against the 16-byte
+// grid of the input.  A tile therefore takes every FOURTH run (class c = run % 4, rows 7056 bytes apart: 16-byte
+// aligned), and its plane columns start SH_c frames before the filter origin so that every row of the tile begins on a
+// quad; the shift is folded into the class's own copy of the filter bank (4 x 92 KB in global memory, one resident per
+// CTA).  Converter warps then read aligned 16-byte quads straight from global memory (a half-warp covers 256 contiguous
+// bytes of one row; no shared-memory staging ring), split them into the two planes and store 8 bytes per plane.  CTA b
+// works on class b % 4, and CTAs b..b+3 walk the same 512-run spans together, so the rows' overlapping halos meet in L2.
+//
+// Roles (512 threads = 4 warpgroups, one persistent CTA per SM), coupled only by mbarriers; registers are moved between
+// the warpgroups with setmaxnreg:
 //   warps 0-3   epilogue: warp q owns TMEM lanes 32q..32q+31 (thread = run): tcgen05.ld 32 columns, add the two
-//               halves, round half-to-even + clip to s16 (swr audioconvert), two 16-byte stores, and the exact uint64
+//               halves, round half-to-even + saturate to s16 (swr audioconvert), two 16-byte stores, and the exact uint64
 //               sum of squares of the millisecond for the silence detector;
 //   warp  4     TMEM allocation; lane 0 issues every tcgen05.mma and the tcgen05.commit arrivals that release ring
 //               pieces back to the converters and hand accumulators to the epilogue (ring of 4 accumulators);
-//   warps 5-12  converters (global -> registers -> planes), one piece prefetched in registers.
+//               warps 5-7 only pad the warpgroup;
+//   warps 8-15  converters (global -> registers -> planes): two register sets alternate and every register quad is
+//               refilled with the piece two ahead the moment it is consumed (48-64 KB of loads in flight per SM).
 #pragma once
 #include "fir_mma.cuh"
 
 namespace b2a {
 
 constexpr int kFuRT = 128;                 // runs per tile = UMMA M
+constexpr int kFuClasses = 4;              // a tile takes every 4th run (class = run % 4)
+constexpr int kFuSpan = kFuRT * kFuClasses;   // runs covered by the 4 tiles of a span
+constexpr int kFuRun0 = 16;                // first run of span 0 (multiple of 16: the head is the legacy kernel's first tile)
 constexpr int kFuPiece = 64;               // columns per ring piece
 constexpr int kFuLbo = kFuRT * 16 + 16;    // bytes between consecutive chunks of a plane
 constexpr int kFuSbo = 128;                // bytes between 8-row groups inside a chunk
@@ -65,11 +77,13 @@ struct FirUmmaGeom {
         int w = 0;
         for (int b = 0; b < kFmBlocks; b++)
             for (int j = 0; j < 16; j++) {
-                const int e = ((16 * b + j) * DEC) / L - kbp(b) + TAPS;
+                const int e = ((16 * b + j) * DEC) / L - kbp(b) + TAPS + 3;     // + the largest class shift
                 w = e > w ? e : w;
             }
         return w;
     }
+    // class c = rows run0 + c + 4 r: frames by which the rows' first quad precedes the filter origin S run - CENTER
+    static constexpr int shift(int run0, int c) { return (int)((((long long)(run0 + c)) * S - CENTER) & 3); }
     static constexpr int KS = (window() + 15) / 16;                      // k-steps per block (9 / 10)
     static constexpr int COLS = kbp(kFmBlocks - 1) + 16 * KS;            // columns of a row the MMAs read
     static constexpr int PIECES = (COLS + kFuPiece - 1) / kFuPiece;      // ring pieces per tile (9 / 10)
@@ -93,16 +107,16 @@ struct FirUmmaGeom {
     }
     static_assert(max_span() < RING_PIECES, "a block window must leave one ring piece for the converters to run ahead");
     static_assert(SMEM_BYTES <= 232448, "shared-memory budget (227 KB per CTA)");
-    static_assert((S * kFuRT * 4) % 16 == 0, "a tile advances the input by whole 16-byte quads");
+    static constexpr int ROWQ = S;                                       // quads between consecutive rows of a tile (4 runs)
+    static constexpr int SPANQ = kFuSpan * S / 4;                        // quads between consecutive spans
 };
 
 struct FirUmmaArgs {
     const unsigned char* in;     // interleaved s16 stereo frames
     int16_t* out_s16;            // nullable
     u64* energy;                 // nullable
-    const uint4* btab;           // filter bank as UMMA B tiles, see build_fir_umma_table
-    i64 run0;                    // first run of tile 0 (>= 1 so that every window starts inside the clip)
-    i64 tile_lo, tile_hi;        // tiles [tile_lo, tile_hi): tile t = runs [run0 + 128 t, +128)
+    const uint4* btab;           // [class][B_BYTES] filter banks as UMMA B tiles, see build_fir_umma_table
+    int spans;                   // spans [0, spans): span t = runs [kFuRun0 + 512 t, +512); CTA b converts class b % 4 of spans b / 4, b / 4 + gridDim / 4, ..
 };
 
 // ---- primitives (GPU: PTX; TEST-ONLY emulation: tests/emu) -------------------------------------------------
@@ -202,85 +216,43 @@ static inline uint4 ldg_stream(const uint4* p) { return *p; }
 #endif
 
 // ---- converter role ------------------------------------------------------------------------------------------
-// Warp cw owns the rows of residue class c = cw & 3 (row = c + 4 j): j in [8 g, 8 g + 8) with g = cw >> 2, as 4 row
-// pairs: half-warp h of row pair i converts row c + 4 (8 g + h) + 8 i, lane q (of 16) the piece's columns 4q..4q+3.
-// Those columns are frames f0 + 4q .. +3 with f0 = 4 G0 + SH, SH the same for the whole class: words SH..3 of quad
-// G0 + q and words 0..SH-1 of quad G0 + q + 1.  For SH > 0 lane q loads quad G0 + q + 1 and takes the 4 - SH words of
-// the quad before it from lane q - 1; lane 0 takes them from lane 15's quad of the PREVIOUS piece (kept in `old`), so
-// no quad is loaded twice.  Two register sets alternate and every register quad is refilled with the piece two ahead
-// the moment it is consumed: 48-64 KB of loads are in flight per SM without a shared-memory staging ring.
-template <int W> __device__ __forceinline__ unsigned quad_word(const uint4& v) { return W == 0 ? v.x : W == 1 ? v.y : W == 2 ? v.z : v.w; }
-
-template <int IN_RATE, int SH>
-__device__ __forceinline__ void fir_umma_convert(const FirUmmaArgs& a, unsigned char* ring, saddr_t pf0, saddr_t pe0, int cw, int lane,
-                                                 i64 tile0, i64 stride, int n_tiles) {
+// Warp cw, row pair i, half-warp h: row 16 i + 2 cw + h; lane q (of 16) converts the piece's columns 4q..4q+3 = one
+// aligned quad of the input.  Two register sets alternate; every register quad is refilled with the piece two ahead as
+// soon as it is consumed.
+template <int IN_RATE>
+__device__ __forceinline__ void fir_umma_convert(const uint4* __restrict__ in_q, unsigned char* ring, saddr_t pf0, saddr_t pe0, int cw, int lane,
+                                                 i64 span_stride_q, int total) {
     using G = FirUmmaGeom<IN_RATE>;
-    constexpr int NW = SH == 0 ? 0 : 4 - SH;                  // words taken from the previous quad
-    constexpr int ROWQ = 8 * G::S / 4;                        // quads between rows 8 apart
+    constexpr int ROWQ = 16 * G::ROWQ;                        // quads between the rows of consecutive row pairs (16 rows)
     constexpr unsigned KHV = 65536u + (0x6400u << 7);         // dp2a bias: (u >> 7) = f16 bits of 1024 + (hv + 512), u & 127 = lo
-    const int h = lane >> 4, q = lane & 15;
-    const int row0 = (cw & 3) + 4 * (2 * kFuRowPairs * (cw >> 2) + h);
-    auto qptr = [&](i64 tile) {                                // this lane's quad of piece 0 of the tile (row row0)
-        const i64 run = a.run0 + tile * kFuRT + row0;
-        return (const uint4*)a.in + (((run * G::S - G::CENTER) >> 2) + (SH ? 1 : 0) + q);
-    };
-    const int total = n_tiles * G::PIECES;
     if (total == 0) return;
-    uint4 set[2][kFuRowPairs];
-    unsigned old[kFuRowPairs][NW ? NW : 1];
-    // load cursor: piece l_P (= piece being converted + 2 in the steady state)
-    i64 l_tile = tile0;
+    const int h = lane >> 4, q = lane & 15;
+    const int row0 = 2 * cw + h;
+    const uint4* tbase = in_q + (i64)row0 * G::ROWQ + q;      // this lane's quad of piece 0 of the CTA's first tile
+    const uint4* lp = tbase;                                  // load cursor: piece l_P (= piece being converted + 2 in the steady state)
     int l_p = 0, l_P = 0;
-    const uint4* lp = qptr(l_tile);
     auto advance_load = [&]() {
         l_P++;
         lp += kFuPiece / 4;
-        if (++l_p == G::PIECES) { l_p = 0; l_tile += stride; lp = qptr(l_tile); }
+        if (++l_p == G::PIECES) { l_p = 0; tbase += span_stride_q; lp = tbase; }
     };
-    // convert cursor
-    i64 c_tile = tile0;
-    int c_p = 0, c_P = 0, slot = 0;
-    unsigned pe_parity = 1;                                    // passes on first use of a slot
-    // converts the piece held in `cur` and refills each register quad with the piece two ahead as soon as it is consumed
+    int c_P = 0, slot = 0;
+    unsigned pe_parity = 1;                                   // passes on first use of a slot
+    uint4 set[2][kFuRowPairs];
     auto step = [&](uint4 (&cur)[kFuRowPairs]) {
         mbar_wait(pe0 + (unsigned)(slot * kFmBarBytes), pe_parity);      // MMAs done with the old contents of the slot
-        if (SH != 0 && c_p == 0) {
-            // first piece of a tile: new rows, the quad before the piece comes from memory (lane 15 only)
-            const uint4* cp = qptr(c_tile);
-#pragma unroll
-            for (int i = 0; i < kFuRowPairs; i++) {
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (q == 15) v = ldg_stream(cp - 16 + i * ROWQ);
-                if (NW > 0) old[i][0] = SH == 1 ? v.y : SH == 2 ? v.z : v.w;
-                if (NW > 1) old[i][1] = SH == 1 ? v.z : v.w;
-                if (NW > 2) old[i][2] = v.w;
-            }
-        }
         unsigned char* dst0 = ring + (size_t)(slot * (kFuPiece / 8) + (q >> 1)) * kFuLbo + (q & 1) * 8 + row0 * 16;
         const bool refill = l_P < total;
 #pragma unroll
         for (int i = 0; i < kFuRowPairs; i++) {
             const uint4 v = cur[i];
-            unsigned f[4];
-            if (SH == 0) { f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
-            else {
-                const unsigned cw_[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int w = 0; w < NW; w++) {
-                    const unsigned x = cw_[SH + w];                          // word SH + w of this lane's quad
-                    f[w] = __shfl_sync(0xffffffffu, q == 15 ? old[i][w] : x, (q + 15) & 15, 16);
-                    old[i][w] = x;                                           // lane 15: handed to lane 0 in the next piece
-                }
-#pragma unroll
-                for (int w = NW; w < 4; w++) f[w] = cw_[w - NW];
-            }
-            const unsigned u0 = (unsigned)__dp2a_lo((int)f[0], 0x0101, (int)KHV), u1 = (unsigned)__dp2a_lo((int)f[1], 0x0101, (int)KHV);
-            const unsigned u2 = (unsigned)__dp2a_lo((int)f[2], 0x0101, (int)KHV), u3 = (unsigned)__dp2a_lo((int)f[3], 0x0101, (int)KHV);
+            const unsigned u0 = (unsigned)__dp2a_lo((int)v.x, 0x0101, (int)KHV), u1 = (unsigned)__dp2a_lo((int)v.y, 0x0101, (int)KHV);
+            const unsigned u2 = (unsigned)__dp2a_lo((int)v.z, 0x0101, (int)KHV), u3 = (unsigned)__dp2a_lo((int)v.w, 0x0101, (int)KHV);
             const unsigned hva = hsub2_bits(((u1 >> 7) << 16) + (u0 >> 7), 0x66006600u);       // (1024 + hv + 512) - 1536
             const unsigned hvb = hsub2_bits(((u3 >> 7) << 16) + (u2 >> 7), 0x66006600u);
             const unsigned loa = hfma2_bits((((u1 & 127u) << 16) | (u0 & 127u)) | 0x64006400u, 0x20002000u, 0xC800C800u);   // (1024 + lo) / 128 - 8
             const unsigned lob = hfma2_bits((((u3 & 127u) << 16) | (u2 & 127u)) | 0x64006400u, 0x20002000u, 0xC800C800u);
-            unsigned char* d = dst0 + i * 128;
+            unsigned char* d = dst0 + i * 256;
             *(uint2*)d = make_uint2(hva, hvb);
             *(uint2*)(d + G::PLANE_BYTES) = make_uint2(loa, lob);
             if (slot == 0 && q < 2) {                                         // mirror of ring chunk 0 behind the last chunk
@@ -295,7 +267,6 @@ __device__ __forceinline__ void fir_umma_convert(const FirUmmaArgs& a, unsigned 
         if (lane == 0) mbar_arrive(pf0 + (unsigned)(slot * kFmBarBytes));
         c_P++;
         if (++slot == G::RING_PIECES) { slot = 0; pe_parity ^= 1u; }
-        if (++c_p == G::PIECES) { c_p = 0; c_tile += stride; }
     };
 #pragma unroll
     for (int k = 0; k < 2; k++) {
@@ -329,7 +300,8 @@ __global__ void __launch_bounds__(kFuThreads, 1) fir_umma_kernel(const FirUmmaAr
     auto DE = [&](int s) { return bars + (unsigned)((2 * G::RING_PIECES + kFuDSlots + s) * kFmBarBytes); };
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    for (int i = tid; i < G::B_BYTES / 16; i += kFuThreads) ((uint4*)btab)[i] = a.btab[i];
+    const int cls = blockIdx.x & (kFuClasses - 1);              // this CTA's run class
+    for (int i = tid; i < G::B_BYTES / 16; i += kFuThreads) ((uint4*)btab)[i] = a.btab[(size_t)cls * (G::B_BYTES / 16) + i];
     fence_proxy_async();                                          // the tensor core reads shared memory through the async proxy
     if (tid == 0) {
         for (int s = 0; s < G::RING_PIECES; s++) { mbar_init(PF(s), kFuCvtWarps); mbar_init(PE(s), 1); }
@@ -342,9 +314,9 @@ __global__ void __launch_bounds__(kFuThreads, 1) fir_umma_kernel(const FirUmmaAr
     tc_fence_after();
     const unsigned tmem = *tmem_slot;
 
-    const i64 tile0 = a.tile_lo + blockIdx.x;
-    const i64 stride = gridDim.x;
-    const int n_tiles = tile0 < a.tile_hi ? (int)((a.tile_hi - tile0 + stride - 1) / stride) : 0;
+    const int span0 = blockIdx.x / kFuClasses, span_stride = gridDim.x / kFuClasses;     // gridDim.x is a multiple of 4
+    const int n_tiles = span0 < a.spans ? (a.spans - span0 + span_stride - 1) / span_stride : 0;
+    const i64 run_base = kFuRun0 + (i64)span0 * kFuSpan + cls;   // row r of the CTA's tile `it` is run run_base + it * span_stride * 512 + 4 r
 
     if (warp < kFuEpiWarps) {
         // ===================================== epilogue: thread = run =====================================
@@ -352,7 +324,7 @@ __global__ void __launch_bounds__(kFuThreads, 1) fir_umma_kernel(const FirUmmaAr
         const int row = warp * 32 + lane;
         int n = 0;                                                // accumulator counter
         for (int it = 0; it < n_tiles; it++) {
-            const i64 run = a.run0 + (tile0 + it * stride) * kFuRT + row;
+            const i64 run = run_base + (i64)it * span_stride * kFuSpan + kFuClasses * row;
 #pragma unroll 1
             for (int b = 0; b < kFmBlocks; b++, n++) {
                 const int ds = n % kFuDSlots;
@@ -416,13 +388,9 @@ __global__ void __launch_bounds__(kFuThreads, 1) fir_umma_kernel(const FirUmmaAr
         // ============================ converters: global -> registers -> planes ============================
         reg_alloc<kFuRegsCvt>();
         const int cw = warp - kFuCvtWarp0;
-        // the frame offset of a row against the 16-byte grid depends on the row only through row % 4: a warp owns rows
-        // of one residue class, so the realignment is a compile-time constant of its code path
-        const int sh = (int)(((a.run0 + (cw & 3)) * G::S - G::CENTER) & 3);
-        if (sh == 0) fir_umma_convert<IN_RATE, 0>(a, ring, PF(0), PE(0), cw, lane, tile0, stride, n_tiles);
-        else if (sh == 1) fir_umma_convert<IN_RATE, 1>(a, ring, PF(0), PE(0), cw, lane, tile0, stride, n_tiles);
-        else if (sh == 2) fir_umma_convert<IN_RATE, 2>(a, ring, PF(0), PE(0), cw, lane, tile0, stride, n_tiles);
-        else fir_umma_convert<IN_RATE, 3>(a, ring, PF(0), PE(0), cw, lane, tile0, stride, n_tiles);
+        // first quad of row 0 of the CTA's first tile: the class shift makes it land on the 16-byte grid
+        const i64 f0 = run_base * G::S - G::CENTER - G::shift(kFuRun0, cls);
+        fir_umma_convert<IN_RATE>((const uint4*)a.in + (f0 >> 2), ring, PF(0), PE(0), cw, lane, (i64)span_stride * G::SPANQ, n_tiles * G::PIECES);
     }
     tc_fence_before();
     __syncthreads();
@@ -436,14 +404,12 @@ template <int IN_RATE>
 static inline int fir_umma_launch(const void* d_in, i64 n_in, int16_t* d_out_s16, u64* d_energy, FirMmaPlan* plan, cudaStream_t stream) {
     using G = FirUmmaGeom<IN_RATE>;
     plan->out_lo = plan->out_hi = 0;
-    // tile t = runs [1 + 128 t, +128): run >= 1 keeps every window start inside the clip.  The converters read whole
-    // pieces plus one quad: frames up to S run - CENTER + 64 PIECES + 3 of the tile's last row must exist.
-    const i64 run0 = 1;
-    const i64 last_need = (i64)G::CENTER * -1 + (i64)kFuPiece * G::PIECES + 4;             // relative to S * run of the last row
-    // largest T with S (run0 + 128 T - 1) + last_need <= n_in
-    const i64 room = n_in - last_need - (i64)G::S * (run0 - 1);
-    const i64 tiles = room >= (i64)G::S * kFuRT ? room / ((i64)G::S * kFuRT) : 0;
-    if (tiles <= 0) return 0;
+    // span t = runs [16 + 512 t, +512).  A row reads whole pieces from its (shifted) first quad: frames up to
+    // S run - CENTER + 64 PIECES - 1 of the span's last run must exist.
+    const i64 last_need = -(i64)G::CENTER + (i64)kFuPiece * G::PIECES;                 // relative to S * run of the last row
+    const i64 room = n_in - last_need - (i64)G::S * (kFuRun0 - 1);
+    const i64 spans = room >= (i64)G::S * kFuSpan ? room / ((i64)G::S * kFuSpan) : 0;
+    if (spans <= 0) return 0;
     const uint4* tab = get_fir_umma_table(IN_RATE);
     if (!tab) return B2A_ECUDA;
     auto k = fir_umma_kernel<IN_RATE>;
@@ -457,16 +423,16 @@ static inline int fir_umma_launch(const void* d_in, i64 n_in, int16_t* d_out_s16
     }
     FirUmmaArgs a;
     a.in = (const unsigned char*)d_in; a.out_s16 = d_out_s16; a.energy = d_energy; a.btab = tab;
-    a.run0 = run0; a.tile_lo = 0; a.tile_hi = tiles;
-    unsigned grid = (unsigned)(tiles < 148 ? tiles : 148);       // persistent: one CTA per SM
+    a.spans = (int)spans;
+    i64 lanes = spans < 37 ? spans : 37;                         // persistent: 4 CTAs (one per class) per span lane, 148 SMs
     if (const char* gs = getenv("B2A_FIR_GRID")) {               // test knob: few CTAs => many tiles per CTA
-        const int gv = atoi(gs);
-        if (gv > 0 && (unsigned)gv < grid) grid = (unsigned)gv;
+        const int gv = (atoi(gs) + kFuClasses - 1) / kFuClasses;
+        if (gv > 0 && gv < lanes) lanes = gv;
     }
-    B2A_LAUNCH(k, grid, kFuThreads, G::SMEM_BYTES, stream, a);
+    B2A_LAUNCH(k, (unsigned)(lanes * kFuClasses), kFuThreads, G::SMEM_BYTES, stream, a);
     B2A_CHECK_LAUNCH("fir_umma_kernel");
-    plan->out_lo = run0 * kFmNout;
-    plan->out_hi = (run0 + tiles * kFuRT) * kFmNout;
+    plan->out_lo = (i64)kFuRun0 * kFmNout;
+    plan->out_hi = ((i64)kFuRun0 + spans * kFuSpan) * kFmNout;
     return 1;
 }
 
