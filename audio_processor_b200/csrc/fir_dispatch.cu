@@ -16,9 +16,13 @@ int fir_fast_dispatch(int in_rate, int fmt, int channels, const void* d_in, i64 
                       u64* d_energy, FirMmaPlan* plan, cudaStream_t stream) {
     plan->out_lo = plan->out_hi = 0;
     if (fmt != B2A_FMT_S16 || d_out_f32 || (channels != 1 && channels != 2)) return 0;
-    // stereo: tcgen05 kernel (fir_umma.cuh) over whole 512-run spans, then the mma.sync kernel (16-run tiles) over what is
-    // left behind the last span; B2A_FIR_IMPL=mma selects the mma.sync kernel alone (A/B profiling only)
-    static const bool legacy = [] { const char* e = getenv("B2A_FIR_IMPL"); return e && e[0] == 'm'; }();
+    // Stereo input has two kernels: the mma.sync kernel (fir_mma.cuh, 16-run tiles fed by a bulk-TMA ring; the default)
+    // and the tcgen05 kernel (fir_umma.cuh, 512-run spans, accumulators in TMEM).  The tcgen05 kernel is parity-green on
+    // B200 but, fed by register-staged global loads, streams the input at ~2 TB/s (profiles/r01_fir_umma.md) and is
+    // therefore opt-in: B2A_FIR_IMPL=umma.  When selected it takes the whole spans and hands what is left behind the last
+    // span to the mma.sync kernel.
+    const char* impl = getenv("B2A_FIR_IMPL");
+    const bool legacy = !(impl && impl[0] == 'u');
     i64 first_tile = 1;
     FirMmaPlan head;
     head.out_lo = head.out_hi = 0;

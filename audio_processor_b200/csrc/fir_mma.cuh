@@ -127,8 +127,10 @@ __device__ __forceinline__ void mbar_arrive(saddr_t bar) {
 __device__ __forceinline__ void mbar_wait(saddr_t bar, unsigned parity) {
     unsigned ok;
     do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        // the suspend-time hint parks the warp in hardware until the phase completes (or the hint expires) instead of
+        // re-issuing the poll through the MIO queue, which the shared-memory stores of the working warps need
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
     } while (!ok);
 }
 // 1-D bulk copy global -> shared (TMA engine), completion counted on the mbarrier

@@ -154,6 +154,7 @@ def test_emu_fir_tcgen05_tiles(emu, rate, grid, monkeypatch):
     """index logic of the tcgen05 FIR (fir_umma.cuh) under the functional emulation of tcgen05.mma / TMEM: column ring
     with wrap and mirrored chunk, class tiles (every 4th run, shifted filter banks), accumulator ring, 3 spans over 4-8 persistent
     CTAs, and the hand-over to the mma.sync kernel behind the last span"""
+    monkeypatch.setenv("B2A_FIR_IMPL", "umma")
     monkeypatch.setenv("B2A_FIR_GRID", grid)
     S = 441 if rate == 44100 else 480
     rng = np.random.default_rng(rate)

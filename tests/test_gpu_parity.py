@@ -69,6 +69,7 @@ def test_resample_tcgen05_tiles(ops, T, rate, spans, grid, monkeypatch):
     ring wrap, mbarrier phases, accumulator ring) + the mma.sync kernel behind the last span, against the float64 restatement (<= 1 LSB), the real libswresample (>= 99.8 % identical) and the
     exact per-millisecond energies"""
     from oracle import resample_oracle as ro, swr_ref
+    monkeypatch.setenv("B2A_FIR_IMPL", "umma")
     if grid:
         monkeypatch.setenv("B2A_FIR_GRID", grid)
     S = 441 if rate == 44100 else 480
