@@ -7,6 +7,8 @@ int fir_mma_run_44100(int channels, const void*, i64, int16_t*, u64*, FirMmaPlan
 int fir_mma_run_48000(int channels, const void*, i64, int16_t*, u64*, FirMmaPlan*, cudaStream_t, i64 first_tile);
 int fir_umma_run_44100(const void*, i64, int16_t*, u64*, FirMmaPlan*, cudaStream_t);
 int fir_umma_run_48000(const void*, i64, int16_t*, u64*, FirMmaPlan*, cudaStream_t);
+int fir_tmem_run_44100(const void*, i64, int16_t*, u64*, FirMmaPlan*, cudaStream_t);
+int fir_tmem_run_48000(const void*, i64, int16_t*, u64*, FirMmaPlan*, cudaStream_t);
 
 // returns 1 if the tensor-core kernel was launched (plan filled), 0 if this input has no fast path, <0 on error.
 // s16 input at the two named rates only; the pre-quantisation float output and every other case use the
@@ -22,14 +24,15 @@ int fir_fast_dispatch(int in_rate, int fmt, int channels, const void* d_in, i64 
     // therefore opt-in: B2A_FIR_IMPL=umma.  When selected it takes the whole spans and hands what is left behind the last
     // span to the mma.sync kernel.
     const char* impl = getenv("B2A_FIR_IMPL");
-    const bool legacy = !(impl && impl[0] == 'u');
+    const bool legacy = !(impl && (impl[0] == 'u' || impl[0] == 't'));
+    const bool tmem = impl && impl[0] == 't';                 // B2A_FIR_IMPL=tmem: TMA-fed kernel with the planes in TMEM (fir_tmem.cuh)
     i64 first_tile = 1;
     FirMmaPlan head;
     head.out_lo = head.out_hi = 0;
     if (channels == 2 && !legacy) {
         int rc = 0;
-        if (in_rate == 44100) rc = fir_umma_run_44100(d_in, n_in, d_out_s16, d_energy, &head, stream);
-        else if (in_rate == 48000) rc = fir_umma_run_48000(d_in, n_in, d_out_s16, d_energy, &head, stream);
+        if (in_rate == 44100) rc = tmem ? fir_tmem_run_44100(d_in, n_in, d_out_s16, d_energy, &head, stream) : fir_umma_run_44100(d_in, n_in, d_out_s16, d_energy, &head, stream);
+        else if (in_rate == 48000) rc = tmem ? fir_tmem_run_48000(d_in, n_in, d_out_s16, d_energy, &head, stream) : fir_umma_run_48000(d_in, n_in, d_out_s16, d_energy, &head, stream);
         if (rc < 0) return rc;
         if (rc > 0) first_tile = head.out_hi / (kFmRT * kFmNout);          // span ends are multiples of 16 runs
     }

@@ -151,6 +151,67 @@ __global__ void __launch_bounds__(160, 1) rate_kernel(int reps, int naccs, int n
     if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512u) : "memory");
 }
 
+
+// TS-mode correctness: A[128 x 32] f16 is written to TMEM by the four quadrant warps (thread = row, register j = column
+// j = K elements 2j (low half), 2j+1 (high half)) starting at column a_col0; D = A[:, k0:k0+16] * B0 for two k0 values
+// (k0 = 0 -> A column a_col0, k0 = 8 -> A column a_col0 + 4: a 4-column-aligned operand address)
+__global__ void __launch_bounds__(160, 1) ts_kernel(const unsigned* a_words /*[128][16]*/, const unsigned char* b_img, unsigned idesc, int a_col0, float* out /*[128][32]*/) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long bar_mem;
+    __shared__ unsigned tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < kBTile; i += blockDim.x) smem[i] = b_img[i];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const unsigned bar = smem_u32(&bar_mem);
+    if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(128u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tbase = tmem_base_s;
+    if (warp < 4) {
+        unsigned r[16];
+        for (int j = 0; j < 16; j++) r[j] = a_words[tid * 16 + j];
+        const unsigned taddr = tbase + ((unsigned)(warp * 32) << 16) + 64 + a_col0;
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                     ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                       "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 128) {
+        const uint64_t db = make_desc(smem_u32(smem), 128, 256);
+        for (int v = 0; v < 2; v++) {
+            const unsigned a_tm = tbase + 64 + a_col0 + 4 * v, d_tm = tbase + 16 * v;
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                         ::"r"(d_tm), "r"(a_tm), "l"(db), "r"(idesc), "r"(0u) : "memory");
+        }
+        umma_commit(bar);
+    }
+    if (warp < 4) {
+        mbar_wait(bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int c0 = 0; c0 < 32; c0 += 16) {
+            unsigned r[16];
+            const unsigned taddr = tbase + ((unsigned)(warp * 32) << 16) + c0;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                         : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            for (int j = 0; j < 16; j++) out[tid * 32 + c0 + j] = __uint_as_float(r[j]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(128u) : "memory");
+}
+
 static unsigned make_idesc(int m, int n) {
     // c_format f32 = 1 at [4,6); a/b format f16 = 0; K-major both; n>>3 at [17,23); m>>4 at [24,29)
     return (1u << 4) | ((unsigned)(n >> 3) << 17) | ((unsigned)(m >> 4) << 24);
@@ -213,10 +274,41 @@ int main() {
             printf("  sample row 9: got"); for (int c = 0; c < 8; c++) printf(" %g", out[9 * 64 + c]); printf(" | want"); for (int c = 0; c < 8; c++) printf(" %g", ref[9 * 64 + c]); printf("\n");
         }
     }
+    {   // TS mode: A from TMEM
+        std::vector<unsigned> aw(128 * 16);
+        for (int r = 0; r < 128; r++)
+            for (int j = 0; j < 16; j++) {
+                __half lo = __float2half(A[r * KA + 2 * j]), hi = __float2half(A[r * KA + 2 * j + 1]);
+                unsigned short l, h; memcpy(&l, &lo, 2); memcpy(&h, &hi, 2);
+                aw[r * 16 + j] = (unsigned)l | ((unsigned)h << 16);
+            }
+        unsigned* d_aw; float* d_o2; CK(cudaMalloc(&d_aw, aw.size() * 4)); CK(cudaMalloc(&d_o2, 128 * 32 * 4));
+        CK(cudaMemcpy(d_aw, aw.data(), aw.size() * 4, cudaMemcpyHostToDevice));
+        for (int a_col0 : {0, 4, 20}) {
+            CK(cudaMemset(d_o2, 0xff, 128 * 32 * 4));
+            ts_kernel<<<1, 160, kBTile>>>(d_aw, d_b, make_idesc(128, 16), a_col0, d_o2);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("TS a_col0=%d: kernel failed: %s\n", a_col0, cudaGetErrorString(e)); return 1; }
+            std::vector<float> o2(128 * 32);
+            CK(cudaMemcpy(o2.data(), d_o2, o2.size() * 4, cudaMemcpyDeviceToHost));
+            for (int v = 0; v < 2; v++) {
+                int bad = 0; double me = 0;
+                for (int r = 0; r < 128; r++)
+                    for (int n = 0; n < 16; n++) {
+                        float acc = 0;
+                        for (int k = 0; k < 16; k++) acc += A[r * KA + 8 * v + k] * B[(0 * 16 + n) * 16 + k];
+                        double d = fabs((double)o2[r * 32 + 16 * v + n] - acc);
+                        if (!(d <= 1e-3)) bad++;
+                        if (d > me || d != d) me = d;
+                    }
+                printf("TS mode (A in TMEM, thread = row, 2 f16 per column) a_col0=%d operand column +%d: max err %.4g bad %d -> %s\n", a_col0, 4 * v, me, bad, bad ? "FAIL" : "PASS");
+            }
+        }
+    }
     long long* d_cyc; CK(cudaMalloc(&d_cyc, 16));
     CK(cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     for (int mode = 0; mode < 3; mode++)
-        for (int n : {8, 16, 32, 64, 128, 256})
+        for (int n : {16, 32, 64, 128, 256})
             for (int naccs : {1, 2}) {
                 if (n * naccs > 256) continue;
                 const int reps = 4096;
