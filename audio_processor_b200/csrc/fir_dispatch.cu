@@ -18,14 +18,14 @@ int fir_fast_dispatch(int in_rate, int fmt, int channels, const void* d_in, i64 
                       u64* d_energy, FirMmaPlan* plan, cudaStream_t stream) {
     plan->out_lo = plan->out_hi = 0;
     if (fmt != B2A_FMT_S16 || d_out_f32 || (channels != 1 && channels != 2)) return 0;
-    // Stereo input has two kernels: the mma.sync kernel (fir_mma.cuh, 16-run tiles fed by a bulk-TMA ring; the default)
-    // and the tcgen05 kernel (fir_umma.cuh, 512-run spans, accumulators in TMEM).  The tcgen05 kernel is parity-green on
-    // B200 but, fed by register-staged global loads, streams the input at ~2 TB/s (profiles/r01_fir_umma.md) and is
-    // therefore opt-in: B2A_FIR_IMPL=umma.  When selected it takes the whole spans and hands what is left behind the last
-    // span to the mma.sync kernel.
+    // Stereo input has three kernels:
+    //   fir_tmem.cuh  tcgen05, fed by 2-D TMA, operand planes in TMEM, 512-run spans             (the default)
+    //   fir_umma.cuh  tcgen05, register-staged loads, planes in shared memory    (B2A_FIR_IMPL=umma; profiles/r01_fir_umma.md)
+    //   fir_mma.cuh   mma.sync, 16-run tiles fed by a bulk-TMA ring              (B2A_FIR_IMPL=mma; also mono input)
+    // A tcgen05 kernel takes the whole spans and hands what is left behind the last span to the mma.sync kernel.
     const char* impl = getenv("B2A_FIR_IMPL");
-    const bool legacy = !(impl && (impl[0] == 'u' || impl[0] == 't'));
-    const bool tmem = impl && impl[0] == 't';                 // B2A_FIR_IMPL=tmem: TMA-fed kernel with the planes in TMEM (fir_tmem.cuh)
+    const bool legacy = impl && impl[0] == 'm';
+    const bool tmem = !(impl && impl[0] == 'u');
     i64 first_tile = 1;
     FirMmaPlan head;
     head.out_lo = head.out_hi = 0;
