@@ -1,5 +1,6 @@
 // fir_dispatch.cu — picks the tensor-core FIR instantiation for a (rate, format, channels) triple.
 #include "fir_mma.cuh"
+#include "resample_generic.cuh"
 
 namespace b2a {
 
@@ -7,15 +8,17 @@ int fir_mma_run_44100(int channels, const void*, i64, int16_t*, u64*, FirMmaPlan
 int fir_mma_run_48000(int channels, const void*, i64, int16_t*, u64*, FirMmaPlan*, cudaStream_t, i64 first_tile);
 int fir_umma_run_44100(const void*, i64, int16_t*, u64*, FirMmaPlan*, cudaStream_t);
 int fir_umma_run_48000(const void*, i64, int16_t*, u64*, FirMmaPlan*, cudaStream_t);
-int fir_tmem_run_44100(const void*, i64, int16_t*, u64*, FirMmaPlan*, cudaStream_t);
-int fir_tmem_run_48000(const void*, i64, int16_t*, u64*, FirMmaPlan*, cudaStream_t);
+int fir_tmem_run_44100(const void*, i64, int16_t*, u64*, FirMmaPlan*, const GenericParams*, cudaStream_t);
+int fir_tmem_run_48000(const void*, i64, int16_t*, u64*, FirMmaPlan*, const GenericParams*, cudaStream_t);
+i64 fir_tmem_plan_44100(i64, FirMmaPlan*);
+i64 fir_tmem_plan_48000(i64, FirMmaPlan*);
 
 // returns 1 if the tensor-core kernel was launched (plan filled), 0 if this input has no fast path, <0 on error.
 // s16 input at the two named rates only; the pre-quantisation float output and every other case use the
 // table-driven kernel in resample.cu.  Clips too short for a 128-run tile of the tcgen05 kernel fall back to the
 // 16-run tiles of the mma.sync kernel.
 int fir_fast_dispatch(int in_rate, int fmt, int channels, const void* d_in, i64 n_in, int16_t* d_out_s16, float* d_out_f32,
-                      u64* d_energy, FirMmaPlan* plan, cudaStream_t stream) {
+                      u64* d_energy, FirMmaPlan* plan, const GenericParams* edge, cudaStream_t stream) {
     plan->out_lo = plan->out_hi = 0;
     if (fmt != B2A_FMT_S16 || d_out_f32 || (channels != 1 && channels != 2)) return 0;
     // Stereo input has three kernels:
@@ -26,13 +29,34 @@ int fir_fast_dispatch(int in_rate, int fmt, int channels, const void* d_in, i64 
     const char* impl = getenv("B2A_FIR_IMPL");
     const bool legacy = impl && impl[0] == 'm';
     const bool tmem = !(impl && impl[0] == 'u');
+    if (channels == 2 && !legacy && tmem && edge && (in_rate == 44100 || in_rate == 48000)) {
+        // default: spans by the TMA-fed tcgen05 kernel, the 16-run tiles behind the last span by the mma.sync kernel, and
+        // the head / the last partial tile by the tcgen05 kernel's spare warps => the whole clip is done, no edge kernel
+        FirMmaPlan head, tail;
+        tail.out_lo = tail.out_hi = 0;
+        const i64 spans = in_rate == 44100 ? fir_tmem_plan_44100(n_in, &head) : fir_tmem_plan_48000(n_in, &head);
+        if (spans > 0) {
+            const i64 first = head.out_hi / (kFmRT * kFmNout);              // span ends are multiples of 16 runs
+            int rc = in_rate == 44100 ? fir_mma_run_44100(channels, d_in, n_in, d_out_s16, d_energy, &tail, stream, first)
+                                      : fir_mma_run_48000(channels, d_in, n_in, d_out_s16, d_energy, &tail, stream, first);
+            if (rc < 0) return rc;
+            GenericParams e = *edge;
+            e.lo0 = 0; e.hi0 = head.out_lo;
+            e.lo1 = rc > 0 ? tail.out_hi : head.out_hi; e.hi1 = e.n_out;
+            rc = in_rate == 44100 ? fir_tmem_run_44100(d_in, n_in, d_out_s16, d_energy, &head, &e, stream)
+                                  : fir_tmem_run_48000(d_in, n_in, d_out_s16, d_energy, &head, &e, stream);
+            if (rc <= 0) return rc < 0 ? rc : B2A_ECUDA;
+            plan->out_lo = 0; plan->out_hi = e.n_out;
+            return 1;
+        }
+    }
     i64 first_tile = 1;
     FirMmaPlan head;
     head.out_lo = head.out_hi = 0;
-    if (channels == 2 && !legacy) {
+    if (channels == 2 && !legacy && !tmem) {
         int rc = 0;
-        if (in_rate == 44100) rc = tmem ? fir_tmem_run_44100(d_in, n_in, d_out_s16, d_energy, &head, stream) : fir_umma_run_44100(d_in, n_in, d_out_s16, d_energy, &head, stream);
-        else if (in_rate == 48000) rc = tmem ? fir_tmem_run_48000(d_in, n_in, d_out_s16, d_energy, &head, stream) : fir_umma_run_48000(d_in, n_in, d_out_s16, d_energy, &head, stream);
+        if (in_rate == 44100) rc = fir_umma_run_44100(d_in, n_in, d_out_s16, d_energy, &head, stream);
+        else if (in_rate == 48000) rc = fir_umma_run_48000(d_in, n_in, d_out_s16, d_energy, &head, stream);
         if (rc < 0) return rc;
         if (rc > 0) first_tile = head.out_hi / (kFmRT * kFmNout);          // span ends are multiples of 16 runs
     }

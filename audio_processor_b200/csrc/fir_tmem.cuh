@@ -21,11 +21,14 @@
 // Roles (512 threads), coupled only by mbarriers:
 //   warps 0-3   epilogue (as in fir_umma.cuh);
 //   warp  4     MMA issuer (compile-time schedule, elected issue) + TMEM allocation;
-//   warp  5     TMA producer: lane 0 keeps the raw ring full (two boxes per 64-column piece);  warps 6-7 idle;
+//   warp  5     TMA producer: lane 0 keeps the raw ring full (two boxes per 64-column piece);
+//   warps 6-7   the clip's edge outputs (reflect / symmetric extension at the head, the tail behind the last span),
+//               table-driven, one thread per output, spread over all CTAs: no separate edge kernel on the stream;
 //   warps 8-15  converters: warp w converts lane quadrant w % 4 (rows 32 (w % 4) + lane), frames 32 h .. 32 h + 31 of the
 //               piece with h = (w - 8) / 4: eight swizzle-aware LDS.128, 16 + 16 packed words, two tcgen05.st.
 #pragma once
 #include "fir_umma.cuh"
+#include "resample_generic.cuh"
 
 #ifndef B2A_EMU
 #include <cuda.h>
@@ -74,6 +77,8 @@ struct FirTmemArgs {
     const uint4* btab;              // [class][B_BYTES] filter banks (build_fir_umma_table)
     int spans;
     int phases;                     // profiling aid (env B2A_FIR_PHASES): bit 2 epilogue stores; 31 = the product
+    GenericParams edge;             // the clip's head and tail outputs (table-driven, one thread per output): warps 6-7
+    i64 edge_total;                 // linear indices of `edge` (resample_generic_total), 0 = none
 };
 
 // ---- primitives ---------------------------------------------------------------------------------------------------
@@ -299,7 +304,11 @@ __global__ void __launch_bounds__(kFtThreads, 1) fir_tmem_kernel(const __grid_co
             }
         }
         __syncwarp();
-    } else if (warp >= kFtCvtWarp0) {
+    } else if (warp < kFtCvtWarp0) {
+        // ===================================== edge outputs (warps 6-7 of every CTA) =====================================
+        const i64 groups = (a.edge_total + 31) / 32;
+        for (i64 g = (i64)blockIdx.x * 2 + (warp - 6); g < groups; g += (i64)gridDim.x * 2) resample_generic_output(a.edge, g * 32 + lane);
+    } else {
         // ===================================== converters: thread = row =====================================
         constexpr unsigned KHV = 65536u + (0x6400u << 7);         // dp2a bias: (u >> 7) = f16 bits of 1024 + (hv + 512), u & 127 = lo
         const int cw = warp - kFtCvtWarp0, q = cw & 3, h = cw >> 2;
@@ -364,14 +373,27 @@ static inline b2a_tmap_encode_fn fir_tmem_encoder() {
 }
 #endif
 
+// outputs the kernel would produce for a clip of n_in frames (no launch); returns the number of spans
 template <int IN_RATE>
-static inline int fir_tmem_launch(const void* d_in, i64 n_in, int16_t* d_out_s16, u64* d_energy, FirMmaPlan* plan, cudaStream_t stream) {
+static inline i64 fir_tmem_plan(i64 n_in, FirMmaPlan* plan) {
     using G = FirTmemGeom<IN_RATE>;
     plan->out_lo = plan->out_hi = 0;
     // tensor rows are 4 runs apart and declared kFtTensorD0 frames long from frame XMIN on: the last declared row must end
     // inside the clip (which also covers every box: X(3) - XMIN + 64 PIECES <= kFtTensorD0)
     const i64 rows_fit = n_in >= (i64)G::XMIN + kFtTensorD0 ? (n_in - G::XMIN - kFtTensorD0) / ((i64)4 * G::S) + 1 : 0;
     const i64 spans = rows_fit / kFuRT;
+    if (spans <= 0) return 0;
+    plan->out_lo = (i64)kFuRun0 * kFmNout;
+    plan->out_hi = ((i64)kFuRun0 + spans * kFuSpan) * kFmNout;
+    return spans;
+}
+
+// edge: the outputs outside [plan->out_lo, plan->out_hi) (and outside whatever another kernel covers) that warps 6-7 compute
+template <int IN_RATE>
+static inline int fir_tmem_launch(const void* d_in, i64 n_in, int16_t* d_out_s16, u64* d_energy, FirMmaPlan* plan, const GenericParams* edge,
+                                  cudaStream_t stream) {
+    using G = FirTmemGeom<IN_RATE>;
+    const i64 spans = fir_tmem_plan<IN_RATE>(n_in, plan);
     if (spans <= 0) return 0;
     const uint4* tab = get_fir_umma_table(IN_RATE);
     if (!tab) return B2A_ECUDA;
@@ -402,6 +424,9 @@ static inline int fir_tmem_launch(const void* d_in, i64 n_in, int16_t* d_out_s16
     a.spans = (int)spans;
     a.phases = 31;
     if (const char* ph = getenv("B2A_FIR_PHASES")) a.phases = atoi(ph);          // profiling only
+    a.edge_total = 0;
+    if (edge) { a.edge = *edge; a.edge_total = resample_generic_total(*edge); }
+    else memset(&a.edge, 0, sizeof(a.edge));
     i64 lanes = spans < 37 ? spans : 37;                         // persistent: 4 CTAs (one per class) per span lane, 148 SMs
     if (const char* gs = getenv("B2A_FIR_GRID")) {               // test knob: few CTAs => many tiles per CTA
         const int gv = (atoi(gs) + kFuClasses - 1) / kFuClasses;
@@ -409,8 +434,6 @@ static inline int fir_tmem_launch(const void* d_in, i64 n_in, int16_t* d_out_s16
     }
     B2A_LAUNCH(k, (unsigned)(lanes * kFuClasses), kFtThreads, G::SMEM_BYTES, stream, a);
     B2A_CHECK_LAUNCH("fir_tmem_kernel");
-    plan->out_lo = (i64)kFuRun0 * kFmNout;
-    plan->out_hi = ((i64)kFuRun0 + spans * kFuSpan) * kFmNout;
     return 1;
 }
 

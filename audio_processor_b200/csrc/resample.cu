@@ -7,115 +7,16 @@
 // and the same-rate paths (identity, (L+R+1)>>1 stereo s16 downmix, float quantisation).
 #include "b2a_tables.cuh"
 #include "fir_mma.cuh"
+#include "resample_generic.cuh"
 
 namespace b2a {
 
 // tensor-core fast path (fir_mma.cuh), instantiated in its own translation units
 int fir_fast_dispatch(int in_rate, int fmt, int channels, const void* d_in, i64 n_in, int16_t* d_out_s16, float* d_out_f32,
-                      u64* d_energy, FirMmaPlan* plan, cudaStream_t stream);
+                      u64* d_energy, FirMmaPlan* plan, const GenericParams* edge, cudaStream_t stream);
 
-struct GenericParams {
-    const void* in;
-    int fmt, channels;
-    i64 n_in;
-    i64 n_out;
-    int L, M, taps, center;
-    const float* taps_dev;        // [L][taps]
-    int16_t* out_s16;
-    float* out_f32;
-    u64* energy;                  // nullable
-    int spm;                      // samples per ms at the output rate (0: no energy)
-    i64 n_energy;
-    // output ranges [lo0,hi0) and [lo1,hi1) (multiples of 32 at the low ends); blocks cover them back to back
-    i64 lo0, hi0, lo1, hi1;
-    int energy_atomic;
-};
-
-__device__ __forceinline__ float generic_sample(const GenericParams& p, i64 k) {
-    // libswresample edge handling: reflect before the start (edge not repeated),
-    // symmetric after the end (edge repeated)
-    if (k < 0) k = -k;
-    if (k >= p.n_in) k = 2 * p.n_in - 1 - k;
-    if (k < 0) k = 0;
-    if (k >= p.n_in) k = p.n_in - 1;
-    if (p.fmt == B2A_FMT_S16) {
-        const int16_t* s = (const int16_t*)p.in;
-        if (p.channels == 1) return (float)s[k] * (1.0f / 32768.0f);
-        return ((float)s[2 * k] + (float)s[2 * k + 1]) * (1.0f / 65536.0f);   // exact: 0.5*L + 0.5*R
-    } else {
-        const float* s = (const float*)p.in;
-        if (p.channels == 1) return s[k];
-        return 0.5f * s[2 * k] + 0.5f * s[2 * k + 1];
-    }
-}
-
-// one thread per output sample, taps from global memory (L2/L1 resident)
 __global__ void __launch_bounds__(256) resample_generic_kernel(GenericParams p) {
-    const i64 span0 = p.hi0 - p.lo0;
-    const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    // block ranges are padded to multiples of 32 so a warp never straddles the two ranges
-    const i64 span0p = (span0 + 31) / 32 * 32;
-    i64 m;
-    bool valid;
-    if (r < span0p) { m = p.lo0 + r; valid = m < p.hi0; }
-    else { m = p.lo1 + (r - span0p); valid = m < p.hi1; }
-    int q = 0;
-    if (valid) {
-        const i64 t = m * p.M;
-        const i64 idx = t / p.L;
-        const int ph = (int)(t % p.L);
-        const float* h = p.taps_dev + (size_t)ph * p.taps;
-        float a0 = 0.f, a1 = 0.f;
-        const i64 base = idx - p.center;
-        int i = 0;
-        if (base >= 0 && base + p.taps <= p.n_in) {
-            // interior window: no edge extension, plain strided loads, four taps in flight per accumulator pair
-            float b0 = 0.f, b1 = 0.f;
-            if (p.fmt == B2A_FMT_S16 && p.channels == 2 && (((uintptr_t)p.in) & 3) == 0) {
-                const int* s = (const int*)p.in + base;            // one 32-bit word per stereo frame
-                for (; i + 3 < p.taps; i += 4) {
-                    a0 = fmaf((float)__dp2a_lo(s[i], 0x0101, 0), h[i], a0);
-                    a1 = fmaf((float)__dp2a_lo(s[i + 1], 0x0101, 0), h[i + 1], a1);
-                    b0 = fmaf((float)__dp2a_lo(s[i + 2], 0x0101, 0), h[i + 2], b0);
-                    b1 = fmaf((float)__dp2a_lo(s[i + 3], 0x0101, 0), h[i + 3], b1);
-                }
-                for (; i < p.taps; i++) a0 = fmaf((float)__dp2a_lo(s[i], 0x0101, 0), h[i], a0);
-                a0 = ((a0 + b0) + (a1 + b1)) * (1.0f / 65536.0f);   // exact power-of-two scale of 0.5*(L+R)/32768
-                a1 = 0.f;
-            } else {
-                for (; i + 3 < p.taps; i += 4) {
-                    a0 = fmaf(generic_sample(p, base + i), h[i], a0);
-                    a1 = fmaf(generic_sample(p, base + i + 1), h[i + 1], a1);
-                    b0 = fmaf(generic_sample(p, base + i + 2), h[i + 2], b0);
-                    b1 = fmaf(generic_sample(p, base + i + 3), h[i + 3], b1);
-                }
-                for (; i < p.taps; i++) a0 = fmaf(generic_sample(p, base + i), h[i], a0);
-                a0 += b0; a1 += b1;
-            }
-        } else {
-            for (; i + 1 < p.taps; i += 2) {
-                a0 = fmaf(generic_sample(p, base + i), h[i], a0);
-                a1 = fmaf(generic_sample(p, base + i + 1), h[i + 1], a1);
-            }
-            if (i < p.taps) a0 = fmaf(generic_sample(p, base + i), h[i], a0);
-        }
-        const float y = a0 + a1;
-        q = quant_s16(y * 32768.0f);
-        if (p.out_s16) p.out_s16[m] = (int16_t)q;
-        if (p.out_f32) p.out_f32[m] = y;
-    }
-    if (p.energy && p.spm > 0) {
-        u64 sq = valid ? (u64)(unsigned)(q * q) : 0ull;
-        if (!p.energy_atomic) {
-            // a warp covers 32 consecutive outputs starting at a multiple of 32 and spm divides 32:
-            // reduce per spm-lane group; the group leader is valid iff the millisecond has any output
-            // in this range (a trailing partial millisecond is thereby zero-extended)
-            for (int o = 1; o < p.spm; o <<= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-            if ((m % p.spm) == 0 && valid) p.energy[m / p.spm] = sq;
-        } else if (valid) {
-            atomicAdd((unsigned long long*)&p.energy[m / p.spm], (unsigned long long)sq);
-        }
-    }
+    resample_generic_output(p, (i64)blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 // same-rate paths: libswresample stays in the sample domain
@@ -183,36 +84,30 @@ int resample_launch(const void* d_in, int fmt, int channels, int in_rate, i64 n_
     if (!des) return B2A_EINVAL;
     if (n_in < des->taps) { set_error("resample: input shorter than the %d-tap filter is unsupported", des->taps); return B2A_EUNSUPPORTED; }
 
-    // fast path for the named rate pairs (needs 16-byte aligned buffers)
-    FirMmaPlan plan;
-    plan.out_lo = plan.out_hi = 0;
-    const bool aligned = ((((uintptr_t)d_in) | ((uintptr_t)d_out_s16) | ((uintptr_t)d_out_f32) | ((uintptr_t)d_energy)) & 15) == 0;
-    bool fast = false;
-    if (aligned && out_rate == 16000) {
-        int rc = fir_fast_dispatch(in_rate, fmt, channels, d_in, n_in, d_out_s16, d_out_f32, d_energy, &plan, stream);
-        if (rc < 0) return rc;
-        fast = rc > 0;
-    }
-    (void)fast;
-
     GenericParams p;
     p.in = d_in; p.fmt = fmt; p.channels = channels; p.n_in = n_in; p.n_out = n_out;
     p.L = des->L; p.M = des->M; p.taps = des->taps; p.center = des->center; p.taps_dev = des->d_taps;
     p.out_s16 = d_out_s16; p.out_f32 = d_out_f32; p.energy = d_energy; p.spm = spm; p.n_energy = n_energy;
     p.energy_atomic = 0;
+    p.lo0 = 0; p.hi0 = n_out; p.lo1 = p.hi1 = n_out;
+
+    // fast path for the named rate pairs (needs 16-byte aligned buffers).  The tcgen05 kernel also computes the edge
+    // outputs (in its otherwise idle warps) and then reports the whole clip as done.
+    FirMmaPlan plan;
+    plan.out_lo = plan.out_hi = 0;
+    const bool aligned = ((((uintptr_t)d_in) | ((uintptr_t)d_out_s16) | ((uintptr_t)d_out_f32) | ((uintptr_t)d_energy)) & 15) == 0;
+    if (aligned && out_rate == 16000) {
+        int rc = fir_fast_dispatch(in_rate, fmt, channels, d_in, n_in, d_out_s16, d_out_f32, d_energy, &plan, &p, stream);
+        if (rc < 0) return rc;
+    }
     if (plan.out_hi > plan.out_lo) { p.lo0 = 0; p.hi0 = plan.out_lo; p.lo1 = plan.out_hi; p.hi1 = n_out; }
-    else { p.lo0 = 0; p.hi0 = n_out; p.lo1 = p.hi1 = n_out; }
     const bool direct = spm > 0 && spm <= 32 && (32 % spm) == 0;
     if (d_energy && !direct) {
         // (the fast path zeroes the table itself when it accumulates atomically)
         cudaMemsetAsync(d_energy, 0, (size_t)n_energy * 8, stream);     // only for output rates whose millisecond is not a power-of-two count (no fast path there)
         p.energy_atomic = 1;
     }
-    // cover the zero-extended tail of the last millisecond too
-    i64 span0 = (p.hi0 - p.lo0 + 31) / 32 * 32;
-    i64 span1 = p.hi1 - p.lo1;
-    if (spm > 0) span1 = (span1 + spm - 1) / spm * spm;
-    i64 total = span0 + span1;
+    const i64 total = resample_generic_total(p);
     if (total > 0) {
         auto k = resample_generic_kernel;
         B2A_LAUNCH(k, (unsigned)((total + 255) / 256), 256, 0, stream, p);
