@@ -412,9 +412,11 @@ def run_b200(args):
             "log-mel": n_keep * 2 + 4 * n_mels * (n_keep // 160),
         }
         top = max(stages, key=lambda k: stages[k])
-        kname = {"resample+downmix+energy": "fir_mma_kernel (+ resample_generic_kernel for the clip edges)" if in_rate in (44100, 48000) else "passthrough_kernel",
+        fir_name = ("fir_tmem_kernel (+ fir_mma_kernel behind the last span)" if ch == 2 else "fir_mma_kernel (+ resample_generic_kernel for the clip edges)")
+        kname = {"resample+downmix+energy": fir_name if in_rate in (44100, 48000) else "passthrough_kernel",
                  "silence ranges": "cover_kernel", "compaction": "compact_kernel", "log-mel": "stft_mel_kernel"}[top]
-        roof = dict(kernel=kname, stage=top, bytes=stage_bytes[top], ms=stages[top])
+        roof = dict(kernel=kname, stage=top, bytes=stage_bytes[top], ms=stages[top],
+                    per_stage={k: dict(algorithmic_bytes=int(stage_bytes[k]), ms=stages[k]) for k in stages})
 
     # ---- e2e: the public host API with pinned HOST buffers; H2D + D2H inside the timed region ----
     e2e = None
@@ -529,6 +531,12 @@ def run_b200(args):
                          "pipeline_frac": abytes / (ms_step * 1e-3) / 1e9 / peak},
             "clocks": clocks,
         }
+        if roof.get("per_stage"):
+            # every stage against the same HBM peak (stage's own algorithmic bytes / its CUDA-event time)
+            out["roofline"]["stages"] = {k: {"achieved": v["algorithmic_bytes"] / (v["ms"] * 1e-3) / 1e9,
+                                             "frac": v["algorithmic_bytes"] / (v["ms"] * 1e-3) / 1e9 / peak,
+                                             "algorithmic_bytes": v["algorithmic_bytes"], "ms": round(v["ms"], 4)}
+                                         for k, v in roof["per_stage"].items()}
         if gathered is not None:
             out["segment_tables_gathered"] = gathered
         if e2e is not None:
