@@ -35,6 +35,7 @@ SIGNATURES = {
     "b2a_version": (C.c_int, []),
     "b2a_last_error": (C.c_char_p, []),
     "b2a_launch_count": (C.c_int64, []),
+    "b2a_fir_schedule": (C.c_int, [C.c_int, P, C.c_int]),
     "b2a_resample_out_len": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
     "b2a_resample_ntaps": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "b2a_resample_taps": (C.c_int, [C.c_int, C.c_int, P, C.c_size_t]),

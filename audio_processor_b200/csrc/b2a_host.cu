@@ -238,6 +238,18 @@ const uint4* get_fir_umma_table(int in_rate) {
 
 }  // namespace b2a
 
+template <int IN_RATE>
+static int fir_schedule_dump(uint32_t* out, int cap) {
+    using G = b2a::FirUmmaGeom<IN_RATE>;
+    constexpr b2a::FirUmmaSched S = b2a::FirUmmaSchedOf<IN_RATE>::value;
+    if (cap < 16 + S.n) { b2a::set_error("capacity %d < %d", cap, 16 + S.n); return B2A_EINVAL; }
+    for (int i = 0; i < 16; i++) out[i] = 0;
+    out[0] = (uint32_t)S.n; out[1] = (uint32_t)G::PIECES; out[2] = (uint32_t)G::KS;
+    for (int b = 0; b < b2a::kFmBlocks; b++) out[3 + b] = (uint32_t)(G::kbp(b) / 8);
+    for (int j = 0; j < S.n; j++) out[16 + j] = S.w[j];
+    return 16 + S.n;
+}
+
 extern "C" {
 
 int b2a_version(void) { return 100; }  // 0.1.0
@@ -245,6 +257,14 @@ int b2a_version(void) { return 100; }  // 0.1.0
 const char* b2a_last_error(void) { return b2a::g_err; }
 
 int64_t b2a_launch_count(void) { return (int64_t)b2a::g_launches.load(std::memory_order_relaxed); }
+
+int b2a_fir_schedule(int in_rate, uint32_t* out, int capacity_words) {
+    if (!out) { b2a::set_error("bad argument"); return B2A_EINVAL; }
+    if (in_rate == 44100) return fir_schedule_dump<44100>(out, capacity_words);
+    if (in_rate == 48000) return fir_schedule_dump<48000>(out, capacity_words);
+    b2a::set_error("no tcgen05 FIR for %d Hz", in_rate);
+    return B2A_EUNSUPPORTED;
+}
 
 int b2a_resample_ntaps(int in_rate, int out_rate, int* phases) {
     if (in_rate <= 0 || out_rate <= 0) { b2a::set_error("bad sample rate"); return B2A_EINVAL; }

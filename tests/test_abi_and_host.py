@@ -198,3 +198,40 @@ def test_gather_segment_tables_world_size_2_gloo(tmp_path):
                               stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+@pytest.mark.parametrize("rate", [44100, 48000])
+def test_fir_issue_schedule_is_hazard_free(rate):
+    """the tcgen05 FIR issues its k-steps in column order and releases a ring piece right after its last reader
+    (csrc/fir_umma.cuh, fir_umma_schedule).  The functional emulation cannot see a premature release (it executes an MMA
+    when it is issued), so the schedule itself is checked: every k-step once and in order per block, operands only in
+    pieces that were awaited and not yet released, every piece awaited and released exactly once, and never more live
+    pieces than the smallest plane ring holds."""
+    from audio_processor_b200 import _abi
+    lib = _abi.declare(C.CDLL(_built_lib()))
+    buf = (C.c_uint32 * 256)()
+    n_words = lib.b2a_fir_schedule(rate, buf, 256)
+    assert n_words > 16
+    n, pieces, ks = buf[0], buf[1], buf[2]
+    kbp = [buf[3 + b] for b in range(10)]
+    assert n == 10 * ks
+    ready = freed = 0
+    next_s = [0] * 10
+    max_live = 0
+    for j in range(n):
+        w = buf[16 + j]
+        cidx, bidx, b = w & 127, (w >> 7) & 127, (w >> 14) & 15
+        first, last, need, frees = bool(w & (1 << 18)), bool(w & (1 << 19)), (w >> 20) & 15, (w >> 24) & 15
+        s = next_s[b]
+        next_s[b] += 1
+        assert cidx == kbp[b] + 2 * s and first == (s == 0) and last == (s == ks - 1)
+        assert bidx == ((0 if rate == 48000 else b) * ks + s)
+        ready = max(ready, need)                          # the issuer waits for pieces [.., need) before the k-step
+        p0, p1 = cidx // 8, (cidx + 1) // 8               # pieces the operand's two chunks live in
+        assert freed <= p0 <= p1 < ready, (j, p0, p1, freed, ready)
+        max_live = max(max_live, ready - freed)
+        if frees and j < n - 1:
+            assert freed + frees <= ready                 # only awaited pieces are released (the last item awaits the rest itself)
+        freed += frees
+    assert next_s == [ks] * 10 and freed == pieces and ready <= pieces
+    assert max_live <= 3                                  # the plane ring has 4 (44.1 kHz) / 5 (48 kHz) pieces
