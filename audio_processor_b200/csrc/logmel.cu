@@ -147,6 +147,16 @@ struct LogMelParams {
     float* tile_min;       // [batch][tiles_cap]
     i64 tiles_cap;         // tiles per clip at capacity
     const LogMelTables* tab;
+    // fused stream compaction (pipeline, s16, batch == 1): when kept_ms != nullptr `audio` is the UNTRIMMED 16 kHz PCM of
+    // n_src samples and the clip this kernel sees is the concatenation of the kept ranges (pydub `+`): trimmed index q in
+    // [kept_off[s], kept_off[s+1]) lives at source sample 16 kept_ms[2s] + q - kept_off[s] (zero past n_src: pydub
+    // zero-fills a rounded-up last millisecond).  Every tile also writes the 5120 trimmed samples it owns to trim_out,
+    // so there is no separate compaction kernel and the trimmed PCM is never re-read.
+    const int32_t* kept_ms;
+    const i64* kept_off;
+    const i64* info;       // B2A_INFO_N_KEPT
+    int16_t* trim_out;
+    i64 n_src;
 };
 
 __device__ __forceinline__ float load_sample(const void* audio, int fmt, i64 idx) {
@@ -248,7 +258,10 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
     if (p.d_n) { n_act = *p.d_n; if (n_act > p.n) n_act = p.n; if (n_act < 0) n_act = 0; }
     const i64 ltot = n_act + p.padding;          // padded length
     const i64 T = ltot / kHop;                   // frames
-    const i64 tiles = (T + LM_FRAMES - 1) / LM_FRAMES;
+    const bool gather = S16 && p.kept_ms != nullptr;
+    const int n_seg = gather ? (int)p.info[B2A_INFO_N_KEPT] : 0;
+    i64 tiles = (T + LM_FRAMES - 1) / LM_FRAMES;
+    if (gather && tiles * (LM_FRAMES * kHop) < n_act) tiles++;          // a last partial hop still has trimmed samples to write
     if (blockIdx.x == 0 && tid == 0 && p.d_frames_out) *p.d_frames_out = T;
 
     const int u = tid >> 5, f = tid & 31;        // role (warp-uniform), frame within the tile
@@ -274,27 +287,64 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
     const i64 n_work = tiles * p.batch;
 
     // where a work item's samples live: row base, first padded-domain index, and whether the fast (interior) path applies
-    struct Src { const char* row; i64 q0; int mode; };   // mode 0: generic (reflect / zero pad), 1: interior s16, 2: interior f32
+    struct Src { const char* row; i64 q0; int mode; i64 lo0, add0, bound1, add1, bound2; };   // mode 0: generic (reflect / zero pad), 1: interior s16, 2: interior f32
+    // gather: source sample of trimmed index q (segment search; the two segments cached in a Src cover an interior tile)
+    auto seg_of = [&](i64 q) -> int {
+        int lo = 0, hi = n_seg - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (p.kept_off[mid] <= q) lo = mid; else hi = mid - 1;
+        }
+        return lo;
+    };
     auto locate = [&](i64 work) -> Src {
         Src r;
         const int b = (int)(work / tiles);
         const i64 tile = work - (i64)b * tiles;
         r.row = (const char*)p.audio + (size_t)b * (size_t)p.row_stride * elem;
         r.q0 = tile * (LM_FRAMES * kHop) - 200;
-        const bool interior = r.q0 >= 0 && r.q0 + LM_TILE <= n_act && ((((uintptr_t)(r.row + r.q0 * elem)) & 7) == 0);
+        r.add0 = r.add1 = 0;
+        r.lo0 = 0;
+        r.bound1 = r.bound2 = (i64)1 << 62;
+        bool interior = r.q0 >= 0 && r.q0 + LM_TILE <= n_act;
+        if (gather) {
+            if (n_seg > 0) {
+                const int sg = seg_of(r.q0 > 0 ? r.q0 : 0);
+                r.lo0 = p.kept_off[sg];
+                r.add0 = (i64)p.kept_ms[2 * sg] * 16 - r.lo0;
+                if (sg + 1 < n_seg) { r.bound1 = p.kept_off[sg + 1]; r.add1 = (i64)p.kept_ms[2 * sg + 2] * 16 - r.bound1; }
+                if (sg + 2 < n_seg) r.bound2 = p.kept_off[sg + 2];
+            }
+            // interior: at most two segments under the tile and every source sample inside the buffer
+            interior = interior && r.q0 + LM_TILE <= r.bound2 && r.add0 + r.q0 >= 0 &&
+                       r.add0 + (r.bound1 < r.q0 + LM_TILE ? r.bound1 : r.q0 + LM_TILE) <= p.n_src &&
+                       (r.bound1 >= r.q0 + LM_TILE || r.add1 + r.q0 + LM_TILE <= p.n_src);
+        } else {
+            interior = interior && ((((uintptr_t)(r.row + r.q0 * elem)) & 7) == 0);
+        }
         r.mode = interior ? (S16 ? 1 : 2) : 0;
         return r;
+    };
+    // trimmed-domain sample q of a gathered clip (0 <= q < n_act)
+    auto gather_sample = [&](const Src& sc, i64 q) -> short {
+        i64 si;
+        if (q >= sc.lo0 && q < sc.bound1) si = sc.add0 + q;                   // the two segments cached for the tile
+        else if (q >= sc.bound1 && q < sc.bound2) si = sc.add1 + q;
+        else { const int sg = seg_of(q); si = (i64)p.kept_ms[2 * sg] * 16 + (q - p.kept_off[sg]); }
+        return (si >= 0 && si < p.n_src) ? ((const short*)p.audio)[si] : (short)0;
     };
     // generic tile load: padded-domain index q = q0 + i, reflect at both ends, zeros past n_act
     auto load_generic = [&](const Src& sc) {
         for (int i = tid; i < LM_TILE; i += LM_THREADS) {
             i64 q = sc.q0 + i;
+            const bool own = gather && q >= 0 && q < n_act && i >= 200 && i < 200 + LM_FRAMES * kHop;   // the tile's own 5120 samples
             if (q < 0) q = -q;
             if (q >= ltot) q = 2 * (ltot - 1) - q;
             if (S16) {
                 short v = 0;
-                if (q >= 0 && q < n_act) v = ((const short*)sc.row)[q];
+                if (q >= 0 && q < n_act) v = gather ? gather_sample(sc, q) : ((const short*)sc.row)[q];
                 ((short*)s_tile16)[i + 2 * (i / kHop)] = v;                     // one word of skew per hop
+                if (own) p.trim_out[q] = v;
             } else {
                 float v = 0.0f;
                 if (q >= 0 && q < n_act) v = ((const float*)sc.row)[q];
@@ -303,14 +353,27 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
         }
     };
     // pair pr (samples 2pr, 2pr+1) lives at word 2pr + LM_SKEW * (pr / 80) of the skewed tile
-    auto store_s16_pairs = [&](const unsigned (&pre)[LM_PRE]) {
+    auto store_s16_pairs = [&](const Src& sc, const unsigned (&pre)[LM_PRE]) {
 #pragma unroll
         for (int i = 0; i < LM_PRE; i++) {
             const int pr = tid + LM_THREADS * i;
             if (pr < LM_PAIRS) s_tile16[pr + pr / 80] = pre[i];                    // raw pair, converted where it is used
+            if (gather && pr >= 100 && pr < 100 + LM_FRAMES * kHop / 2) ((unsigned*)p.trim_out)[(sc.q0 >> 1) + pr] = pre[i];   // the tile's own samples
         }
     };
     auto fetch_s16_pairs = [&](const Src& sc, unsigned (&pre)[LM_PRE]) {
+        if (gather) {
+            // segment bounds are multiples of 16 samples: a pair never straddles two segments
+            const unsigned* g0 = (const unsigned*)((const short*)p.audio + sc.add0 + sc.q0);
+            const unsigned* g1 = (const unsigned*)((const short*)p.audio + sc.add1 + sc.q0);
+            const i64 split = (sc.bound1 - sc.q0) >> 1;                           // first pair of the second segment
+#pragma unroll
+            for (int i = 0; i < LM_PRE; i++) {
+                const int pr = tid + LM_THREADS * i;
+                pre[i] = pr < LM_PAIRS ? (pr < split ? g0[pr] : g1[pr]) : 0u;
+            }
+            return;
+        }
         const unsigned* g = (const unsigned*)(sc.row + sc.q0 * 2);
 #pragma unroll
         for (int i = 0; i < LM_PRE; i++) {
@@ -330,7 +393,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
     // first tile of this CTA: synchronous
     if ((i64)blockIdx.x < n_work) {
         const Src sc = locate(blockIdx.x);
-        if (sc.mode == 1) { unsigned pre[LM_PRE]; fetch_s16_pairs(sc, pre); store_s16_pairs(pre); }
+        if (sc.mode == 1) { unsigned pre[LM_PRE]; fetch_s16_pairs(sc, pre); store_s16_pairs(sc, pre); }
         else if (sc.mode == 2) { copy_f32_pairs(sc); cp_async_drain(); }
         else load_generic(sc);
     }
@@ -382,7 +445,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
         __syncthreads();   // exchange complete; every stage-1 read of s_tile is done
 
         // ---- next tile -> s_tile (overlaps stage 2 + mel projection) ----
-        if (nsc.mode == 1) store_s16_pairs(pre);
+        if (nsc.mode == 1) store_s16_pairs(nsc, pre);
         else if (nsc.mode == 2) copy_f32_pairs(nsc);
         else if (nsc.mode == 0) load_generic(nsc);
 
@@ -501,7 +564,7 @@ template <int FMT> static size_t logmel_smem_bytes() { return (size_t)LmSmem<FMT
 
 static i64 logmel_tiles_cap(i64 n, i64 padding) {
     i64 T = (n + padding) / kHop;
-    return (T + LM_FRAMES - 1) / LM_FRAMES;
+    return (T + LM_FRAMES - 1) / LM_FRAMES + 1;     // + 1: fused compaction adds a tile for a last partial hop
 }
 
 // workspace layout: [gmax keys: batch ints, padded to 256 B][tile_min: batch * tiles_cap floats]
@@ -509,9 +572,11 @@ size_t logmel_workspace_bytes(i64 batch, i64 n, i64 padding) {
     return align_up((size_t)batch * 4, 256) + align_up((size_t)batch * (size_t)logmel_tiles_cap(n, padding) * 4, 256) + 256;
 }
 
+struct LogMelGather { const int32_t* kept_ms; const i64* kept_off; const i64* info; int16_t* trim_out; i64 n_src; };
+
 int logmel_launch(const void* d_audio, int fmt, i64 batch, i64 n, i64 row_stride, const i64* d_n, i64 padding,
                   int n_mels, int norm_mode, float* d_out, i64* d_frames_out, void* d_ws, size_t ws_bytes,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, const LogMelGather* gather = nullptr) {
     if (!d_audio || !d_out || !d_ws) { set_error("log_mel: null pointer"); return B2A_EINVAL; }
     if (fmt != B2A_FMT_S16 && fmt != B2A_FMT_F32) { set_error("log_mel: bad fmt %d", fmt); return B2A_EINVAL; }
     if (batch <= 0 || n < 0 || padding < 0 || row_stride < n) { set_error("log_mel: bad shape"); return B2A_EINVAL; }
@@ -530,6 +595,11 @@ int logmel_launch(const void* d_audio, int fmt, i64 batch, i64 n, i64 row_stride
     p.tile_min = (float*)((char*)d_ws + align_up((size_t)batch * 4, 256));
     p.tiles_cap = logmel_tiles_cap(n, padding);
     p.tab = tab;
+    p.kept_ms = nullptr; p.kept_off = nullptr; p.info = nullptr; p.trim_out = nullptr; p.n_src = 0;
+    if (gather) {
+        if (fmt != B2A_FMT_S16 || batch != 1 || !d_n) { set_error("log_mel: fused compaction needs one s16 clip with a device-side length"); return B2A_EINVAL; }
+        p.kept_ms = gather->kept_ms; p.kept_off = gather->kept_off; p.info = gather->info; p.trim_out = gather->trim_out; p.n_src = gather->n_src;
+    }
 
     i64 work = p.tiles_cap * batch;
     if (work <= 0) { if (d_frames_out) cudaMemsetAsync(d_frames_out, 0, 8, stream); return B2A_OK; }

@@ -15,9 +15,10 @@ int silence_launch(const u64* d_energy, i64 n_samples, int sample_rate, const b2
                    size_t ws_bytes, cudaStream_t stream);
 int compact_launch(const int16_t* d_pcm, i64 n_samples, int sample_rate, const int32_t* d_kept, const i64* d_kept_off,
                    const i64* d_info, int16_t* d_out, i64 out_cap, cudaStream_t stream);
+struct LogMelGather { const int32_t* kept_ms; const i64* kept_off; const i64* info; int16_t* trim_out; i64 n_src; };
 int logmel_launch(const void* d_audio, int fmt, i64 batch, i64 n, i64 row_stride, const i64* d_n, i64 padding,
                   int n_mels, int norm_mode, float* d_out, i64* d_frames_out, void* d_ws, size_t ws_bytes,
-                  cudaStream_t stream);
+                  cudaStream_t stream, const LogMelGather* gather);
 size_t logmel_workspace_bytes(i64 batch, i64 n, i64 padding);
 size_t silence_workspace_bytes(i64 n_samples, int sample_rate);
 
@@ -74,7 +75,7 @@ int pipeline_launch(const void* d_in, int fmt, int channels, int in_rate, i64 n_
         B2A_LAUNCH(k, 1, 32, 0, stream, d_info, n16, d_nonsilent, d_kept, cap);
         B2A_CHECK_LAUNCH("pipeline_notrim_info_kernel");
         return logmel_launch(d_pcm_out, B2A_FMT_S16, 1, n16, n16, d_info + B2A_INFO_N_KEEP, padding, n_mels, B2A_NORM_WHISPER,
-                             d_mel_out, d_info + B2A_INFO_N_FRAMES, ws_logmel, ws_logmel_bytes, stream);
+                             d_mel_out, d_info + B2A_INFO_N_FRAMES, ws_logmel, ws_logmel_bytes, stream, nullptr);
     }
     int16_t* pcm16 = (int16_t*)(ws + w.off_pcm);
     u64* energy = (u64*)(ws + w.off_energy);
@@ -84,11 +85,13 @@ int pipeline_launch(const void* d_in, int fmt, int channels, int in_rate, i64 n_
     rc = silence_launch(energy, n16, kSampleRate, prm, cap, nullptr, d_nonsilent, d_kept, kept_off, d_info, ws + w.off_sil,
                         w.off_keptoff - w.off_sil, stream);
     if (rc) return rc;
-    rc = compact_launch(pcm16, n16, kSampleRate, d_kept, kept_off, d_info, d_pcm_out, n16 + 16, stream);
-    if (rc) return rc;
-    // the compacted length lives in d_info[N_KEEP]; n16 + 16 is its upper bound (pydub may zero-fill < 1 ms)
-    return logmel_launch(d_pcm_out, B2A_FMT_S16, 1, n16 + 16, n16 + 16, d_info + B2A_INFO_N_KEEP, padding, n_mels, B2A_NORM_WHISPER,
-                         d_mel_out, d_info + B2A_INFO_N_FRAMES, ws_logmel, ws_logmel_bytes, stream);
+    // stream compaction is fused into the log-mel tile loader: it gathers the kept ranges from the untrimmed PCM and
+    // writes the trimmed PCM as it goes.  The compacted length lives in d_info[N_KEEP]; n16 + 16 is its upper bound
+    // (pydub may zero-fill < 1 ms)
+    LogMelGather g;
+    g.kept_ms = d_kept; g.kept_off = kept_off; g.info = d_info; g.trim_out = d_pcm_out; g.n_src = n16;
+    return logmel_launch(pcm16, B2A_FMT_S16, 1, n16 + 16, n16 + 16, d_info + B2A_INFO_N_KEEP, padding, n_mels, B2A_NORM_WHISPER,
+                         d_mel_out, d_info + B2A_INFO_N_FRAMES, ws_logmel, ws_logmel_bytes, stream, &g);
 }
 
 }  // namespace b2a

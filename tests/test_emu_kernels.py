@@ -167,3 +167,25 @@ def test_emu_fir_tcgen05_tiles(emu, rate, grid, impl, monkeypatch):
     if swr_ref.available():
         _cmp16(y, swr_ref.convert(x, rate), 0.998)
     assert np.array_equal(en.astype(np.int64), H.energy_oracle(y))
+
+
+@pytest.mark.parametrize("keep,pad,extra", [(0, 0, 37), (30, 480, 0), (0, 0, 160 * 32 + 5)])
+def test_emu_pipeline_fused_compaction_many_short_segments(emu, keep, pad, extra):
+    """the log-mel tile loader gathers the kept ranges itself and writes the trimmed PCM (no compaction kernel): bursts of
+    120-300 ms put three and more segments under one 5360-sample tile (per-sample segment search), the clip lengths leave
+    a partial last hop / a whole extra tile of trimmed samples behind the last frame, with and without right padding"""
+    rng = np.random.default_rng(keep + pad + extra)
+    parts = []
+    for i in range(28):
+        n_b = int(rng.integers(120, 300)) * 16
+        parts.append((rng.standard_normal(n_b) * 4000).astype(np.int16))
+        parts.append((rng.standard_normal(int(rng.integers(140, 260)) * 16) * 3).astype(np.int16))
+    parts.append((rng.standard_normal(16 * 400 + extra) * 4000).astype(np.int16))
+    x = np.concatenate(parts)
+    kw = dict(min_silence_len=100, silence_thresh=-50, keep_silence=keep, seek_step=1)
+    r = emu.pipeline(x, 16000, n_mels=80, padding=pad, **kw)
+    assert r["kept"] == ps.kept_ranges_fast(x, 16000, **kw) and len(r["kept"]) >= 20
+    trimmed = ps.strip_silence_fast(x, 16000, **kw)
+    assert np.array_equal(r["pcm"], trimmed)
+    ref = wl.log_mel_spectrogram(trimmed.astype(np.float32) / 32768.0, 80, padding=pad).numpy()
+    assert r["mel"].shape == ref.shape and np.abs(r["mel"] - ref).max() <= 1e-4

@@ -284,6 +284,27 @@ def test_pipeline_vs_oracle(ops, T, rate, ch, secs, nm, pad):
     assert tuple(r.mel.shape) == ref.shape and np.abs(r.mel.cpu().numpy() - ref).max() <= MEL_TOL
 
 
+@pytest.mark.parametrize("keep,pad,extra", [(0, 0, 37), (30, 480, 0), (0, 0, 160 * 32 + 5)])
+def test_pipeline_fused_compaction_many_short_segments(ops, T, keep, pad, extra):
+    """the log-mel tile loader gathers the kept ranges itself and writes the trimmed PCM (no compaction kernel): three and
+    more segments under one tile, partial last hop / an extra tile of trimmed samples behind the last frame, padding"""
+    from oracle import pydub_silence as ps, whisper_logmel as wl
+    rng = np.random.default_rng(keep + pad + extra)
+    parts = []
+    for i in range(28):
+        parts.append((rng.standard_normal(int(rng.integers(120, 300)) * 16) * 4000).astype(np.int16))
+        parts.append((rng.standard_normal(int(rng.integers(140, 260)) * 16) * 3).astype(np.int16))
+    parts.append((rng.standard_normal(16 * 400 + extra) * 4000).astype(np.int16))
+    x = np.concatenate(parts)
+    kw = dict(min_silence_len=100, silence_thresh=-50, keep_silence=keep, seek_step=1)
+    r = ops.pipeline(T.from_numpy(x).cuda(), 16000, n_mels=80, padding=pad, **kw)
+    assert r.kept == ps.kept_ranges_fast(x, 16000, **kw) and len(r.kept) >= 20
+    trimmed = ps.strip_silence_fast(x, 16000, **kw)
+    assert np.array_equal(r.pcm.cpu().numpy(), trimmed)
+    ref = wl.log_mel_spectrogram(trimmed.astype(np.float32) / 32768.0, 80, padding=pad).numpy()
+    assert tuple(r.mel.shape) == ref.shape and np.abs(r.mel.cpu().numpy() - ref).max() <= MEL_TOL
+
+
 def test_pipeline_notrim_and_service(ops, T, tmp_path):
     from audio_processor_b200 import synth, wavio
     from audio_processor_b200.service import AudioFrontend
