@@ -239,6 +239,8 @@ def run_b200(args):
     dev = torch.device(f"cuda:{local}")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its version banner on stdout: stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     desc, in_rate, ch, secs, sil, clips, n_mels, seed = WORKLOADS[args.workload]
     if args.clips:
