@@ -35,6 +35,7 @@ constexpr int LM_SKEW = 2;                          // extra words per hop (bank
 constexpr int LM_HOPW = kHop + LM_SKEW;             // words between consecutive frames in the skewed tile
 constexpr int LM_TILE_WORDS = LM_TILE + LM_SKEW * (LM_TILE / kHop + 1);
 constexpr int LM_EXP = 201;                         // exchange pitch per frame, in complex values (odd: conflict free)
+constexpr int LM_GBATCH = 32;                       // gathered tiles whose segment descriptors are looked up together
 constexpr int LM_PP = 203;                          // power-spectrum pitch per frame, in floats (odd)
 
 #ifndef B2A_MEL_TABLES_INCLUDED
@@ -225,11 +226,11 @@ constexpr int LM_PRE = (LM_PAIRS + LM_THREADS - 1) / LM_THREADS;        // 17 pa
 template <int FMT> struct LmSmem {
     static constexpr int TILE_WORDS = ((FMT == B2A_FMT_S16 ? (LM_TILE / 2 + (LM_TILE / kHop + 2)) : LM_TILE_WORDS) + 3) / 4 * 4;   // keeps the buffers behind it 16-byte aligned
     static constexpr int HOPW = FMT == B2A_FMT_S16 ? (kHop / 2 + 1) : LM_HOPW;      // words between frames (81: odd, conflict free)
-    static constexpr int WORDS = TILE_WORDS + 2 * LM_FRAMES * LM_EXP + kNFFT + 2 * 200 + 2 * 202 + 8 + kMelFlatN128 + 2 * kMelMaxMels;
+    static constexpr int WORDS = TILE_WORDS + 2 * LM_FRAMES * LM_EXP + kNFFT + 2 * 200 + 2 * 202 + 8 + kMelFlatN128 + 2 * kMelMaxMels + 12 * LM_GBATCH;   // + LM_GBATCH x 6 int64 gather descriptors
     static constexpr int CTAS = FMT == B2A_FMT_S16 ? 3 : 2;
 };
 
-template <int NM, int FMT>
+template <int NM, int FMT, bool GATHER>
 __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel(LogMelParams p) {
     using SM = LmSmem<FMT>;
     constexpr bool S16 = FMT == B2A_FMT_S16;
@@ -244,6 +245,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
     float* s_red = (float*)(s_tw400 + 202);                             // 8
     float4* s_flat4 = (float4*)(s_red + 8);                             // padded mel weights (<= kMelFlatN128 floats, 16-byte aligned)
     uint2* s_desc = (uint2*)(s_flat4 + kMelFlatN128 / 4);                // n_mels filter descriptors
+    i64* s_g = (i64*)(s_desc + kMelMaxMels);                            // [LM_GBATCH][6]: lo0, add0, bound1, add1, bound2, mode of the CTA's next gathered tiles
 
     const int tid = threadIdx.x;
     const LogMelTables* tab = p.tab;
@@ -258,7 +260,8 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
     if (p.d_n) { n_act = *p.d_n; if (n_act > p.n) n_act = p.n; if (n_act < 0) n_act = 0; }
     const i64 ltot = n_act + p.padding;          // padded length
     const i64 T = ltot / kHop;                   // frames
-    const bool gather = S16 && p.kept_ms != nullptr;
+    constexpr bool gather = GATHER;                                     // fused stream compaction: own instantiation, the plain kernel keeps its registers
+    static_assert(!GATHER || S16, "fused compaction is an s16 path");
     const int n_seg = gather ? (int)p.info[B2A_INFO_N_KEPT] : 0;
     i64 tiles = (T + LM_FRAMES - 1) / LM_FRAMES;
     if (gather && tiles * (LM_FRAMES * kHop) < n_act) tiles++;          // a last partial hop still has trimmed samples to write
@@ -287,8 +290,8 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
     const i64 n_work = tiles * p.batch;
 
     // where a work item's samples live: row base, first padded-domain index, and whether the fast (interior) path applies
-    struct Src { const char* row; i64 q0; int mode; i64 lo0, add0, bound1, add1, bound2; };   // mode 0: generic (reflect / zero pad), 1: interior s16, 2: interior f32
-    // gather: source sample of trimmed index q (segment search; the two segments cached in a Src cover an interior tile)
+    struct Src { const char* row; i64 q0; int mode; const i64* g; };   // mode 0: generic (reflect / zero pad), 1: interior s16, 2: interior f32; g: gather descriptor (shared memory)
+    // gather: source sample of trimmed index q (segment search; the two segments cached per tile cover an interior tile)
     auto seg_of = [&](i64 q) -> int {
         int lo = 0, hi = n_seg - 1;
         while (lo < hi) {
@@ -297,39 +300,50 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
         }
         return lo;
     };
-    auto locate = [&](i64 work) -> Src {
+    // gathered tiles: every LM_GBATCH iterations the first LM_GBATCH threads look up the segments under the CTA's next
+    // tiles (one binary search each, in parallel) and publish lo0, add0, bound1, add1, bound2, mode in shared memory
+    auto lookup_batch = [&](i64 work0) {
+        if (tid < LM_GBATCH) {
+            const i64 work = work0 + (i64)tid * gridDim.x;
+            if (work < tiles * p.batch) {
+                const i64 q0 = (work % tiles) * (LM_FRAMES * kHop) - 200;
+                i64 lo0 = 0, add0 = 0, add1 = 0, bound1 = (i64)1 << 62, bound2 = (i64)1 << 62;
+                if (n_seg > 0) {
+                    const int sg = seg_of(q0 > 0 ? q0 : 0);
+                    lo0 = p.kept_off[sg];
+                    add0 = (i64)p.kept_ms[2 * sg] * 16 - lo0;
+                    if (sg + 1 < n_seg) { bound1 = p.kept_off[sg + 1]; add1 = (i64)p.kept_ms[2 * sg + 2] * 16 - bound1; }
+                    if (sg + 2 < n_seg) bound2 = p.kept_off[sg + 2];
+                }
+                // interior: inside the clip, at most two segments under the tile, every source sample inside the buffer
+                const bool interior = q0 >= 0 && q0 + LM_TILE <= n_act && q0 + LM_TILE <= bound2 && add0 + q0 >= 0 &&
+                                      add0 + (bound1 < q0 + LM_TILE ? bound1 : q0 + LM_TILE) <= p.n_src &&
+                                      (bound1 >= q0 + LM_TILE || add1 + q0 + LM_TILE <= p.n_src);
+                i64* g = s_g + 6 * tid;
+                g[0] = lo0; g[1] = add0; g[2] = bound1; g[3] = add1; g[4] = bound2; g[5] = interior ? 1 : 0;
+            }
+        }
+    };
+    auto locate = [&](i64 work, int slot) -> Src {
         Src r;
         const int b = (int)(work / tiles);
         const i64 tile = work - (i64)b * tiles;
         r.row = (const char*)p.audio + (size_t)b * (size_t)p.row_stride * elem;
         r.q0 = tile * (LM_FRAMES * kHop) - 200;
-        r.add0 = r.add1 = 0;
-        r.lo0 = 0;
-        r.bound1 = r.bound2 = (i64)1 << 62;
-        bool interior = r.q0 >= 0 && r.q0 + LM_TILE <= n_act;
+        r.g = s_g + 6 * slot;
         if (gather) {
-            if (n_seg > 0) {
-                const int sg = seg_of(r.q0 > 0 ? r.q0 : 0);
-                r.lo0 = p.kept_off[sg];
-                r.add0 = (i64)p.kept_ms[2 * sg] * 16 - r.lo0;
-                if (sg + 1 < n_seg) { r.bound1 = p.kept_off[sg + 1]; r.add1 = (i64)p.kept_ms[2 * sg + 2] * 16 - r.bound1; }
-                if (sg + 2 < n_seg) r.bound2 = p.kept_off[sg + 2];
-            }
-            // interior: at most two segments under the tile and every source sample inside the buffer
-            interior = interior && r.q0 + LM_TILE <= r.bound2 && r.add0 + r.q0 >= 0 &&
-                       r.add0 + (r.bound1 < r.q0 + LM_TILE ? r.bound1 : r.q0 + LM_TILE) <= p.n_src &&
-                       (r.bound1 >= r.q0 + LM_TILE || r.add1 + r.q0 + LM_TILE <= p.n_src);
+            r.mode = (int)r.g[5];
         } else {
-            interior = interior && ((((uintptr_t)(r.row + r.q0 * elem)) & 7) == 0);
+            const bool interior = r.q0 >= 0 && r.q0 + LM_TILE <= n_act && ((((uintptr_t)(r.row + r.q0 * elem)) & 7) == 0);
+            r.mode = interior ? (S16 ? 1 : 2) : 0;
         }
-        r.mode = interior ? (S16 ? 1 : 2) : 0;
         return r;
     };
     // trimmed-domain sample q of a gathered clip (0 <= q < n_act)
     auto gather_sample = [&](const Src& sc, i64 q) -> short {
         i64 si;
-        if (q >= sc.lo0 && q < sc.bound1) si = sc.add0 + q;                   // the two segments cached for the tile
-        else if (q >= sc.bound1 && q < sc.bound2) si = sc.add1 + q;
+        if (q >= sc.g[0] && q < sc.g[2]) si = sc.g[1] + q;                    // the two segments cached for the tile
+        else if (q >= sc.g[2] && q < sc.g[4]) si = sc.g[3] + q;
         else { const int sg = seg_of(q); si = (i64)p.kept_ms[2 * sg] * 16 + (q - p.kept_off[sg]); }
         return (si >= 0 && si < p.n_src) ? ((const short*)p.audio)[si] : (short)0;
     };
@@ -364,9 +378,9 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
     auto fetch_s16_pairs = [&](const Src& sc, unsigned (&pre)[LM_PRE]) {
         if (gather) {
             // segment bounds are multiples of 16 samples: a pair never straddles two segments
-            const unsigned* g0 = (const unsigned*)((const short*)p.audio + sc.add0 + sc.q0);
-            const unsigned* g1 = (const unsigned*)((const short*)p.audio + sc.add1 + sc.q0);
-            const i64 split = (sc.bound1 - sc.q0) >> 1;                           // first pair of the second segment
+            const unsigned* g0 = (const unsigned*)((const short*)p.audio + sc.g[1] + sc.q0);
+            const unsigned* g1 = (const unsigned*)((const short*)p.audio + sc.g[3] + sc.q0);
+            const i64 split = (sc.g[2] - sc.q0) >> 1;                             // first pair of the second segment
 #pragma unroll
             for (int i = 0; i < LM_PRE; i++) {
                 const int pr = tid + LM_THREADS * i;
@@ -392,7 +406,8 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
 
     // first tile of this CTA: synchronous
     if ((i64)blockIdx.x < n_work) {
-        const Src sc = locate(blockIdx.x);
+        if (gather) { lookup_batch(blockIdx.x); __syncthreads(); }
+        const Src sc = locate(blockIdx.x, 0);
         if (sc.mode == 1) { unsigned pre[LM_PRE]; fetch_s16_pairs(sc, pre); store_s16_pairs(sc, pre); }
         else if (sc.mode == 2) { copy_f32_pairs(sc); cp_async_drain(); }
         else load_generic(sc);
@@ -405,7 +420,14 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
         const i64 nwork = work + gridDim.x;
         Src nsc;
         nsc.mode = -1;
-        if (nwork < n_work) nsc = locate(nwork);
+        nsc.g = s_g;
+        const int nit = (int)((work - blockIdx.x) / gridDim.x) + 1;              // iteration index of the next tile
+        if (gather && nit % LM_GBATCH == 0) {
+            __syncthreads();                                                       // every reader of the old batch is done
+            lookup_batch(nwork);
+            __syncthreads();
+        }
+        if (nwork < n_work) nsc = locate(nwork, nit % LM_GBATCH);
 
         __syncthreads();   // s_tile (and, first time, the tables) visible; previous tile's s_red written
         if (tid == 0 && prev_slot >= 0) {
@@ -608,8 +630,9 @@ int logmel_launch(const void* d_audio, int fmt, i64 batch, i64 n, i64 row_stride
     B2A_LAUNCH(kinit, (nkeys + 255) / 256, 256, 0, stream, p.gmax_key, nkeys);
     const bool s16 = fmt == B2A_FMT_S16;
     size_t smem = s16 ? logmel_smem_bytes<B2A_FMT_S16>() : logmel_smem_bytes<B2A_FMT_F32>();
-    auto k4 = n_mels == 80 ? (s16 ? stft_mel_kernel<80, B2A_FMT_S16> : stft_mel_kernel<80, B2A_FMT_F32>)
-                           : (s16 ? stft_mel_kernel<128, B2A_FMT_S16> : stft_mel_kernel<128, B2A_FMT_F32>);
+    auto k4 = gather ? (n_mels == 80 ? stft_mel_kernel<80, B2A_FMT_S16, true> : stft_mel_kernel<128, B2A_FMT_S16, true>)
+              : n_mels == 80 ? (s16 ? stft_mel_kernel<80, B2A_FMT_S16, false> : stft_mel_kernel<80, B2A_FMT_F32, false>)
+                             : (s16 ? stft_mel_kernel<128, B2A_FMT_S16, false> : stft_mel_kernel<128, B2A_FMT_F32, false>);
     {
         cudaError_t e = cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // idempotent, cheap
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(stft_mel)");
