@@ -524,6 +524,8 @@ def run_b200(args):
                              if in_bytes > 2.5e8 else "input smaller than L2: L2-resident between steps (latency config)"},
             "gpu_launches": int(launches),
             "stages_ms": {k: round(v, 4) for k, v in stages.items()},
+            "stages_note": "each stage timed alone through its own entry point (b2a_resample / b2a_detect_silence / b2a_compact / b2a_log_mel); "
+                           "the timed step runs b2a_pipeline, where the compaction is fused into the log-mel tile loader",
             "roofline": {"bound": "hbm", "kernel": roof["kernel"], "achieved": roof["bytes"] / (roof["ms"] * 1e-3) / 1e9,
                          "peak": peak, "unit": "GB/s", "frac": roof["bytes"] / (roof["ms"] * 1e-3) / 1e9 / peak,
                          "peak_source": peak_src, "traffic": measured_traffic(args.workload, roof["kernel"].split(" ")[0]), "algorithmic_bytes_per_launch": int(roof["bytes"]),

@@ -1,5 +1,5 @@
 #!/bin/bash
-# one GPU call: tests-free bench of every workload + ncu launch list + full capture of the two top kernels
+# one GPU call: tests + bench of every workload + ncu launch list + full capture of the two top kernels
 set -x
 timeout -s KILL 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 mkdir -p gpurun_out
