@@ -208,12 +208,20 @@ __device__ __forceinline__ void mel_group(const uint2* __restrict__ s_desc, cons
 }
 
 #ifndef B2A_EMU
+// 32-bit global load that stays where it is written (memory clobber): the next tile's prefetch must be issued before
+// stage 1, not sunk to its first use behind it
+__device__ __forceinline__ unsigned ldg_pinned(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
     unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_drain() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
 #else
+static inline unsigned ldg_pinned(const unsigned* p) { return *p; }
 static inline void cp_async8(void* smem_dst, const void* gsrc) { memcpy(smem_dst, gsrc, 8); }
 static inline void cp_async_drain() {}
 #endif
@@ -290,6 +298,15 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
     const i64 n_work = tiles * p.batch;
 
     // where a work item's samples live: row base, first padded-domain index, and whether the fast (interior) path applies
+    // work item -> (clip b, tile): one clip needs no division, batches stay in 32 bits (a 64-bit division is ~70 dependent
+    // instructions at the top of every tile, ahead of the barrier everybody waits at)
+    const bool one_clip = p.batch == 1;
+    const bool small_work = tiles * p.batch < ((i64)1 << 31);
+    auto split_work = [&](i64 work, int& b, i64& tile) {
+        if (one_clip) { b = 0; tile = work; }
+        else if (small_work) { b = (int)((unsigned)work / (unsigned)tiles); tile = (i64)((unsigned)work - (unsigned)b * (unsigned)tiles); }
+        else { b = (int)(work / tiles); tile = work - (i64)b * tiles; }
+    };
     struct Src { const char* row; i64 q0; int mode; const i64* g; };   // mode 0: generic (reflect / zero pad), 1: interior s16, 2: interior f32; g: gather descriptor (shared memory)
     // gather: source sample of trimmed index q (segment search; the two segments cached per tile cover an interior tile)
     auto seg_of = [&](i64 q) -> int {
@@ -326,8 +343,9 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
     };
     auto locate = [&](i64 work, int slot) -> Src {
         Src r;
-        const int b = (int)(work / tiles);
-        const i64 tile = work - (i64)b * tiles;
+        int b;
+        i64 tile;
+        split_work(work, b, tile);
         r.row = (const char*)p.audio + (size_t)b * (size_t)p.row_stride * elem;
         r.q0 = tile * (LM_FRAMES * kHop) - 200;
         r.g = s_g + 6 * slot;
@@ -384,7 +402,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
 #pragma unroll
             for (int i = 0; i < LM_PRE; i++) {
                 const int pr = tid + LM_THREADS * i;
-                pre[i] = pr < LM_PAIRS ? (pr < split ? g0[pr] : g1[pr]) : 0u;
+                pre[i] = pr < LM_PAIRS ? ldg_pinned(pr < split ? g0 + pr : g1 + pr) : 0u;
             }
             return;
         }
@@ -392,7 +410,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
 #pragma unroll
         for (int i = 0; i < LM_PRE; i++) {
             const int pr = tid + LM_THREADS * i;
-            pre[i] = pr < LM_PAIRS ? g[pr] : 0u;
+            pre[i] = pr < LM_PAIRS ? ldg_pinned(g + pr) : 0u;
         }
     };
     auto copy_f32_pairs = [&](const Src& sc) {
@@ -414,8 +432,9 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
     }
 
     for (i64 work = blockIdx.x; work < n_work; work += gridDim.x) {
-        const int b = (int)(work / tiles);
-        const i64 tile = work - (i64)b * tiles;
+        int b;
+        i64 tile;
+        split_work(work, b, tile);
         const i64 t0 = tile * LM_FRAMES;
         const i64 nwork = work + gridDim.x;
         Src nsc;
