@@ -46,9 +46,13 @@ def _as_cuda_pcm(torch, pcm, device=None):
     return pcm.contiguous()
 
 
+_graph_launches = 0     # kernels launched through replays of captured pipeline graphs (the library only counts its own launch calls)
+
+
 def launch_count() -> int:
-    """kernels launched by libb2a so far in this process (diagnostics / bench `gpu_launches`)."""
-    return int(lib().b2a_launch_count())
+    """CUDA kernels of libb2a launched by this process so far: the library's own launch calls plus the kernels inside
+    every replayed pipeline graph (PipelinePlan.run(graph=True))."""
+    return int(lib().b2a_launch_count()) + _graph_launches
 
 
 def resample_out_len(n_in: int, in_rate: int, out_rate: int = SAMPLE_RATE) -> int:
@@ -231,9 +235,15 @@ class PipelinePlan:
             self.ws = torch.empty(self.ws_bytes + 512, dtype=torch.uint8, device=self.device)
             off = (-self.ws.data_ptr()) % 256
             self._ws_ptr = C.c_void_p(self.ws.data_ptr() + off)
+        self._graphs = {}        # (input pointer, silence parameters) -> captured CUDA graph of the 8 launches (run(graph=True))
+        self._warm = set()
 
     def run(self, pcm, *, trim: bool = True, min_silence_len: int = 1000, silence_thresh: float = -40,
-            keep_silence: Union[int, bool] = 200, seek_step: int = 1) -> "PipelineResult":
+            keep_silence: Union[int, bool] = 200, seek_step: int = 1, graph: bool = False) -> "PipelineResult":
+        """Enqueue the whole path for one clip on the current stream.  graph=True replays a CUDA graph of the same
+        b2a_pipeline call (captured on the second use of an input buffer with the same parameters): one launch instead
+        of eight, for callers that keep their input in a fixed device buffer (ClipStream slots, the benchmark)."""
+        global _graph_launches
         torch = self.torch
         x = pcm
         if (not x.is_cuda) or x.dtype != self.dtype or not x.is_contiguous():
@@ -242,11 +252,36 @@ class PipelinePlan:
         if int(x.shape[0]) != self.n_in or ch != self.channels:
             raise ValueError("clip shape differs from the plan")
         prm = _params(min_silence_len, silence_thresh, keep_silence, seek_step) if trim else None
-        with torch.cuda.device(self.device):
+
+        def launch():
             check(lib().b2a_pipeline(_ptr(x), self.fmt, ch, self.in_rate, self.n_in, C.byref(prm) if prm is not None else None,
                                      self.n_mels, self.padding, self.cap, _ptr(self.pcm), _ptr(self.mel),
                                      _ptr(self.nonsilent), _ptr(self.kept), _ptr(self.info), self._ws_ptr, self.ws_bytes,
                                      _stream(torch)))
+
+        with torch.cuda.device(self.device):
+            if not graph:
+                launch()
+                return PipelineResult(self)
+            key = (x.data_ptr(), bool(trim), int(min_silence_len), float(silence_thresh), keep_silence, int(seek_step))
+            g = self._graphs.get(key)
+            if g is None:
+                if key not in self._warm:                # first use: run eagerly (builds the device tables, sets kernel attributes)
+                    self._warm.add(key)
+                    launch()
+                    return PipelineResult(self)
+                g = torch.cuda.CUDAGraph()
+                cap_stream = torch.cuda.Stream(device=self.device)
+                cap_stream.wait_stream(torch.cuda.current_stream())
+                n0 = int(lib().b2a_launch_count())
+                with torch.cuda.graph(g, stream=cap_stream):
+                    launch()
+                torch.cuda.current_stream().wait_stream(cap_stream)
+                g = (g, int(lib().b2a_launch_count()) - n0)      # the graph and the number of kernels it holds
+                self._graphs[key] = g
+                _graph_launches -= g[1]                           # the capture only recorded them; the replay below runs them
+            g[0].replay()
+            _graph_launches += g[1]
         return PipelineResult(self)
 
 

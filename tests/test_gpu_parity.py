@@ -305,6 +305,28 @@ def test_pipeline_fused_compaction_many_short_segments(ops, T, keep, pad, extra)
     assert tuple(r.mel.shape) == ref.shape and np.abs(r.mel.cpu().numpy() - ref).max() <= MEL_TOL
 
 
+def test_pipeline_graph_replay_matches_direct_calls(ops, T):
+    """PipelinePlan.run(graph=True): first use eager, second captures, later ones replay one CUDA graph of the same
+    b2a_pipeline call — same bytes out as the direct call, and the launch counter still sees every kernel"""
+    from audio_processor_b200 import synth
+    x = synth.synth_clip(5, 44100, 2, 9.0, 0.3, device="cuda")
+    kw = dict(min_silence_len=1000, silence_thresh=-40, keep_silence=200)
+    ref = ops.PipelinePlan(int(x.shape[0]), 44100, 2, x.dtype, n_mels=80).run(x, **kw)
+    pcm0, mel0, kept0 = ref.pcm.clone(), ref.mel.clone(), ref.kept
+    plan = ops.PipelinePlan(int(x.shape[0]), 44100, 2, x.dtype, n_mels=80)
+    per_call = None
+    for i in range(4):
+        n0 = ops.launch_count()
+        plan.pcm.zero_(); plan.mel.zero_()
+        r = plan.run(x, graph=True, **kw)
+        T.cuda.synchronize()
+        n = ops.launch_count() - n0
+        per_call = n if per_call is None else per_call
+        assert n == per_call and n >= 6
+        assert r.kept == kept0 and T.equal(r.pcm, pcm0) and T.equal(r.mel, mel0)
+    assert len(plan._graphs) == 1
+
+
 def test_pipeline_notrim_and_service(ops, T, tmp_path):
     from audio_processor_b200 import synth, wavio
     from audio_processor_b200.service import AudioFrontend
