@@ -274,7 +274,7 @@ class PipelinePlan:
                 cap_stream = torch.cuda.Stream(device=self.device)
                 cap_stream.wait_stream(torch.cuda.current_stream())
                 n0 = int(lib().b2a_launch_count())
-                with torch.cuda.graph(g, stream=cap_stream):
+                with torch.cuda.graph(g, stream=cap_stream, capture_error_mode="thread_local"):   # other threads (NCCL watchdog, job workers) keep using CUDA
                     launch()
                 torch.cuda.current_stream().wait_stream(cap_stream)
                 g = (g, int(lib().b2a_launch_count()) - n0)      # the graph and the number of kernels it holds
