@@ -72,7 +72,7 @@ struct CUtensorMap { const unsigned char* base; long long row_stride_bytes; };
 
 struct FirTmemArgs {
     alignas(64) CUtensorMap tmap;   // uint32 frames, dims {kFtTensorD0, rows}, row stride 4 S frames, box {32, 128}, SWIZZLE_128B
-    const unsigned char* in;        // the clip (for the L2 prefetch of the next span)
+    const unsigned char* in;        // the clip (diagnostics)
     int16_t* out_s16;               // nullable
     u64* energy;                    // nullable
     const uint4* btab;              // [class][B_BYTES] filter banks (build_fir_umma_table)
