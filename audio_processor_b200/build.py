@@ -74,7 +74,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(job):
         src, obj = job
-        cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-c", src, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("B2A_NVCC_EXTRA", "").split(), "-I", os.path.join(ROOT, "include"), "-c", src, "-o", obj]   # B2A_NVCC_EXTRA: experiment knobs (-D...)
         if verbose:
             cmd.insert(1, "-Xptxas")
             cmd.insert(2, "-v")

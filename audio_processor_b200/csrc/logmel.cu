@@ -35,6 +35,9 @@ constexpr int LM_SKEW = 2;                          // extra words per hop (bank
 constexpr int LM_HOPW = kHop + LM_SKEW;             // words between consecutive frames in the skewed tile
 constexpr int LM_TILE_WORDS = LM_TILE + LM_SKEW * (LM_TILE / kHop + 1);
 constexpr int LM_EXP = 201;                         // exchange pitch per frame, in complex values (odd: conflict free)
+#ifndef LM_S16_CTAS
+#define LM_S16_CTAS 3
+#endif
 constexpr int LM_GBATCH = 32;                       // gathered tiles whose segment descriptors are looked up together
 constexpr int LM_PP = 203;                          // power-spectrum pitch per frame, in floats (odd)
 
@@ -235,7 +238,7 @@ template <int FMT> struct LmSmem {
     static constexpr int TILE_WORDS = ((FMT == B2A_FMT_S16 ? (LM_TILE / 2 + (LM_TILE / kHop + 2)) : LM_TILE_WORDS) + 3) / 4 * 4;   // keeps the buffers behind it 16-byte aligned
     static constexpr int HOPW = FMT == B2A_FMT_S16 ? (kHop / 2 + 1) : LM_HOPW;      // words between frames (81: odd, conflict free)
     static constexpr int WORDS = TILE_WORDS + 2 * LM_FRAMES * LM_EXP + kNFFT + 2 * 200 + 2 * 202 + 8 + kMelFlatN128 + 2 * kMelMaxMels + 12 * LM_GBATCH;   // + LM_GBATCH x 6 int64 gather descriptors
-    static constexpr int CTAS = FMT == B2A_FMT_S16 ? 3 : 2;
+    static constexpr int CTAS = FMT == B2A_FMT_S16 ? LM_S16_CTAS : 2;
 };
 
 template <int NM, int FMT, bool GATHER>
