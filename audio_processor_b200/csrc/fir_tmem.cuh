@@ -51,7 +51,8 @@ constexpr int kFtTensorD0 = 2304;          // declared inner extent of the (over
 template <int IN_RATE>
 struct FirTmemGeom : FirUmmaGeom<IN_RATE> {
     using G = FirUmmaGeom<IN_RATE>;
-    // plane ring in TMEM: a block window must leave one piece for the converters (4 pieces at 44.1 kHz, 5 at 48 kHz)
+    // plane ring in TMEM: a block window must leave one piece for the converters (4 pieces at 44.1 kHz, 5 at 48 kHz);
+    // a 5-piece ring at 44.1 kHz (5 accumulator slots instead of 7) was measured: 160 -> 164 us, no gain
     static constexpr int A_PIECES = G::max_span() + 1 > 4 ? G::max_span() + 1 : 4;
     static constexpr int A_CHUNKS = A_PIECES * kFuPiece / 8;
     static constexpr int PLANE_COLS = A_CHUNKS * 4 + 4;                  // + mirror of chunk 0
@@ -80,7 +81,7 @@ struct FirTmemArgs {
     u64* energy;                    // nullable
     const uint4* btab;              // [class][B_BYTES] filter banks (build_fir_umma_table)
     int spans;
-    int phases;                     // profiling aid (env B2A_FIR_PHASES): bit 2 epilogue stores; 31 = the product
+    int phases;                     // profiling aid (env B2A_FIR_PHASES): bit 0 conversion (LDS + split + tcgen05.st), bit 1 MMAs, bit 2 epilogue stores; 31 = the product
     GenericParams edge;             // the clip's head and tail outputs (table-driven, one thread per output): warps 6-7
     i64 edge_total;                 // linear indices of `edge` (resample_generic_total), 0 = none
 };
@@ -161,6 +162,7 @@ struct FirTmemIssue {
     saddr_t pf0, pe0, df0, de0;
     unsigned b_lo0, b_hi, tmem;
     unsigned piece0, chunk_base, blk_base;
+    int phases;
 };
 
 template <int IN_RATE, int J>
@@ -185,8 +187,10 @@ __device__ __forceinline__ void fir_tmem_issue_item(const FirTmemIssue& c) {
     // the last ring chunk pairs with the mirror of chunk 0 stored right behind it
     const unsigned a_col = ((c.chunk_base + cidx) % G::A_CHUNKS) * 4u;
     const unsigned b_lo = c.b_lo0 + bidx * (unsigned)(kFuBTile >> 4);
-    umma_ts_warp(d_tmem, c.tmem + G::COL_HV + a_col, b_lo, c.b_hi, kFuIdesc, first ? 0u : 1u);
-    umma_ts_warp(d_tmem, c.tmem + G::COL_LO + a_col, b_lo, c.b_hi, kFuIdesc, 1u);
+    if (c.phases & 2) {
+        umma_ts_warp(d_tmem, c.tmem + G::COL_HV + a_col, b_lo, c.b_hi, kFuIdesc, first ? 0u : 1u);
+        umma_ts_warp(d_tmem, c.tmem + G::COL_LO + a_col, b_lo, c.b_hi, kFuIdesc, 1u);
+    }
     if constexpr (last) umma_commit_warp(c.df0 + ds * kFmBarBytes);
     if constexpr (frees > 0) {
         constexpr unsigned freed0 = [] { unsigned f = 0; for (int k = 0; k < J; k++) f += (FirUmmaSchedOf<IN_RATE>::value.w[k] >> 24) & 15u; return f; }();
@@ -283,7 +287,7 @@ __global__ void __launch_bounds__(kFtThreads, 1) fir_tmem_kernel(const __grid_co
         FirTmemIssue c;
         c.pf0 = PF(0); c.pe0 = PE(0); c.df0 = DF(0); c.de0 = DE(0);
         c.b_lo0 = desc_start(smem_addr(btab)) | ((unsigned)(kFuBLbo >> 4) << 16); c.b_hi = (unsigned)(kFuBSbo >> 4) | (1u << 14);
-        c.tmem = tmem;
+        c.tmem = tmem; c.phases = a.phases;
         c.piece0 = 0; c.blk_base = 0;
 #pragma unroll 1
         for (int it = 0; it < n_tiles; it++, c.piece0 += G::PIECES, c.blk_base += kFmBlocks) {
@@ -326,6 +330,17 @@ __global__ void __launch_bounds__(kFtThreads, 1) fir_tmem_kernel(const __grid_co
         unsigned rparity = 0, aparity = 1;                        // plane slots pass on first use
         for (int P = 0; P < total; P++) {
             mbar_wait(RF(rslot), rparity);                        // the piece's raw frames landed
+            if (!(a.phases & 1)) {                                // profiling: barrier traffic only
+                __syncwarp();
+                if (lane == 0) mbar_arrive(RE(rslot));
+                mbar_wait(PE(aslot), aparity);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(PF(aslot));
+                if (++rslot == kFtRawSlots) { rslot = 0; rparity ^= 1u; }
+                if (++aslot == G::A_PIECES) { aslot = 0; aparity ^= 1u; }
+                continue;
+            }
             uint4 v[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) v[j] = lds128(row_s + (unsigned)(rslot * kFtPieceBytes) + (((unsigned)j ^ sw) << 4));
