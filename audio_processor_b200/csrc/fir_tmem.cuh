@@ -81,7 +81,7 @@ struct FirTmemArgs {
     u64* energy;                    // nullable
     const uint4* btab;              // [class][B_BYTES] filter banks (build_fir_umma_table)
     int spans;
-    int phases;                     // profiling aid (env B2A_FIR_PHASES): bit 0 conversion (LDS + split + tcgen05.st), bit 1 MMAs, bit 2 epilogue stores; 31 = the product
+    int phases;                     // profiling aid (env B2A_FIR_PHASES): bit 0 conversion (LDS + split + tcgen05.st), bit 2 epilogue stores; 31 = the product
     GenericParams edge;             // the clip's head and tail outputs (table-driven, one thread per output): warps 6-7
     i64 edge_total;                 // linear indices of `edge` (resample_generic_total), 0 = none
 };
@@ -162,7 +162,6 @@ struct FirTmemIssue {
     saddr_t pf0, pe0, df0, de0;
     unsigned b_lo0, b_hi, tmem;
     unsigned piece0, chunk_base, blk_base;
-    int phases;
 };
 
 template <int IN_RATE, int J>
@@ -187,10 +186,10 @@ __device__ __forceinline__ void fir_tmem_issue_item(const FirTmemIssue& c) {
     // the last ring chunk pairs with the mirror of chunk 0 stored right behind it
     const unsigned a_col = ((c.chunk_base + cidx) % G::A_CHUNKS) * 4u;
     const unsigned b_lo = c.b_lo0 + bidx * (unsigned)(kFuBTile >> 4);
-    if (c.phases & 2) {
-        umma_ts_warp(d_tmem, c.tmem + G::COL_HV + a_col, b_lo, c.b_hi, kFuIdesc, first ? 0u : 1u);
-        umma_ts_warp(d_tmem, c.tmem + G::COL_LO + a_col, b_lo, c.b_hi, kFuIdesc, 1u);
-    }
+    // (no profiling knob around these two: the issuer is the kernel's critical path — one extra runtime branch per k-step
+    // cost 36 us, profiles/r01_probes.md)
+    umma_ts_warp(d_tmem, c.tmem + G::COL_HV + a_col, b_lo, c.b_hi, kFuIdesc, first ? 0u : 1u);
+    umma_ts_warp(d_tmem, c.tmem + G::COL_LO + a_col, b_lo, c.b_hi, kFuIdesc, 1u);
     if constexpr (last) umma_commit_warp(c.df0 + ds * kFmBarBytes);
     if constexpr (frees > 0) {
         constexpr unsigned freed0 = [] { unsigned f = 0; for (int k = 0; k < J; k++) f += (FirUmmaSchedOf<IN_RATE>::value.w[k] >> 24) & 15u; return f; }();
@@ -287,7 +286,7 @@ __global__ void __launch_bounds__(kFtThreads, 1) fir_tmem_kernel(const __grid_co
         FirTmemIssue c;
         c.pf0 = PF(0); c.pe0 = PE(0); c.df0 = DF(0); c.de0 = DE(0);
         c.b_lo0 = desc_start(smem_addr(btab)) | ((unsigned)(kFuBLbo >> 4) << 16); c.b_hi = (unsigned)(kFuBSbo >> 4) | (1u << 14);
-        c.tmem = tmem; c.phases = a.phases;
+        c.tmem = tmem;
         c.piece0 = 0; c.blk_base = 0;
 #pragma unroll 1
         for (int it = 0; it < n_tiles; it++, c.piece0 += G::PIECES, c.blk_base += kFmBlocks) {

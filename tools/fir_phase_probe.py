@@ -9,4 +9,4 @@ a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True
 a.record()
 for _ in range(30): ops.resample(x, 44100, want_energy=True)
 b.record(); torch.cuda.synchronize()
-print("B2A_FIR_PHASES=%s  resample %.1f us" % (os.environ.get("B2A_FIR_PHASES", "7"), a.elapsed_time(b) / 30 * 1e3))
+print("B2A_FIR_IMPL=%s B2A_FIR_PHASES=%s  resample %.1f us" % (os.environ.get("B2A_FIR_IMPL", "tmem"), os.environ.get("B2A_FIR_PHASES", "all"), a.elapsed_time(b) / 30 * 1e3))
