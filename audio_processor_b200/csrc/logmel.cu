@@ -571,30 +571,49 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
 
 // K5: out = max(out, ((gmax - 8) + 4) / 4) in place; tiles whose minimum already clears the floor are skipped.
 // One warp per 32-frame tile (lane = frame): the skip test is a single broadcast load per warp.
-__global__ void __launch_bounds__(256) mel_floor_kernel(LogMelParams p) {
+template <int NM>
+__global__ void __launch_bounds__(256, 3) mel_floor_kernel(LogMelParams p, int chunk) {
     i64 n_act = p.n;
     if (p.d_n) { n_act = *p.d_n; if (n_act > p.n) n_act = p.n; if (n_act < 0) n_act = 0; }
     const i64 T = (n_act + p.padding) / kHop;
     const i64 tiles = (T + LM_FRAMES - 1) / LM_FRAMES;
-    const int n_mels = p.n_mels;
+    const i64 total = tiles * p.batch;
     const int lane = threadIdx.x & 31;
-    const i64 warps = (i64)gridDim.x * (blockDim.x >> 5);
-    for (i64 work = (i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); work < tiles * p.batch; work += warps) {
-        const int b = (int)(work / tiles);
-        const i64 tile = work - (i64)b * tiles;
-        const float gmax = key_to_float(p.gmax_key[p.per_clip ? b : 0]);
-        const float floor_v = ((gmax - 8.0f) + 4.0f) * 0.25f;
-        if (p.tile_min[(size_t)b * (size_t)p.tiles_cap + (size_t)tile] >= floor_v) continue;
-        const i64 t = tile * LM_FRAMES + lane;
-        if (t >= T) continue;
-        float* q = p.out + (size_t)b * (size_t)n_mels * (size_t)T + t;
-        for (int m0 = 0; m0 < n_mels; m0 += 8, q += 8 * T) {       // n_mels is 80 or 128: whole groups of 8 loads in flight
-            float v[8];
+    // A warp checks `chunk` (1..32) consecutive tiles with one load per lane, then walks only the tiles below the floor,
+    // 16 rows in flight per round.  The host picks chunk = 1 for a few thousand tiles (one clip: the
+    // kernel is three dependent memory latencies long) and 32 for hundreds of thousands (chunk batches: the tile_min latency
+    // and the work -> (clip, tile) division are paid once per 32 tiles).
+    constexpr int R = 16;                      // 16 values + 16 addresses: 80 registers per thread, 3 CTAs per SM
+    const i64 stride = (i64)gridDim.x * (blockDim.x >> 5) * chunk;
+    for (i64 w0 = ((i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * chunk; w0 < total; w0 += stride) {
+        const i64 work = w0 + lane;
+        int b = 0, tile = 0;
+        float floor_l = 0.0f;
+        bool need = false;
+        if (lane < chunk && work < total) {
+            b = (int)(work / tiles);
+            tile = (int)(work - (i64)b * tiles);
+            floor_l = ((key_to_float(p.gmax_key[p.per_clip ? b : 0]) - 8.0f) + 4.0f) * 0.25f;
+            need = p.tile_min[(size_t)b * (size_t)p.tiles_cap + (size_t)tile] < floor_l;
+        }
+        unsigned m = __ballot_sync(0xFFFFFFFFu, need);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const float floor_v = __shfl_sync(0xFFFFFFFFu, floor_l, src);
+            const int bb = __shfl_sync(0xFFFFFFFFu, b, src);
+            const i64 t = (i64)__shfl_sync(0xFFFFFFFFu, tile, src) * LM_FRAMES + lane;
+            if (t >= T) continue;
+            float* q = p.out + (size_t)bb * (size_t)NM * (size_t)T + t;
+#pragma unroll 1
+            for (int m0 = 0; m0 < NM; m0 += R, q += (size_t)R * (size_t)T) {
+                float v[R];
 #pragma unroll
-            for (int e = 0; e < 8; e++) v[e] = q[(size_t)e * (size_t)T];
+                for (int e = 0; e < R; e++) v[e] = q[(size_t)e * (size_t)T];
 #pragma unroll
-            for (int e = 0; e < 8; e++)
-                if (v[e] < floor_v) q[(size_t)e * (size_t)T] = floor_v;
+                for (int e = 0; e < R; e++)
+                    if (v[e] < floor_v) q[(size_t)e * (size_t)T] = floor_v;
+            }
         }
     }
 }
@@ -663,9 +682,17 @@ int logmel_launch(const void* d_audio, int fmt, i64 batch, i64 n, i64 row_stride
     i64 grid = work < resident ? work : resident;
     B2A_LAUNCH(k4, (unsigned)grid, LM_THREADS, smem, stream, p);
     B2A_CHECK_LAUNCH("stft_mel_kernel");
-    i64 grid5 = (work + 7) / 8 < 148 * 8 ? (work + 7) / 8 : 148 * 8;     // 8 warps per block, one tile per warp
-    auto k5 = mel_floor_kernel;
-    B2A_LAUNCH(k5, (unsigned)grid5, 256, 0, stream, p);
+    i64 chunk5 = work / (148 * 8 * 8);                                     // tiles per warp and round: fill the machine first
+    chunk5 = chunk5 < 1 ? 1 : chunk5 > 32 ? 32 : chunk5;
+    const i64 warps5 = (work + chunk5 - 1) / chunk5;
+    const i64 grid5 = (warps5 + 7) / 8 < 148 * 8 ? (warps5 + 7) / 8 : 148 * 8;
+    if (n_mels == 80) {
+        auto k5 = mel_floor_kernel<80>;
+        B2A_LAUNCH(k5, (unsigned)grid5, 256, 0, stream, p, (int)chunk5);
+    } else {
+        auto k5 = mel_floor_kernel<128>;
+        B2A_LAUNCH(k5, (unsigned)grid5, 256, 0, stream, p, (int)chunk5);
+    }
     B2A_CHECK_LAUNCH("mel_floor_kernel");
     return B2A_OK;
 }
