@@ -5,6 +5,7 @@ import ctypes as C
 
 FMT_S16 = 0
 FMT_F32 = 1
+FMT_F16 = 2   # b2a_mel_windows output only
 NORM_WHISPER = 0
 NORM_PER_CLIP = 1
 
@@ -50,6 +51,7 @@ SIGNATURES = {
     "b2a_log_mel_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int64]),
     "b2a_log_mel": (C.c_int, [P, C.c_int, C.c_int64, C.c_int64, C.c_int64, P, C.c_int64, C.c_int, C.c_int, P, P, P,
                               C.c_size_t, P]),
+    "b2a_mel_windows": (C.c_int, [P, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, P, P]),
     "b2a_mel_filters": (C.c_int, [C.c_int, P, C.c_size_t]),
     "b2a_pipeline_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int64, C.c_int32]),
     "b2a_pipeline": (C.c_int, [P, C.c_int, C.c_int, C.c_int, C.c_int64, C.POINTER(SilenceParams), C.c_int, C.c_int64,

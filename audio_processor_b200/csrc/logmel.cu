@@ -24,6 +24,7 @@
 //    max/min and the [n_mels][T] store follow; a warp stores 32 consecutive frames of one mel = one 128-byte line.
 //  * K5 applies Whisper's global floor in place and skips tiles whose minimum is already above it.
 #include "b2a_tables.cuh"
+#include "f16_bits.h"
 
 namespace b2a {
 
@@ -697,6 +698,67 @@ int logmel_launch(const void* d_audio, int fmt, i64 batch, i64 n, i64 row_stride
     return B2A_OK;
 }
 
+// ---- encoder windows: transcribe's mel[:, seek : seek + n_frames] -> pad_or_trim -> dtype cast, all windows in one launch ----
+__device__ __forceinline__ unsigned short f32_to_f16_rn(float v) {
+#ifndef B2A_EMU
+    unsigned short h;
+    asm("cvt.rn.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+    return h;
+#else
+    return b2a_f16::f32_to_f16(v);
+#endif
+}
+
+// one block per (window, mel) row; a thread writes two neighbouring frames per round (one 4-byte store for f16 when the row
+// starts on a 4-byte boundary, i.e. n_frames even).  Frames at or beyond `content` read as zero (pad_or_trim).
+template <bool HALF>
+__global__ void __launch_bounds__(256) mel_windows_kernel(const float* __restrict__ mel, int n_mels, i64 T, i64 content, i64 seek0,
+                                                          i64 stride, int n_frames, void* __restrict__ out) {
+    const i64 row = blockIdx.x;
+    const int w = (int)(row / n_mels), m = (int)(row - (i64)w * n_mels);
+    const i64 s = seek0 + (i64)w * stride;
+    const float* src = mel + (size_t)m * (size_t)T;
+    const bool paired = (n_frames & 1) == 0;
+    for (int f = 2 * threadIdx.x; f < n_frames; f += 2 * blockDim.x) {
+        const i64 t0 = s + f, t1 = t0 + 1;
+        const float v0 = (t0 >= 0 && t0 < content) ? src[t0] : 0.0f;
+        const float v1 = (f + 1 < n_frames && t1 >= 0 && t1 < content) ? src[t1] : 0.0f;
+        const size_t o = (size_t)row * (size_t)n_frames + (size_t)f;
+        if (HALF) {
+            unsigned short* q = (unsigned short*)out;
+            if (paired) *(unsigned*)(q + o) = (unsigned)f32_to_f16_rn(v0) | ((unsigned)f32_to_f16_rn(v1) << 16);
+            else { q[o] = f32_to_f16_rn(v0); if (f + 1 < n_frames) q[o + 1] = f32_to_f16_rn(v1); }
+        } else {
+            float* q = (float*)out;
+            if (paired) *(float2*)(q + o) = make_float2(v0, v1);
+            else { q[o] = v0; if (f + 1 < n_frames) q[o + 1] = v1; }
+        }
+    }
+}
+
+int mel_windows_launch(const float* d_mel, int n_mels, i64 T, i64 content, i64 seek0, i64 stride, int n_win, int n_frames,
+                       int out_fmt, void* d_out, cudaStream_t stream) {
+    if (!d_mel || !d_out) { set_error("mel_windows: null pointer"); return B2A_EINVAL; }
+    if (n_mels <= 0 || T < 0 || content < 0 || content > T || seek0 < 0 || stride < 0 || n_win < 0 || n_frames <= 0) {
+        set_error("mel_windows: bad shape (n_mels=%d T=%lld content=%lld seek0=%lld stride=%lld n_win=%d n_frames=%d)", n_mels,
+                  (long long)T, (long long)content, (long long)seek0, (long long)stride, n_win, n_frames);
+        return B2A_EINVAL;
+    }
+    if (out_fmt != B2A_FMT_F32 && out_fmt != B2A_FMT_F16) { set_error("mel_windows: output format must be F32 or F16"); return B2A_EUNSUPPORTED; }
+    const i64 rows = (i64)n_win * n_mels;
+    if (rows == 0) return B2A_OK;
+    if (rows > 0x7fffffffLL) { set_error("mel_windows: too many rows"); return B2A_EINVAL; }
+    if (out_fmt == B2A_FMT_F16) {
+        auto k = mel_windows_kernel<true>;
+        B2A_LAUNCH(k, (unsigned)rows, 256, 0, stream, d_mel, n_mels, T, content, seek0, stride, n_frames, d_out);
+    } else {
+        auto k = mel_windows_kernel<false>;
+        B2A_LAUNCH(k, (unsigned)rows, 256, 0, stream, d_mel, n_mels, T, content, seek0, stride, n_frames, d_out);
+    }
+    B2A_CHECK_LAUNCH("mel_windows_kernel");
+    return B2A_OK;
+}
+
 }  // namespace b2a
 
 extern "C" {
@@ -711,6 +773,12 @@ int b2a_log_mel(const void* d_audio, int fmt, int64_t batch, int64_t n, int64_t 
                 size_t ws_bytes, b2a_stream_t stream) {
     return b2a::logmel_launch(d_audio, fmt, batch, n, row_stride, (const b2a::i64*)d_n, padding, n_mels, norm_mode,
                               d_out, (b2a::i64*)d_frames_out, d_ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int b2a_mel_windows(const float* d_mel, int n_mels, int64_t T, int64_t content_frames, int64_t seek0, int64_t stride,
+                    int n_windows, int n_frames, int out_fmt, void* d_out, b2a_stream_t stream) {
+    return b2a::mel_windows_launch(d_mel, n_mels, T, content_frames, seek0, stride, n_windows, n_frames, out_fmt, d_out,
+                                   (cudaStream_t)stream);
 }
 
 }  // extern "C"

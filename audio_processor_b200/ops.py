@@ -165,11 +165,11 @@ def detect(pcm16, sample_rate: int = SAMPLE_RATE, min_silence_len: int = 1000, s
         if energy is None:
             energy = energy_ms(x, sample_rate)
         dev = x.device
-        sil = torch.zeros((cap, 2), dtype=torch.int32, device=dev)
-        ns = torch.zeros((cap, 2), dtype=torch.int32, device=dev)
-        kp = torch.zeros((cap, 2), dtype=torch.int32, device=dev)
-        koff = torch.zeros(cap + 2, dtype=torch.int64, device=dev)
-        info = torch.zeros(_abi.INFO_LEN, dtype=torch.int64, device=dev)
+        # one zeroed block carved into the five tables (one memset launch instead of five: the call is launch bound)
+        blk = torch.zeros(3 * cap + (cap + 2) + _abi.INFO_LEN, dtype=torch.int64, device=dev)
+        sil, ns, kp = (blk[i * cap:(i + 1) * cap].view(torch.int32).view(cap, 2) for i in range(3))
+        koff = blk[3 * cap:4 * cap + 2]
+        info = blk[4 * cap + 2:]
         wsb = int(lib().b2a_silence_workspace_bytes(n, sample_rate))
         ws = torch.empty(wsb + 256, dtype=torch.uint8, device=dev)
         if energy.numel() == 0:
@@ -210,6 +210,33 @@ def log_mel(audio, n_mels: int = 80, padding: int = 0, *, per_clip_max: bool = F
                                 _abi.NORM_PER_CLIP if per_clip_max else _abi.NORM_WHISPER, _ptr(out), None, _ptr(ws), wsb,
                                 _stream(torch)))
     return out[0] if x.dim() == 1 else out
+
+
+def mel_windows(mel, n_frames: int = 3000, *, content_frames: Optional[int] = None, seek0: int = 0, stride: Optional[int] = None,
+                n_windows: Optional[int] = None, dtype=None):
+    """All encoder windows of a [n_mels, T] float32 mel in one launch: window w = ``mel[:, s : s + n_frames]`` with
+    s = seek0 + w * stride, frames at or beyond ``content_frames`` zero (whisper's pad_or_trim), cast to ``dtype``
+    (torch.float32 or torch.float16).  Defaults follow ``whisper.transcribe``: the mel carries 3000 frames of padding
+    (content_frames = T - 3000), windows advance by n_frames and cover the content.  Returns [n_windows, n_mels, n_frames]."""
+    torch = require_cuda()
+    if not (mel.is_cuda and mel.dtype == torch.float32 and mel.dim() == 2):
+        raise ValueError("mel must be a 2-D float32 CUDA tensor [n_mels, T]")
+    mel = mel.contiguous()
+    n_mels, T = int(mel.shape[0]), int(mel.shape[1])
+    content = max(T - 3000, 0) if content_frames is None else int(content_frames)
+    stride = int(n_frames) if stride is None else int(stride)
+    if n_windows is None:
+        if stride <= 0:
+            raise ValueError("stride must be positive when n_windows is not given")
+        n_windows = max((content - int(seek0) + stride - 1) // stride, 0)
+    dtype = torch.float32 if dtype is None else dtype
+    if dtype not in (torch.float32, torch.float16):
+        raise ValueError("dtype must be torch.float32 or torch.float16")
+    with torch.cuda.device(mel.device):
+        out = torch.empty((int(n_windows), n_mels, int(n_frames)), dtype=dtype, device=mel.device)
+        check(lib().b2a_mel_windows(_ptr(mel), n_mels, T, content, int(seek0), stride, int(n_windows), int(n_frames),
+                                    _abi.FMT_F16 if dtype == torch.float16 else _abi.FMT_F32, _ptr(out), _stream(torch)))
+    return out
 
 
 class PipelinePlan:

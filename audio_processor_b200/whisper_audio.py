@@ -106,6 +106,13 @@ def mel_segments(mel, n_frames: int = N_FRAMES, dtype=None):
         seek += size
 
 
+def mel_windows(mel, n_frames: int = N_FRAMES, dtype=None):
+    """Every window ``mel_segments`` would yield, as one [n_windows, n_mels, n_frames] tensor produced by a single kernel
+    (slice + zero pad + cast fused; ``dtype`` torch.float16 for an fp16 encoder) — the batched form of transcribe's loop
+    for callers that run the encoder over all 30-second windows at once."""
+    return ops.mel_windows(mel, n_frames, dtype=dtype)
+
+
 def patch_whisper() -> None:
     """Rebind openai-whisper's front-end to this module (transcribe imports the names directly)."""
     import whisper  # type: ignore

@@ -34,6 +34,7 @@ typedef struct CUstream_st* b2a_stream_t; /* == cudaStream_t */
 
 #define B2A_FMT_S16 0 /* interleaved signed 16-bit PCM */
 #define B2A_FMT_F32 1 /* interleaved float32 PCM, nominal range +-1.0 */
+#define B2A_FMT_F16 2 /* OUTPUT of b2a_mel_windows only: IEEE binary16 */
 
 #define B2A_OK 0
 #define B2A_EINVAL (-1)       /* bad argument */
@@ -153,6 +154,16 @@ size_t b2a_log_mel_workspace_bytes(int64_t batch, int64_t n, int64_t padding);
 int b2a_log_mel(const void* d_audio, int fmt, int64_t batch, int64_t n, int64_t row_stride,
                 const int64_t* d_n, int64_t padding, int n_mels, int norm_mode, float* d_out,
                 int64_t* d_frames_out, void* d_ws, size_t ws_bytes, b2a_stream_t stream);
+
+/* The encoder windows whisper.transcribe cuts from the mel (openai-whisper whisper/transcribe.py:
+ * `mel_segment = mel[:, seek : seek + segment_size]`, `pad_or_trim(mel_segment, N_FRAMES).to(device).to(dtype)`;
+ * reached from /root/reference/app/services/audio_processor.py:1076-1080), for every window of a uniform grid at once:
+ * window w starts at frame seek0 + w * stride; frames at or beyond content_frames (transcribe: T - 3000, the mel was
+ * computed with padding = 480000) read as zero.
+ * d_mel: float32 [n_mels][T] (b2a_log_mel / b2a_pipeline output). d_out: [n_windows][n_mels][n_frames] of out_fmt
+ * (B2A_FMT_F32, or B2A_FMT_F16 rounded to nearest even like torch's .half()). */
+int b2a_mel_windows(const float* d_mel, int n_mels, int64_t T, int64_t content_frames, int64_t seek0, int64_t stride,
+                    int n_windows, int n_frames, int out_fmt, void* d_out, b2a_stream_t stream);
 
 /* the float32 [n_mels][201] slaney filterbank the kernel uses (HOST copy, for audits) */
 int b2a_mel_filters(int n_mels, float* h_filters, size_t capacity_floats);

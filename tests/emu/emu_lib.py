@@ -127,6 +127,25 @@ def log_mel(audio, n_mels=80, padding=0, norm_mode=0):
     return r[0] if a.ndim == 1 else r
 
 
+def mel_windows(mel, n_frames=3000, content=None, seek0=0, stride=None, n_windows=None, half=False):
+    L = lib()
+    m = np.ascontiguousarray(mel, dtype=np.float32)
+    n_mels, T = m.shape
+    content = max(T - 3000, 0) if content is None else content
+    stride = n_frames if stride is None else stride
+    if n_windows is None:
+        n_windows = max((content - seek0 + stride - 1) // stride, 0)
+    src = _aligned(m.size + 64, np.float32)
+    src[:m.size] = m.reshape(-1)
+    dt = np.float16 if half else np.float32
+    out = _aligned(n_windows * n_mels * n_frames + 64, dt)
+    out[:] = 7
+    _check(L.b2a_mel_windows(_p(src), n_mels, T, content, seek0, stride, n_windows, n_frames,
+                             _abi.FMT_F16 if half else _abi.FMT_F32, _p(out), None))
+    assert np.all(out[n_windows * n_mels * n_frames:] == 7)            # nothing written past the last window
+    return out[:n_windows * n_mels * n_frames].reshape(n_windows, n_mels, n_frames).copy()
+
+
 def pipeline(pcm, in_rate, n_mels=80, padding=0, trim=True, min_silence_len=1000, silence_thresh=-40.0,
              keep_silence=200, seek_step=1, cap=4096):
     L = lib()

@@ -116,6 +116,36 @@ def test_emu_logmel_cases(emu):
     assert np.abs(emu.log_mel(s, 80) - wl.log_mel_spectrogram(s.astype(np.float32) / 32768.0, 80).numpy()).max() <= 1e-4
 
 
+def _windows_reference(mel, n_frames, content, seek0, stride, n_windows, dtype):
+    """transcribe's loop: mel[:, seek:seek + n_frames] limited to the content frames, pad_or_trim with zeros, cast"""
+    out = np.zeros((n_windows, mel.shape[0], n_frames), dtype)
+    for w in range(n_windows):
+        s = seek0 + w * stride
+        e = min(s + n_frames, content)
+        if e > s:
+            out[w, :, :e - s] = mel[:, s:e].astype(dtype)
+    return out
+
+
+def test_emu_mel_windows(emu):
+    rng = np.random.default_rng(4)
+    mel = (rng.standard_normal((80, 7321 + 3000)) * 0.7).astype(np.float32)
+    mel[3, 10] = 65519.0; mel[4, 11] = 6.0e-8; mel[5, 12] = 2049.0 / 2048.0      # f16 rounding edges: max, subnormal, tie
+    w = emu.mel_windows(mel)                                                   # transcribe defaults: 3 windows, last one padded
+    assert w.shape == (3, 80, 3000) and np.array_equal(w, _windows_reference(mel, 3000, 7321, 0, 3000, 3, np.float32))
+    h = emu.mel_windows(mel, half=True)
+    assert h.dtype == np.float16 and np.array_equal(h.view(np.uint16), _windows_reference(mel, 3000, 7321, 0, 3000, 3, np.float16).view(np.uint16))
+    # odd window length (unpaired stores), overlapping stride, a start offset, windows entirely past the content
+    for half in (False, True):
+        dt = np.float16 if half else np.float32
+        got = emu.mel_windows(mel[:5], n_frames=301, content=1000, seek0=7, stride=150, n_windows=9, half=half)
+        assert np.array_equal(got.view(np.uint16 if half else np.uint32),
+                              _windows_reference(mel[:5], 301, 1000, 7, 150, 9, dt).view(np.uint16 if half else np.uint32))
+    assert emu.mel_windows(mel[:2, :3000]).shape == (0, 2, 3000)               # no content frames: no windows
+    with pytest.raises(RuntimeError):
+        emu.mel_windows(mel, content=mel.shape[1] + 1)
+
+
 def test_emu_pipeline(emu):
     from audio_processor_b200 import synth
     x = synth.synth_clip(3, 44100, 2, 7.0, 0.35).numpy()

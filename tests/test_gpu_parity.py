@@ -249,6 +249,31 @@ def test_logmel_whisper_api(ops, T, tmp_path):
     assert np.abs(wa.mel_filters(None, 80).numpy() - wl.mel_filters(80)).max() <= 1e-9
 
 
+def test_mel_windows_match_transcribe_loop(ops, T):
+    """b2a_mel_windows == whisper.transcribe's slice + pad_or_trim + cast, window by window (bit-exact, f32 and f16)"""
+    from audio_processor_b200 import whisper_audio as wa
+    g = T.Generator(device="cuda").manual_seed(5)
+    audio = (T.randn(16000 * 73, device="cuda", generator=g) * 0.1).clamp(-1, 1)
+    mel = wa.log_mel_spectrogram(audio, 80, padding=wa.N_SAMPLES)
+    for dtype in (T.float32, T.float16):
+        ref = list(wa.mel_segments(mel, dtype=dtype))
+        got = wa.mel_windows(mel, dtype=dtype)
+        assert got.shape == (len(ref), 80, 3000) and got.dtype == dtype
+        for w, (_, seg) in enumerate(ref):
+            assert T.equal(got[w], seg)
+    # overlapping grid with an odd window length and windows past the content
+    got = ops.mel_windows(mel, 301, content_frames=1000, seek0=7, stride=150, n_windows=9, dtype=T.float16)
+    for w in range(9):
+        s = 7 + 150 * w
+        e = min(s + 301, 1000)
+        ref = T.zeros((80, 301), dtype=T.float16, device="cuda")
+        if e > s:
+            ref[:, :e - s] = mel[:, s:e].half()
+        assert T.equal(got[w], ref)
+    with pytest.raises(RuntimeError):
+        ops.mel_windows(mel, content_frames=mel.shape[1] + 1)
+
+
 def test_logmel_batch_4096_property(ops, T):
     """cfg3 shape [4096, 480000] f32 -> [4096, 128, 3000]; spot-check rows against the oracle and the floor invariant"""
     from audio_processor_b200 import synth

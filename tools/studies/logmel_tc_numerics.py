@@ -43,8 +43,24 @@ def planes_basis(B, nplanes):
     return out
 
 
+TRUNCATE = False        # True: emulate the tcgen05 accumulator the probe saw (tools/probes/umma_accum_probe.cu)
+
+
+def trunc32(x64):
+    """float64 -> float32 rounding toward zero."""
+    f = x64.astype(np.float32)
+    over = np.abs(f.astype(np.float64)) > np.abs(x64)
+    return np.where(over, np.nextafter(f, np.float32(0)), f).astype(np.float32)
+
+
 def mm32(a, b):
-    return a.astype(np.float32) @ b.astype(np.float32)          # fp32 accumulate (blocked order; a proxy for the MMA)
+    if not TRUNCATE:
+        return a.astype(np.float32) @ b.astype(np.float32)      # fp32 accumulate (blocked order; a proxy for the MMA)
+    # K in steps of 16: the 16 products of a step are summed exactly, the running fp32 accumulator truncates toward zero
+    acc = np.zeros((a.shape[0], b.shape[1]), np.float32)
+    for k0 in range(0, a.shape[1], 16):
+        acc = trunc32(acc.astype(np.float64) + a[:, k0:k0 + 16].astype(np.float64) @ b[k0:k0 + 16].astype(np.float64))
+    return acc
 
 
 def run(pcm, n_mels, shift, nb, drop_lolo):
@@ -147,3 +163,7 @@ if __name__ == "__main__":
         for shift, nb in ((7, 2), (6, 2), (6, 3)):
             print(f"  radix-2 unwindowed, x split 2^{shift}, basis planes {nb} ({2 * nb} passes, 4 x [K<=101, N<=101]): "
                   f"{np.abs(run_radix2(p, 80, shift, nb) - ref).max():.2e}")
+        TRUNCATE = True
+        print(f"  radix-2 unwindowed, x split 2^7, 4 passes, accumulator truncating toward zero every 16 products: "
+              f"{np.abs(run_radix2(p, 80, 7, 2) - ref).max():.2e}")
+        TRUNCATE = False
