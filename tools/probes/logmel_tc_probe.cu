@@ -82,6 +82,13 @@ __device__ __forceinline__ unsigned pack_f16x2(float lo, float hi) {
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
     return d;
 }
+// packed f16 arithmetic on raw bits
+__device__ __forceinline__ unsigned hadd2(unsigned a, unsigned b) { unsigned d; asm("add.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ unsigned hsub2(unsigned a, unsigned b) { unsigned d; asm("sub.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ unsigned hfma2(unsigned a, unsigned b, unsigned c) { unsigned d; asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+// a pair of s16 samples x = 128 xh + xl -> (xh, xh') and (xl / 128, xl' / 128) as f16x2, exact: 0x6400 | n is the f16 1024 + n
+__device__ __forceinline__ unsigned split_hi(unsigned w) { return hsub2((((w ^ 0x80008000u) >> 7) & 0x01ff01ffu) | 0x64006400u, 0x65006500u); }
+__device__ __forceinline__ unsigned split_lo(unsigned w) { return hfma2((w & 0x007f007fu) | 0x64006400u, 0x20002000u, 0xC800C800u); }
 template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ int s16_lo(unsigned w) { return (int)(short)(w & 0xffffu); }
@@ -226,31 +233,29 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const Args a) {
             const unsigned fw2[8] = {cur.f2a.x, cur.f2a.y, cur.f2a.z, cur.f2a.w, cur.f2b.x, cur.f2b.y, cur.f2b.z, cur.f2b.w};
             const unsigned rw1[8] = {cur.r1a.x, cur.r1a.y, cur.r1a.z, cur.r1a.w, cur.r1b.x, cur.r1b.y, cur.r1b.z, cur.r1b.w};
             const unsigned rw2[8] = {cur.r2a.x, cur.r2a.y, cur.r2a.z, cur.r2a.w, cur.r2b.x, cur.r2b.y, cur.r2b.z, cur.r2b.w};
+            // The planes are linear in the samples: split every sample once (x = 128 xh + xl), fold in packed f16.
+            // sum = (x[n] +- x[n+200]) + (x[200-n] +- x[400-n]) is ae (even warp) or do (odd warp), diff is ao or de.
+            unsigned ws_h[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ws_l[8] = {0, 0, 0, 0, 0, 0, 0, 0}, wd_h[8] = {0, 0, 0, 0, 0, 0, 0, 0}, wd_l[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (a.phases & 1) {
+                const unsigned sgn = odd ? 0xBC00BC00u : 0x3C003C00u;        // (-1, -1) or (1, 1)
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    // reversed pair c = (block[16 - 2c], block[15 - 2c]); block[16] is the extra scalar
+                    const unsigned q1 = __byte_perm(c == 0 ? (unsigned)cur.r1x : rw1[8 - (c == 0 ? 1 : c)], rw1[7 - c], 0x7610);
+                    const unsigned q2 = __byte_perm(c == 0 ? (unsigned)cur.r2x : rw2[8 - (c == 0 ? 1 : c)], rw2[7 - c], 0x7610);
+                    const unsigned uh = hfma2(split_hi(fw2[c]), sgn, split_hi(fw1[c])), ul = hfma2(split_lo(fw2[c]), sgn, split_lo(fw1[c]));
+                    const unsigned vh = hfma2(split_hi(q2), sgn, split_hi(q1)), vl = hfma2(split_lo(q2), sgn, split_lo(q1));
+                    ws_h[c] = hadd2(uh, vh); ws_l[c] = hadd2(ul, vl);
+                    wd_h[c] = hsub2(uh, vh); wd_l[c] = hsub2(ul, vl);
+                }
+            }
 #pragma unroll
             for (int e = 0; e < 2; e++) {
                 const int p = 2 * odd + e;
-                unsigned wh[8] = {0, 0, 0, 0, 0, 0, 0, 0}, wl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                if (a.phases & 1)
+                const bool use_sum = (e == 0) == (odd == 0);               // p0 = ae (sum), p1 = ao (diff), p2 = de (diff), p3 = do (sum)
+                unsigned wh[8], wl[8];
 #pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    float h2[2], l2[2];
-#pragma unroll
-                    for (int z = 0; z < 2; z++) {
-                        const int i = 2 * c + z;
-                        const int a1 = (i & 1) ? s16_hi(fw1[i >> 1]) : s16_lo(fw1[i >> 1]);
-                        const int a2 = (i & 1) ? s16_hi(fw2[i >> 1]) : s16_lo(fw2[i >> 1]);
-                        const int j = 16 - i;          // reversed element i = block[16 - i] for i >= 1, the extra scalar for i = 0
-                        const int b1 = i == 0 ? cur.r1x : ((j & 1) ? s16_hi(rw1[j >> 1]) : s16_lo(rw1[j >> 1]));
-                        const int b2 = i == 0 ? cur.r2x : ((j & 1) ? s16_hi(rw2[j >> 1]) : s16_lo(rw2[j >> 1]));
-                        const int u = odd ? a1 - a2 : a1 + a2, w = odd ? b1 - b2 : b1 + b2;
-                        const int v = (e == 0) == (odd == 0) ? u + w : u - w;      // ae = A + B, ao = A - B | de = Dn - Dr, do = Dn + Dr
-                        const int h = (v + 64) >> 7;
-                        h2[z] = (float)h;
-                        l2[z] = (float)(v - (h << 7)) * 0.0078125f;
-                    }
-                    wh[c] = pack_f16x2(h2[0], h2[1]);
-                    wl[c] = pack_f16x2(l2[0], l2[1]);
-                }
+                for (int c = 0; c < 8; c++) { wh[c] = use_sum ? ws_h[c] : wd_h[c]; wl[c] = use_sum ? ws_l[c] : wd_l[c]; }
                 if (g > 0) { mbar_wait(BAR(4 + p), (g - 1) & 1); tc_fence_after(); }
                 const unsigned t = tbase + ((unsigned)(quad * 32) << 16) + kRingCol0 + p * 16;
                 tmem_st8(t, wh);
