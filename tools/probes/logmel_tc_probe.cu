@@ -139,7 +139,8 @@ struct Args {
     const unsigned char* bank;
     float* out;              // [80][n_frames] log10(mel power)
     float* dbg_power;        // optional [128][201] windowed power of tile 0
-    int phases;              // bit 0: converter loads + ALU, bit 1: MMAs, bit 2: epilogue math + stores (timing knobs; all = 7)
+    int phases;              // bit 0: converter loads + ALU, bit 1: MMAs, bit 2: epilogue math + stores (timing knobs; all = 7);
+                             // bit 3: the epilogue does only 3 of its 7 rounds (WRONG results: sizes a 12-warp epilogue)
 };
 
 __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const Args a) {
@@ -284,6 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const Args a) {
             auto round = [&](auto cc) {
                 constexpr int c = decltype(cc)::value;
                 float re_e[16], im_e[16], re_o[16], im_o[16];
+                if ((a.phases & 8) && c >= 2 && c < kKS - 1) return;       // timing only: this warp's share if three warps per quadrant split the bins
                 tmem_ld16(t0 + 0 * kNB + 16 * c, re_e);
                 tmem_ld16(t0 + 1 * kNB + 16 * c, im_e);
                 tmem_ld16(t0 + 2 * kNB + 16 * c, re_o);
