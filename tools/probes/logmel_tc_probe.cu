@@ -11,7 +11,7 @@
 //   4 x 112 accumulator columns; epilogue thread = frame: Hann as the 3-tap X[k]/2 - (X[k-1] + X[k+1])/4, power, two running
 //   mel sums (a bin feeds at most two neighbouring slaney filters), log10, coalesced stores along T.
 //
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -shared -Xcompiler -fPIC -o _bin/liblogmel_tc_probe.so logmel_tc_probe.cu
+// Build: nvcc -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -shared -Xcompiler -fPIC -o _bin/liblogmel_tc_probe.so logmel_tc_probe.cu
 #include <cuda_runtime.h>
 
 #include <cstdint>
