@@ -296,11 +296,7 @@ int b2a_mel_filters(int n_mels, float* h_filters, size_t capacity_floats) {
 }
 
 int64_t b2a_resample_out_len(int64_t n_in, int in_rate, int out_rate) {
-    if (n_in <= 0 || in_rate <= 0 || out_rate <= 0) return 0;
-    long long g = b2a::gcd_ll(in_rate, out_rate);
-    long long L = out_rate / g, M = in_rate / g;
-    if (L == 1 && M == 1) return n_in;
-    return (int64_t)(((__int128)n_in * L + M - 1) / M);   // ceil: every output whose centre tap is inside the input
+    return (int64_t)b2a_design::one_shot_out_len(n_in, in_rate, out_rate);   // exactly what one-shot swr_convert + flush returns
 }
 
 int64_t b2a_energy_len(int64_t n_out, int out_rate) {

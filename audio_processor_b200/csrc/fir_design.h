@@ -34,7 +34,7 @@ static inline void design_resampler(int in_rate, int out_rate, int* L_out, int* 
     int L = (int)(out_rate / g), M = (int)(in_rate / g);
     double factor = std::fmin((double)out_rate * kCutoff / (double)in_rate, 1.0);
     int taps = (int)std::ceil(kFilterSize / factor);
-    taps = (taps + 1) & ~1;
+    taps = (taps + 1) & ~1;                                   // == resampler_taps(in_rate, out_rate)
     int center = (taps - 1) / 2;
     float* h = (float*)malloc(sizeof(float) * (size_t)L * taps);
     std::vector<double> row(taps);
@@ -53,6 +53,41 @@ static inline void design_resampler(int in_rate, int out_rate, int* L_out, int* 
         for (int i = 0; i < taps; i++) h[(size_t)ph * taps + i] = (float)(row[i] / norm);
     }
     *L_out = L; *M_out = M; *taps_out = taps; *h_taps_out = h;
+}
+
+// taps per phase of the default design for a rate pair (ceil(32 / factor) rounded up to even)
+static inline int resampler_taps(int in_rate, int out_rate) {
+    double factor = std::fmin((double)out_rate * 0.97 / (double)in_rate, 1.0);
+    int taps = (int)std::ceil(32 / factor);
+    return (taps + 1) & ~1;
+}
+
+// Number of samples a one-shot swr_convert(all input) followed by a flush returns — what `ffmpeg -i IN -ar out_rate`
+// writes.  Restates libswresample's buffering (swresample.c resample(), resample.c invert_initial_buffer / swri_resample /
+// resample_flush): the stream opens with `center` reflected samples; the first call emits every output whose taps-long
+// window fits, m*M < (n_in - taps/2)*L; the flush appends R = (min(buffered, taps) + 1) / 2 mirrored samples, `buffered`
+// being what the first call left unconsumed, and emits what fits then: ceil((n_in - taps/2 + R) * L / M).  R is taps/2 or
+// one less, which is why ceil(n_in*L/M) overshoots by one on about a third of the lengths.  Inputs shorter than taps + 1
+// wait in the initial buffer until the flush (buffered = n_in).  oracle/resample_oracle.py:out_len is the same model,
+// checked against the real library on 25 030 cases.
+static inline long long one_shot_out_len(long long n_in, int in_rate, int out_rate) {
+    if (n_in <= 0 || in_rate <= 0 || out_rate <= 0) return 0;
+    const long long g = gcd_ll(in_rate, out_rate);
+    const long long L = out_rate / g, M = in_rate / g;
+    if (L == 1 && M == 1) return n_in;
+    const long long taps = resampler_taps(in_rate, out_rate), center = (taps - 1) / 2;
+    auto cdiv = [](__int128 a, long long b) -> long long { return (long long)(a >= 0 ? (a + b - 1) / b : -((-a) / b)); };
+    long long buffered;
+    if (n_in < taps + 1) buffered = n_in;
+    else {
+        long long n1 = cdiv((__int128)(n_in - taps / 2) * L, M);
+        if (n1 < 0) n1 = 0;
+        buffered = center + n_in - (long long)(((__int128)n1 * M) / L);
+    }
+    const long long refl = ((buffered < taps ? buffered : taps) + 1) / 2;
+    if (n_in < taps + 1 && n_in + refl < taps + 1) return 0;
+    const long long n = cdiv((__int128)(n_in - taps / 2 + refl) * L, M);
+    return n > 0 ? n : 0;
 }
 
 }  // namespace b2a_design

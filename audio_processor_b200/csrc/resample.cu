@@ -82,7 +82,7 @@ int resample_launch(const void* d_in, int fmt, int channels, int in_rate, i64 n_
 
     const ResampleDesign* des = get_resample_design(in_rate, out_rate);
     if (!des) return B2A_EINVAL;
-    if (n_in < des->taps) { set_error("resample: input shorter than the %d-tap filter is unsupported", des->taps); return B2A_EUNSUPPORTED; }
+    if (n_out == 0) return B2A_OK;     // too short to fill the filter: libswresample returns no samples either (b2a_resample_out_len)
 
     GenericParams p;
     p.in = d_in; p.fmt = fmt; p.channels = channels; p.n_in = n_in; p.n_out = n_out;
@@ -96,7 +96,7 @@ int resample_launch(const void* d_in, int fmt, int channels, int in_rate, i64 n_
     FirMmaPlan plan;
     plan.out_lo = plan.out_hi = 0;
     const bool aligned = ((((uintptr_t)d_in) | ((uintptr_t)d_out_s16) | ((uintptr_t)d_out_f32) | ((uintptr_t)d_energy)) & 15) == 0;
-    if (aligned && out_rate == 16000) {
+    if (aligned && out_rate == 16000 && n_in > des->taps) {    // shorter clips: every window needs the edge extension
         int rc = fir_fast_dispatch(in_rate, fmt, channels, d_in, n_in, d_out_s16, d_out_f32, d_energy, &plan, &p, stream);
         if (rc < 0) return rc;
     }

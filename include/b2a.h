@@ -74,9 +74,10 @@ int b2a_fir_schedule(int in_rate, uint32_t* out, int capacity_words);
  * reflect head / symmetric tail, lrintf + clip quantisation.
  * ------------------------------------------------------------------------------------------ */
 
-/* number of output samples for n_in input frames: ceil(n_in*L/M) with L/M = out_rate/in_rate reduced — every
- * output whose centre tap lies inside the input.  (libswresample emits this many or one fewer, depending on
- * how much input its streaming buffer still held at flush.) */
+/* number of output samples for n_in input frames: exactly what libswresample returns for a one-shot swr_convert of the
+ * whole input followed by a flush (= the sample count of the WAV `ffmpeg -i IN -ar out_rate` writes):
+ * ceil((n_in - taps/2 + R) * L / M), L/M = out_rate/in_rate reduced, R = the library's flush reflection (taps/2 or one
+ * less, from its buffering state; csrc/fir_design.h restates it).  0 for clips too short to fill the filter. */
 int64_t b2a_resample_out_len(int64_t n_in, int in_rate, int out_rate);
 
 /* filter geometry; returns taps per phase (<0 on error) and stores the phase count L */

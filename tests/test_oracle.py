@@ -18,8 +18,8 @@ def test_resample_oracle_vs_golden_tones(name):
     g = G["resample"][name]
     y = ro.convert(H.tone_pair(g["rate"], g["n_in"]), g["rate"])
     ref = A[f"{name}_out"]
-    assert g["n_out"] == len(ref) and 0 <= len(y) - len(ref) <= 1
-    d = np.abs(y[:len(ref)].astype(int) - ref.astype(int))
+    assert g["n_out"] == len(ref) == len(y)
+    d = np.abs(y.astype(int) - ref.astype(int))
     assert d.max() <= 1 and (d == 0).mean() >= 0.998
     assert ref[:16].tolist() == g["first16"] and ref[-8:].tolist() == g["last8"]
     assert int(ref.astype(np.int64).sum()) == g["sum"]
@@ -29,15 +29,15 @@ def test_resample_oracle_vs_golden_tones(name):
 def test_resample_oracle_vs_golden_noise(name, rate):
     y = ro.convert(A[f"{name}_in"], rate)
     ref = A[f"{name}_out"]
-    assert 0 <= len(y) - len(ref) <= 1
-    d = np.abs(y[:len(ref)].astype(int) - ref.astype(int))
+    assert len(y) == len(ref)
+    d = np.abs(y.astype(int) - ref.astype(int))
     assert d.max() <= 1 and (d == 0).mean() >= 0.995
 
 
 def test_resample_oracle_float_mono_golden():
     y = ro.convert(A["F441_in"], 44100)
-    assert 0 <= len(y) - len(A["F441_out"]) <= 1
-    d = np.abs(y[:len(A["F441_out"])].astype(int) - A["F441_out"].astype(int))
+    assert len(y) == len(A["F441_out"])
+    d = np.abs(y.astype(int) - A["F441_out"].astype(int))
     assert d.max() <= 1 and (d == 0).mean() >= 0.995
 
 
@@ -48,12 +48,44 @@ def test_resample_oracle_vs_live_library(rate):
     x = (rng.standard_normal((rate + 13, 2)) * 6000).clip(-32768, 32767).astype(np.int16)
     lib16 = swr_ref.convert(x, rate)
     o = ro.convert(x, rate)
-    assert len(o) == ro.out_len(len(x), rate, 16000) and 0 <= len(o) - len(lib16) <= 1   # flush-state dependent
-    d = np.abs(o[:len(lib16)].astype(int) - lib16.astype(int))
+    assert len(o) == ro.out_len(len(x), rate, 16000) == len(lib16)
+    d = np.abs(o.astype(int) - lib16.astype(int))
     assert d.max() <= 1 and (d == 0).mean() >= 0.995
     xm = x[:, 0].copy()
     libf = swr_ref.convert(xm, rate, out_fmt="flt")
     assert np.abs(libf - ro.resample_float(xm, rate)[:len(libf)]).max() < 2e-6     # filter design matches the library's taps
+
+
+@needs_swr
+@pytest.mark.parametrize("rate", [44100, 48000, 22050, 32000, 8000, 24000, 11025, 96000])
+def test_out_len_matches_library_sweep(rate):
+    """one-shot swr_convert + flush length for >= 1 000 consecutive input lengths per rate (round-1 VERDICT: the old
+    ceil(n*L/M) overshot by one on a third of them), plus clips around and below the filter length, mono and stereo,
+    s16 and f32"""
+    taps = ro.n_taps(rate, 16000)
+    lengths = list(range(1, 2 * taps + 40)) + list(range(5000, 6000)) + [rate * 60, rate * 60 + 1, rate * 3 + 7]
+    bad = []
+    for n in lengths:
+        ch, dt = (1 if n % 2 else 2), (np.int16 if n % 3 else np.float32)
+        x = np.zeros((n, ch) if ch > 1 else (n,), dtype=dt)
+        got = len(swr_ref.convert(x, rate))
+        if got != ro.out_len(n, rate, 16000):
+            bad.append((n, got, ro.out_len(n, rate, 16000)))
+    assert not bad, bad[:10]
+
+
+@needs_swr
+@pytest.mark.parametrize("rate", [44100, 48000, 22050, 8000])
+def test_short_clip_values_match_library(rate):
+    """clips shorter than the filter: the library still emits samples once n_in + reflection fills it; same extension rule"""
+    taps = ro.n_taps(rate, 16000)
+    rng = np.random.default_rng(rate)
+    for n in range(taps // 2, taps + 12):
+        x = (rng.standard_normal((n, 2)) * 8000).astype(np.int16)
+        a, b = swr_ref.convert(x, rate), ro.convert(x, rate)
+        assert len(a) == len(b), (n, len(a), len(b))
+        if len(a):
+            assert np.abs(a.astype(int) - b.astype(int)).max() <= 1
 
 
 @needs_swr
