@@ -22,7 +22,7 @@ LIB = os.path.join(HERE, "libb2a.so")
 
 SOURCES = [
     "b2a_host.cu", "logmel.cu", "silence.cu", "resample.cu", "pipeline.cu", "fir_dispatch.cu",
-    "fir_mma_44100.cu", "fir_mma_48000.cu", "fir_umma_44100.cu", "fir_umma_48000.cu", "fir_tmem_44100.cu", "fir_tmem_48000.cu",
+    "fir_mma_44100.cu", "fir_mma_48000.cu", "fir_tmem_44100.cu", "fir_tmem_48000.cu",
 ]
 
 NVCC_FLAGS = [

@@ -13,7 +13,7 @@
 #include "b2a_tables.cuh"
 #include "f16_bits.h"
 #include "fir_mma.cuh"
-#include "fir_umma.cuh"
+#include "fir_tc_common.cuh"
 #include "fir_design.h"
 #include "mel_design.h"
 
@@ -183,7 +183,7 @@ const uint2* get_fir_mma_table(int in_rate) {
 }
 
 
-// ---- filter bank of the tcgen05 FIR (fir_umma.cuh) as UMMA B operand tiles ---------------------------------------
+// ---- filter bank of the tcgen05 FIR (fir_tc_common.cuh, fir_tmem.cuh) as UMMA B operand tiles ---------------------------------------
 // [class c][block b][k-step s] -> one [N = 32][K = 16] f16 tile in the canonical no-swizzle K-major layout
 // (element (n, k) at (n / 8) * 256 + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2 bytes): rows 0-15 = T_hi, rows 16-31 =
 // T_lo of output J = 16 b + n % 16.  Plane column j of a class-c row is input frame S run - CENTER - shift(c) + j, so

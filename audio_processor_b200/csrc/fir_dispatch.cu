@@ -1,4 +1,5 @@
-// fir_dispatch.cu — picks the tensor-core FIR instantiation for a (rate, format, channels) triple.
+// fir_dispatch.cu — picks the tensor-core FIR instantiation for a (rate, format, channels) triple.  One kernel per
+// case, decided by the input alone: no environment switches, no alternative back ends.
 #include "fir_mma.cuh"
 #include "resample_generic.cuh"
 
@@ -6,32 +7,23 @@ namespace b2a {
 
 int fir_mma_run_44100(int channels, const void*, i64, int16_t*, u64*, FirMmaPlan*, cudaStream_t, i64 first_tile);
 int fir_mma_run_48000(int channels, const void*, i64, int16_t*, u64*, FirMmaPlan*, cudaStream_t, i64 first_tile);
-int fir_umma_run_44100(const void*, i64, int16_t*, u64*, FirMmaPlan*, cudaStream_t);
-int fir_umma_run_48000(const void*, i64, int16_t*, u64*, FirMmaPlan*, cudaStream_t);
 int fir_tmem_run_44100(const void*, i64, int16_t*, u64*, FirMmaPlan*, const GenericParams*, cudaStream_t);
 int fir_tmem_run_48000(const void*, i64, int16_t*, u64*, FirMmaPlan*, const GenericParams*, cudaStream_t);
 i64 fir_tmem_plan_44100(i64, FirMmaPlan*);
 i64 fir_tmem_plan_48000(i64, FirMmaPlan*);
 
-// returns 1 if the tensor-core kernel was launched (plan filled), 0 if this input has no fast path, <0 on error.
+// returns 1 if a tensor-core kernel was launched (plan filled), 0 if this input has no fast path, <0 on error.
 // s16 input at the two named rates only; the pre-quantisation float output and every other case use the
-// table-driven kernel in resample.cu.  Clips too short for a 128-run tile of the tcgen05 kernel fall back to the
-// 16-run tiles of the mma.sync kernel.
+// table-driven kernel in resample.cu.
+//   stereo, at least one 512-run span: fir_tmem.cuh (tcgen05, fed by 2-D TMA, operand planes in TMEM) takes the spans and,
+//           in its spare warps, the clip's head and tail outputs; the 16-run tiles behind the last span go to fir_mma.cuh;
+//   mono, or stereo clips shorter than a span (< 5.1 s): fir_mma.cuh (mma.sync, 16-run tiles fed by a bulk-TMA ring).
 int fir_fast_dispatch(int in_rate, int fmt, int channels, const void* d_in, i64 n_in, int16_t* d_out_s16, float* d_out_f32,
                       u64* d_energy, FirMmaPlan* plan, const GenericParams* edge, cudaStream_t stream) {
     plan->out_lo = plan->out_hi = 0;
     if (fmt != B2A_FMT_S16 || d_out_f32 || (channels != 1 && channels != 2)) return 0;
-    // Stereo input has three kernels:
-    //   fir_tmem.cuh  tcgen05, fed by 2-D TMA, operand planes in TMEM, 512-run spans             (the default)
-    //   fir_umma.cuh  tcgen05, register-staged loads, planes in shared memory    (B2A_FIR_IMPL=umma; profiles/r01_fir_umma.md)
-    //   fir_mma.cuh   mma.sync, 16-run tiles fed by a bulk-TMA ring              (B2A_FIR_IMPL=mma; also mono input)
-    // A tcgen05 kernel takes the whole spans and hands what is left behind the last span to the mma.sync kernel.
-    const char* impl = getenv("B2A_FIR_IMPL");
-    const bool legacy = impl && impl[0] == 'm';
-    const bool tmem = !(impl && impl[0] == 'u');
-    if (channels == 2 && !legacy && tmem && edge && (in_rate == 44100 || in_rate == 48000)) {
-        // default: spans by the TMA-fed tcgen05 kernel, the 16-run tiles behind the last span by the mma.sync kernel, and
-        // the head / the last partial tile by the tcgen05 kernel's spare warps => the whole clip is done, no edge kernel
+    if (in_rate != 44100 && in_rate != 48000) return 0;
+    if (channels == 2 && edge) {
         FirMmaPlan head, tail;
         tail.out_lo = tail.out_hi = 0;
         const i64 spans = in_rate == 44100 ? fir_tmem_plan_44100(n_in, &head) : fir_tmem_plan_48000(n_in, &head);
@@ -50,27 +42,8 @@ int fir_fast_dispatch(int in_rate, int fmt, int channels, const void* d_in, i64 
             return 1;
         }
     }
-    i64 first_tile = 1;
-    FirMmaPlan head;
-    head.out_lo = head.out_hi = 0;
-    if (channels == 2 && !legacy && !tmem) {
-        int rc = 0;
-        if (in_rate == 44100) rc = fir_umma_run_44100(d_in, n_in, d_out_s16, d_energy, &head, stream);
-        else if (in_rate == 48000) rc = fir_umma_run_48000(d_in, n_in, d_out_s16, d_energy, &head, stream);
-        if (rc < 0) return rc;
-        if (rc > 0) first_tile = head.out_hi / (kFmRT * kFmNout);          // span ends are multiples of 16 runs
-    }
-    int rc = 0;
-    if (in_rate == 44100) rc = fir_mma_run_44100(channels, d_in, n_in, d_out_s16, d_energy, plan, stream, first_tile);
-    else if (in_rate == 48000) rc = fir_mma_run_48000(channels, d_in, n_in, d_out_s16, d_energy, plan, stream, first_tile);
-    if (rc < 0) return rc;
-    if (head.out_hi > head.out_lo) {
-        // outputs [head.out_lo, head.out_hi) came from the tcgen05 kernel, [plan->out_lo, plan->out_hi) (if any) follow directly
-        plan->out_lo = head.out_lo;
-        if (rc == 0) plan->out_hi = head.out_hi;
-        return 1;
-    }
-    return rc;
+    return in_rate == 44100 ? fir_mma_run_44100(channels, d_in, n_in, d_out_s16, d_energy, plan, stream, 1)
+                            : fir_mma_run_48000(channels, d_in, n_in, d_out_s16, d_energy, plan, stream, 1);
 }
 
 }  // namespace b2a

@@ -413,13 +413,17 @@ static inline int fir_mma_launch(const void* d_in, i64 n_in, int16_t* d_out_s16,
     a.in = (const unsigned char*)d_in; a.out_s16 = d_out_s16; a.energy = d_energy; a.btab = tab;
     a.tile_lo = tile_lo; a.tile_hi = tile_hi;
     a.phases = 7;
-    if (const char* ph = getenv("B2A_FIR_PHASES")) a.phases = atoi(ph);      // profiling only
+#ifdef B2A_PROFILE
+    if (const char* ph = getenv("B2A_FIR_PHASES")) a.phases = atoi(ph);      // profiling builds only (-DB2A_PROFILE): masks kernel phases, WRONG output
+#endif
     const i64 tiles = tile_hi - tile_lo;
     unsigned grid = (unsigned)(tiles < 148 ? tiles : 148);                   // persistent: one CTA per SM
-    if (const char* gs = getenv("B2A_FIR_GRID")) {                           // test knob: few CTAs => many tiles per CTA
+#if defined(B2A_PROFILE) || defined(B2A_EMU)
+    if (const char* gs = getenv("B2A_FIR_GRID")) {                           // emulation / profiling builds only: few CTAs => many tiles per CTA
         const int gv = atoi(gs);
         if (gv > 0 && (unsigned)gv < grid) grid = (unsigned)gv;
     }
+#endif
     B2A_LAUNCH(k, grid, kFmThreads, G::SMEM_BYTES, stream, a);
     B2A_CHECK_LAUNCH("fir_mma_kernel");
     plan->out_lo = tile_lo * kFmRT * kFmNout;

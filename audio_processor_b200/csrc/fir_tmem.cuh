@@ -1,14 +1,14 @@
 // fir_tmem.cuh — the tcgen05 FIR fed by TMA, with the f16 operand planes in TENSOR MEMORY (sm_100a).
 //
-// Same mathematics, class tiles, filter banks and compile-time k-step schedule as fir_umma.cuh (read that header first);
-// what changes is where the data lives, because profiles/r01_fir_umma.md showed that register-staged global loads
-// cannot feed the kernel (L1 miss tracking caps the bytes in flight at ~14 KB per SM, ~2 TB/s):
+// Mathematics, class tiles, filter banks and the compile-time k-step schedule are in fir_tc_common.cuh (read that header
+// first).  The data path is TMA + TMEM because profiles/r01_fir_umma.md showed that register-staged global loads cannot
+// feed the kernel (L1 miss tracking caps the bytes in flight at ~14 KB per SM, ~2 TB/s):
 //
 //   global --2-D TMA (SWIZZLE_128B boxes of 128 rows x 32 frames)--> raw ring in shared memory (4 x 32 KB)
 //          --converter warps, thread = row: LDS.128 -> (hv, lo / 128) f16 pairs -> tcgen05.st--> plane ring in TMEM
 //          --tcgen05.mma, A operand from TMEM, B = filter bank in shared memory--> accumulators in TMEM --> epilogue
 //
-// The class tiles of fir_umma.cuh are what makes the TMA path possible: rows of a tile are 4 runs = 7056 bytes apart
+// The class tiles are what makes the TMA path possible: rows of a tile are 4 runs = 7056 bytes apart
 // (a legal tensor-map stride) and start on a 16-byte quad.  With the planes in TMEM the shared memory holds only the raw
 // ring and the 92 KB filter bank; there is no generic-proxy store the tensor core has to see (no proxy fence), and 128 KB
 // of input is in flight per SM without a single register.
@@ -19,7 +19,9 @@
 // (low half first); an operand may start on any 4-column boundary.
 //
 // Roles (512 threads), coupled only by mbarriers:
-//   warps 0-3   epilogue (as in fir_umma.cuh);
+//   warps 0-3   epilogue: warp q owns TMEM lanes 32q..32q+31 (thread = run): tcgen05.ld 32 columns, add the two halves,
+//               round half-to-even + saturate to s16 (swr audioconvert), two 16-byte stores, and the exact uint64 sum of
+//               squares of the millisecond for the silence detector;
 //   warp  4     MMA issuer (compile-time schedule, elected issue) + TMEM allocation;
 //   warp  5     TMA producer: lane 0 keeps the raw ring full (two boxes per 64-column piece);
 //   warps 6-7   the clip's edge outputs (reflect / symmetric extension at the head, the tail behind the last span),
@@ -30,7 +32,7 @@
 // Measured (profiles/r01_ncu_fir_tmem.txt, one-hour 44.1 kHz stereo clip): 147-153 us, DRAM 636 MB read + 127 MB written =
 // the algorithmic bytes, 5.1-5.3 TB/s = 78-81 % of the measured HBM copy peak (the mma.sync kernel: 236 us).
 #pragma once
-#include "fir_umma.cuh"
+#include "fir_tc_common.cuh"
 #include "resample_generic.cuh"
 
 #ifndef B2A_EMU
@@ -444,15 +446,19 @@ static inline int fir_tmem_launch(const void* d_in, i64 n_in, int16_t* d_out_s16
     a.in = (const unsigned char*)d_in; a.out_s16 = d_out_s16; a.energy = d_energy; a.btab = tab;
     a.spans = (int)spans;
     a.phases = 31;
-    if (const char* ph = getenv("B2A_FIR_PHASES")) a.phases = atoi(ph);          // profiling only
+#ifdef B2A_PROFILE
+    if (const char* ph = getenv("B2A_FIR_PHASES")) a.phases = atoi(ph);          // profiling builds only (-DB2A_PROFILE): masks kernel phases, WRONG output
+#endif
     a.edge_total = 0;
     if (edge) { a.edge = *edge; a.edge_total = resample_generic_total(*edge); }
     else memset(&a.edge, 0, sizeof(a.edge));
     i64 lanes = spans < 37 ? spans : 37;                         // persistent: 4 CTAs (one per class) per span lane, 148 SMs
-    if (const char* gs = getenv("B2A_FIR_GRID")) {               // test knob: few CTAs => many tiles per CTA
+#if defined(B2A_PROFILE) || defined(B2A_EMU)
+    if (const char* gs = getenv("B2A_FIR_GRID")) {               // emulation / profiling builds only: few CTAs => many tiles per CTA
         const int gv = (atoi(gs) + kFuClasses - 1) / kFuClasses;
         if (gv > 0 && gv < lanes) lanes = gv;
     }
+#endif
     B2A_LAUNCH(k, (unsigned)(lanes * kFuClasses), kFtThreads, G::SMEM_BYTES, stream, a);
     B2A_CHECK_LAUNCH("fir_tmem_kernel");
     return 1;

@@ -60,7 +60,7 @@ int b2a_version(void);
 const char* b2a_last_error(void);
 /* diagnostics: number of CUDA kernels this library has launched in this process so far */
 int64_t b2a_launch_count(void);
-/* diagnostics (host only): the tcgen05 FIR's k-step issue schedule for in_rate 44100 / 48000 (csrc/fir_umma.cuh).
+/* diagnostics (host only): the tcgen05 FIR's k-step issue schedule for in_rate 44100 / 48000 (csrc/fir_tc_common.cuh).
  * out[0] = items, out[1] = ring pieces per tile, out[2] = k-steps per block, out[3 + b] = first column chunk of block b
  * (b < 10), out[16 + j] = item j.  Returns the number of words written, or a negative error. */
 int b2a_fir_schedule(int in_rate, uint32_t* out, int capacity_words);

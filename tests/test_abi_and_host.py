@@ -203,7 +203,7 @@ def test_gather_segment_tables_world_size_2_gloo(tmp_path):
 @pytest.mark.parametrize("rate", [44100, 48000])
 def test_fir_issue_schedule_is_hazard_free(rate):
     """the tcgen05 FIR issues its k-steps in column order and releases a ring piece right after its last reader
-    (csrc/fir_umma.cuh, fir_umma_schedule).  The functional emulation cannot see a premature release (it executes an MMA
+    (csrc/fir_tc_common.cuh, fir_umma_schedule).  The functional emulation cannot see a premature release (it executes an MMA
     when it is issued), so the schedule itself is checked: every k-step once and in order per block, operands only in
     pieces that were awaited and not yet released, every piece awaited and released exactly once, and never more live
     pieces than the smallest plane ring holds."""

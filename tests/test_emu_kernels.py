@@ -179,13 +179,12 @@ def test_emu_fir_pipeline_many_tiles_per_cta(emu, rate, tile_frames, ch, monkeyp
     assert np.array_equal(en.astype(np.int64), H.energy_oracle(y))
 
 
-@pytest.mark.parametrize("impl", ["tmem", "umma"])
 @pytest.mark.parametrize("rate,grid", [(44100, "4"), (48000, "8")])
-def test_emu_fir_tcgen05_tiles(emu, rate, grid, impl, monkeypatch):
-    """index logic of the tcgen05 FIR (fir_umma.cuh) under the functional emulation of tcgen05.mma / TMEM: column ring
+def test_emu_fir_tcgen05_tiles(emu, rate, grid, monkeypatch):
+    """index logic of the tcgen05 FIR (fir_tmem.cuh) under the functional emulation of tcgen05.mma / TMEM: column ring
     with wrap and mirrored chunk, class tiles (every 4th run, shifted filter banks), accumulator ring, 3 spans over 4-8 persistent
-    CTAs, and the hand-over to the mma.sync kernel behind the last span"""
-    monkeypatch.setenv("B2A_FIR_IMPL", impl)
+    CTAs, and the hand-over to the mma.sync kernel behind the last span.  (B2A_FIR_GRID exists in the emulation and
+    -DB2A_PROFILE builds only; the release library reads no environment variable.)"""
     monkeypatch.setenv("B2A_FIR_GRID", grid)
     S = 441 if rate == 44100 else 480
     rng = np.random.default_rng(rate)
