@@ -60,10 +60,24 @@ def gen_mel(force: bool = False) -> None:
     subprocess.run([exe, out], check=True)
 
 
+def gen_mel_tc(force: bool = False) -> None:
+    """csrc/mel_tc_tables_gen.inc (the filterbank as the tensor-core epilogue unrolls it) from tools/gen_mel_tc_tables.cpp."""
+    out = os.path.join(CSRC, "mel_tc_tables_gen.inc")
+    src = os.path.join(ROOT, "tools", "gen_mel_tc_tables.cpp")
+    dep = max(os.path.getmtime(src), os.path.getmtime(os.path.join(CSRC, "mel_design.h")))
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= dep:
+        return
+    os.makedirs(OBJ, exist_ok=True)
+    exe = os.path.join(OBJ, "gen_mel_tc_tables")
+    subprocess.run(["g++", "-O2", "-o", exe, src], check=True)
+    subprocess.run([exe, out], check=True)
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
     gen_mel(force)
+    gen_mel_tc(force)
     dep_m = _deps_mtime()
     jobs = []
     for s in SOURCES:

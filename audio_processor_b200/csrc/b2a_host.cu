@@ -96,6 +96,58 @@ const LogMelTables* get_logmel_tables(int n_mels) {
     return d;
 }
 
+// ---- basis bank + window tables of the tensor-core log-mel (logmel_tc.cuh) ----------------------------------------------
+// Eight f16 planes (product p = even-cos, even-sin, odd-cos, odd-sin; hi = f16(c), lo = f16(c - hi)) in the canonical
+// no-swizzle K-major UMMA layout: element (k = n, row = j) of a plane at (n / 8) * kTcLbo + (j / 8) * 128 + (j % 8) * 16 +
+// (n % 8) * 2 bytes, 13 x 13 blocks of 8 x 8 stored (n, j <= 103; the MMAs' K = N = 112 read one block further, which aliases
+// the next chunk / plane: finite values against zero operands).  Rows n = 100 of the even-cos and odd-sin products carry
+// 1/2 because the fold counts x[100] and x[300] twice.  Behind the planes: 1 792 zero bytes, then the four window
+// tables w[n], w[n+200], w[200-n], w[400-n] (n = 0..111, zero for n > 100 and for the partners of n = 0) times 1/4:
+// the kernel's spectra live in the (s16 / 4) domain so that every folded value fits the f16 range.
+static std::map<int, const unsigned char*> g_logmel_tc;      // device -> blob
+
+const unsigned char* get_logmel_tc_blob() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { cuda_fail(e, "cudaGetDevice"); return nullptr; }
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_logmel_tc.find(dev);
+    if (it != g_logmel_tc.end()) return it->second;
+    const int kLbo = 13 * 128, kPlane = 13 * kLbo, kBank = 8 * kPlane + kLbo + 128, kBlob = kBank + 4 * 112 * 4;
+    std::vector<unsigned char> h((size_t)kBlob, 0);
+    const double kPi = 3.14159265358979323846;
+    for (int pr = 0; pr < 4; pr++)
+        for (int n = 0; n < 104; n++)
+            for (int j = 0; j < 104; j++) {
+                double c = 0.0;
+                // angles as exact multiples of 2 pi / 400
+                const int m_even = (int)(((long long)2 * j * n) % 400), m_odd = (int)(((long long)(2 * j + 1) * n) % 400);
+                if (pr == 0 && n <= 100 && j <= 100) c = std::cos(2.0 * kPi * m_even / 400.0) * (n == 100 ? 0.5 : 1.0);
+                if (pr == 1 && n >= 1 && n <= 99 && j >= 1 && j <= 99) c = std::sin(2.0 * kPi * m_even / 400.0);
+                if (pr == 2 && n <= 99 && j <= 99) c = std::cos(2.0 * kPi * m_odd / 400.0);
+                if (pr == 3 && n >= 1 && n <= 100 && j <= 99) c = std::sin(2.0 * kPi * m_odd / 400.0) * (n == 100 ? 0.5 : 1.0);
+                const uint16_t hi = b2a_f16::f32_to_f16((float)c);
+                const uint16_t lo = b2a_f16::f32_to_f16((float)(c - (double)b2a_f16::f16_to_f32(hi)));
+                const size_t off = (size_t)(n / 8) * kLbo + (size_t)(j / 8) * 128 + (size_t)(j % 8) * 16 + (size_t)(n % 8) * 2;
+                memcpy(&h[(size_t)(2 * pr) * kPlane + off], &hi, 2);
+                memcpy(&h[(size_t)(2 * pr + 1) * kPlane + off], &lo, 2);
+            }
+    float* win = (float*)&h[(size_t)kBank];
+    auto hann = [&](int n) { return (float)(0.5 - 0.5 * std::cos(2.0 * kPi * (double)(n % 400) / 400.0)); };   // torch.hann_window(400), periodic, f32
+    for (int n = 0; n <= 100; n++) {
+        win[0 * 112 + n] = 0.25f * hann(n);
+        win[1 * 112 + n] = 0.25f * hann(n + 200);
+        win[2 * 112 + n] = n == 0 ? 0.0f : 0.25f * hann(200 - n);
+        win[3 * 112 + n] = n == 0 ? 0.0f : 0.25f * hann(400 - n);
+    }
+    unsigned char* d = nullptr;
+    e = cudaMalloc((void**)&d, h.size());
+    if (e == cudaSuccess) e = cudaMemcpy(d, h.data(), h.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cuda_fail(e, "log-mel basis upload"); return nullptr; }
+    g_logmel_tc[dev] = d;
+    return d;
+}
+
 const ResampleDesign* get_resample_design(int in_rate, int out_rate) {
     if (in_rate <= 0 || out_rate <= 0) { set_error("bad sample rate %d -> %d", in_rate, out_rate); return nullptr; }
     int dev = 0;

@@ -146,14 +146,14 @@ static inline void umma_ts_warp(unsigned d_tmem, unsigned a_tmem, unsigned b_lo,
         const int n_dim = (int)((idesc >> 17) & 0x3fu) * 8, col0 = (int)(d_tmem & 0xffffu), acol = (int)(a_tmem & 0xffffu);
         for (int row = 0; row < 128; row++)
             for (int n = 0; n < n_dim; n++) {
-                float acc = accumulate ? g_emu_tmem[row][col0 + n] : 0.0f;
+                double sum = 0.0;
                 for (int k = 0; k < 16; k++) {
                     const unsigned aw = __float_as_uint(g_emu_tmem[row][acol + k / 2]);
                     const unsigned short av = (unsigned short)((k & 1) ? (aw >> 16) : (aw & 0xffffu));
                     const unsigned short bv = *(const unsigned short*)(b + (size_t)(k / 8) * b_lbo + (size_t)(n / 8) * b_sbo + (n % 8) * 16 + (k % 8) * 2);
-                    acc += emu::f16_to_f32(av) * emu::f16_to_f32(bv);
+                    sum += (double)emu::f16_to_f32(av) * (double)emu::f16_to_f32(bv);
                 }
-                g_emu_tmem[row][col0 + n] = acc;
+                g_emu_tmem[row][col0 + n] = emu_mma_accumulate(accumulate ? g_emu_tmem[row][col0 + n] : 0.0f, sum);
             }
     }
     __syncwarp();

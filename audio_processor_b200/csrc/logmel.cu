@@ -23,8 +23,11 @@
 //    pitch 203) — the fully unrolled immediate-weight form was 24-48 % slower on instruction fetch.  log10, running
 //    max/min and the [n_mels][T] store follow; a warp stores 32 consecutive frames of one mel = one 128-byte line.
 //  * K5 applies Whisper's global floor in place and skips tiles whose minimum is already above it.
+#include <cstdlib>
+
 #include "b2a_tables.cuh"
 #include "f16_bits.h"
+#include "logmel_tc.cuh"
 
 namespace b2a {
 
@@ -149,7 +152,7 @@ struct LogMelParams {
     i64* d_frames_out;     // optional
     int* gmax_key;         // [batch] (per-clip) or [1]
     int per_clip;
-    float* tile_min;       // [batch][tiles_cap]
+    int* tile_min;         // [batch][tiles_cap]: float_to_key of the minimum of every 32-frame tile
     i64 tiles_cap;         // tiles per clip at capacity
     const LogMelTables* tab;
     // fused stream compaction (pipeline, s16, batch == 1): when kept_ms != nullptr `audio` is the UNTRIMMED 16 kHz PCM of
@@ -455,7 +458,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
         __syncthreads();   // s_tile (and, first time, the tables) visible; previous tile's s_red written
         if (tid == 0 && prev_slot >= 0) {
             const float l2 = fminf(fminf(fminf(s_red[0], s_red[1]), fminf(s_red[2], s_red[3])), s_red[4]);
-            p.tile_min[prev_slot] = fmaf(l2 * 0.30102999566398120f, 0.25f, 1.0f);
+            p.tile_min[prev_slot] = float_to_key(fmaf(l2 * 0.30102999566398120f, 0.25f, 1.0f));
         }
         // next tile's s16 samples travel global -> registers while stage 1 runs
         unsigned pre[LM_PRE];
@@ -562,7 +565,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
     __syncthreads();
     if (tid == 0 && prev_slot >= 0) {
         const float l2 = fminf(fminf(fminf(s_red[0], s_red[1]), fminf(s_red[2], s_red[3])), s_red[4]);
-        p.tile_min[prev_slot] = fmaf(l2 * 0.30102999566398120f, 0.25f, 1.0f);
+        p.tile_min[prev_slot] = float_to_key(fmaf(l2 * 0.30102999566398120f, 0.25f, 1.0f));
     }
     if (!p.per_clip) {
         const float bm = warp_reduce_max_f(run_max);
@@ -595,7 +598,7 @@ __global__ void __launch_bounds__(256, 3) mel_floor_kernel(LogMelParams p, int c
             b = (int)(work / tiles);
             tile = (int)(work - (i64)b * tiles);
             floor_l = ((key_to_float(p.gmax_key[p.per_clip ? b : 0]) - 8.0f) + 4.0f) * 0.25f;
-            need = p.tile_min[(size_t)b * (size_t)p.tiles_cap + (size_t)tile] < floor_l;
+            need = key_to_float(p.tile_min[(size_t)b * (size_t)p.tiles_cap + (size_t)tile]) < floor_l;
         }
         unsigned m = __ballot_sync(0xFFFFFFFFu, need);
         while (m) {
@@ -619,9 +622,11 @@ __global__ void __launch_bounds__(256, 3) mel_floor_kernel(LogMelParams p, int c
     }
 }
 
-__global__ void logmel_init_kernel(int* gmax_key, int n) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+// gmax keys start at -inf; the per-group minima at +inf (the tensor-core kernel lowers them with atomicMin, one per role)
+__global__ void logmel_init_kernel(int* gmax_key, int n, int* tile_min_key, i64 n_groups) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) gmax_key[i] = float_to_key(-3.0e38f);
+    if (tile_min_key && i < n_groups) tile_min_key[i] = float_to_key(3.0e38f);
 }
 
 template <int FMT> static size_t logmel_smem_bytes() { return (size_t)LmSmem<FMT>::WORDS * 4; }
@@ -656,7 +661,7 @@ int logmel_launch(const void* d_audio, int fmt, i64 batch, i64 n, i64 row_stride
     p.n_mels = n_mels; p.batch = (int)batch; p.out = d_out; p.d_frames_out = d_frames_out;
     p.gmax_key = (int*)d_ws;
     p.per_clip = (norm_mode == B2A_NORM_PER_CLIP);
-    p.tile_min = (float*)((char*)d_ws + align_up((size_t)batch * 4, 256));
+    p.tile_min = (int*)((char*)d_ws + align_up((size_t)batch * 4, 256));
     p.tiles_cap = logmel_tiles_cap(n, padding);
     p.tab = tab;
     p.kept_ms = nullptr; p.kept_off = nullptr; p.info = nullptr; p.trim_out = nullptr; p.n_src = 0;
@@ -668,21 +673,65 @@ int logmel_launch(const void* d_audio, int fmt, i64 batch, i64 n, i64 row_stride
     i64 work = p.tiles_cap * batch;
     if (work <= 0) { if (d_frames_out) cudaMemsetAsync(d_frames_out, 0, 8, stream); return B2A_OK; }
     int nkeys = (int)batch;
-    auto kinit = logmel_init_kernel;
-    B2A_LAUNCH(kinit, (nkeys + 255) / 256, 256, 0, stream, p.gmax_key, nkeys);
     const bool s16 = fmt == B2A_FMT_S16;
-    size_t smem = s16 ? logmel_smem_bytes<B2A_FMT_S16>() : logmel_smem_bytes<B2A_FMT_F32>();
-    auto k4 = gather ? (n_mels == 80 ? stft_mel_kernel<80, B2A_FMT_S16, true> : stft_mel_kernel<128, B2A_FMT_S16, true>)
-              : n_mels == 80 ? (s16 ? stft_mel_kernel<80, B2A_FMT_S16, false> : stft_mel_kernel<80, B2A_FMT_F32, false>)
-                             : (s16 ? stft_mel_kernel<128, B2A_FMT_S16, false> : stft_mel_kernel<128, B2A_FMT_F32, false>);
+    auto kinit = logmel_init_kernel;
+    {
+        const i64 n_groups = s16 ? p.tiles_cap * batch : 0;      // the tensor-core kernel needs the minima initialised
+        const i64 n_init = n_groups > nkeys ? n_groups : nkeys;
+        B2A_LAUNCH(kinit, (unsigned)((n_init + 255) / 256), 256, 0, stream, p.gmax_key, nkeys, s16 ? p.tile_min : (int*)nullptr, n_groups);
+    }
+    if (s16) {
+        // 16-bit input: the tensor-core kernel (logmel_tc.cuh); 128-frame tiles, minima per 32-frame group as before
+        const unsigned char* blob = get_logmel_tc_blob();
+        if (!blob) return B2A_ECUDA;
+        LogMelTcParams q;
+        q.audio = (const int16_t*)d_audio; q.row_stride = row_stride; q.n = n; q.d_n = d_n; q.padding = padding; q.batch = (int)batch;
+        q.out = d_out; q.d_frames_out = d_frames_out; q.gmax_key = p.gmax_key; q.per_clip = p.per_clip;
+        q.tile_min_key = p.tile_min; q.groups_cap = p.tiles_cap; q.blob = blob;
+        q.kept_ms = p.kept_ms; q.kept_off = p.kept_off; q.info = p.info; q.trim_out = p.trim_out; q.n_src = p.n_src;
+        const i64 tiles128 = ((n + padding) / kHop + kTcFrames - 1) / kTcFrames + (gather ? 1 : 0);
+        const i64 work_tc = tiles128 * batch;
+        unsigned grid_tc = (unsigned)(work_tc < 148 ? work_tc : 148);
+#if defined(B2A_PROFILE) || defined(B2A_EMU)
+        if (const char* gs = getenv("B2A_LM_GRID")) {            // emulation / profiling builds only: few CTAs => many tiles per CTA
+            const int gv = atoi(gs);
+            if (gv > 0 && (unsigned)gv < grid_tc) grid_tc = (unsigned)gv;
+        }
+#endif
+        static unsigned long long attr_mask = 0;             // per-device opt-in to > 48 KB of dynamic shared memory
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !((attr_mask >> dev) & 1ull)) {
+            cudaError_t e = cudaFuncSetAttribute(logmel_tc_kernel<80, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_tc_kernel<80, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(logmel_tc_kernel)");
+            if (dev >= 0 && dev < 64) attr_mask |= 1ull << dev;
+        }
+        if (grid_tc > 0) {
+            if (n_mels == 80) {
+                if (gather) { auto k = logmel_tc_kernel<80, true>; B2A_LAUNCH(k, grid_tc, kTcThreads, kTcSmemBytes, stream, q); }
+                else { auto k = logmel_tc_kernel<80, false>; B2A_LAUNCH(k, grid_tc, kTcThreads, kTcSmemBytes, stream, q); }
+            } else {
+                if (gather) { auto k = logmel_tc_kernel<128, true>; B2A_LAUNCH(k, grid_tc, kTcThreads, kTcSmemBytes, stream, q); }
+                else { auto k = logmel_tc_kernel<128, false>; B2A_LAUNCH(k, grid_tc, kTcThreads, kTcSmemBytes, stream, q); }
+            }
+            B2A_CHECK_LAUNCH("logmel_tc_kernel");
+        }
+    } else {
+    // float input: the CUDA-core FFT kernel (its 83 KB f32 tile does not fit next to the tensor-core kernel's basis bank)
+    size_t smem = logmel_smem_bytes<B2A_FMT_F32>();
+    auto k4 = n_mels == 80 ? stft_mel_kernel<80, B2A_FMT_F32, false> : stft_mel_kernel<128, B2A_FMT_F32, false>;
     {
         cudaError_t e = cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // idempotent, cheap
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(stft_mel)");
     }
-    const i64 resident = 148 * (s16 ? LmSmem<B2A_FMT_S16>::CTAS : LmSmem<B2A_FMT_F32>::CTAS);   // persistent: every CTA resident
+    const i64 resident = 148 * LmSmem<B2A_FMT_F32>::CTAS;   // persistent: every CTA resident
     i64 grid = work < resident ? work : resident;
     B2A_LAUNCH(k4, (unsigned)grid, LM_THREADS, smem, stream, p);
     B2A_CHECK_LAUNCH("stft_mel_kernel");
+    }
     i64 chunk5 = work / (148 * 8 * 8);                                     // tiles per warp and round: fill the machine first
     chunk5 = chunk5 < 1 ? 1 : chunk5 > 32 ? 32 : chunk5;
     const i64 warps5 = (work + chunk5 - 1) / chunk5;

@@ -16,7 +16,7 @@ OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libb2a_emu.so")
 
 sys.path.insert(0, ROOT)
-from audio_processor_b200.build import SOURCES, gen_mel  # noqa: E402
+from audio_processor_b200.build import SOURCES, gen_mel, gen_mel_tc  # noqa: E402
 
 FLAGS = ["-O1", "-std=c++17", "-fPIC", "-DB2A_EMU", "-I", HERE, "-I", os.path.join(ROOT, "include"),
          "-include", os.path.join(HERE, "cuda_emu.h"), "-x", "c++", "-mfma", "-mavx2", "-ffp-contract=fast",
@@ -26,6 +26,7 @@ FLAGS = ["-O1", "-std=c++17", "-fPIC", "-DB2A_EMU", "-I", HERE, "-I", os.path.jo
 def build(force: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     gen_mel()
+    gen_mel_tc()
     dep_m = 0.0
     for d in (CSRC, HERE, os.path.join(ROOT, "include")):
         for f in os.listdir(d):

@@ -218,3 +218,60 @@ def test_emu_pipeline_fused_compaction_many_short_segments(emu, keep, pad, extra
     assert np.array_equal(r["pcm"], trimmed)
     ref = wl.log_mel_spectrogram(trimmed.astype(np.float32) / 32768.0, 80, padding=pad).numpy()
     assert r["mel"].shape == ref.shape and np.abs(r["mel"] - ref).max() <= 1e-4
+
+
+def test_emu_logmel_tc_many_tiles_per_cta(emu, monkeypatch):
+    """the tensor-core log-mel (logmel_tc.cuh) with 2 persistent CTAs over 7 tiles of 128 frames: operand-ring and
+    accumulator barrier parities across tiles, raw-tile reuse, a partial last tile, whole-call maximum"""
+    monkeypatch.setenv("B2A_LM_GRID", "2")
+    rng = np.random.default_rng(5)
+    n = 160 * 128 * 6 + 160 * 50 + 77
+    t = np.arange(n) / 16000.0
+    x = (6000 * np.sin(2 * np.pi * 523.0 * t) * (1 + 0.5 * np.sin(2 * np.pi * 0.7 * t)) + rng.standard_normal(n) * 40).astype(np.int16)
+    ref = wl.log_mel_spectrogram(x.astype(np.float32) / 32768.0, 80).numpy()
+    got = emu.log_mel(x, 80)
+    assert got.shape == ref.shape and np.abs(got - ref).max() <= 1e-4
+    monkeypatch.setenv("B2A_LM_GRID", "3")
+    ref = wl.log_mel_spectrogram(x.astype(np.float32) / 32768.0, 128, padding=160 * 300).numpy()
+    got = emu.log_mel(x, 128, padding=160 * 300)
+    assert got.shape == ref.shape and np.abs(got - ref).max() <= 1e-4
+
+
+def test_emu_logmel_tc_batch_unaligned_and_short(emu):
+    """batches of 16-bit clips (work item = clip x tile, per-clip and whole-call maximum), rows whose stride breaks the
+    16-byte alignment of the bulk copies (lanes copy those rows themselves), clips shorter than one tile"""
+    rng = np.random.default_rng(6)
+    b = (rng.standard_normal((3, 160 * 130 + 3)) * np.array([[3000], [100], [3]])).astype(np.int16)
+    f = b.astype(np.float32) / 32768.0
+    assert np.abs(emu.log_mel(b, 80) - wl.log_mel_spectrogram(f, 80).numpy()).max() <= 1e-4
+    assert np.abs(emu.log_mel(b, 128, norm_mode=1) - wl.log_mel_spectrogram(f, 128, per_clip_max=True).numpy()).max() <= 1e-4
+    s = (rng.standard_normal(401) * 2000).astype(np.int16)
+    assert np.abs(emu.log_mel(s, 80) - wl.log_mel_spectrogram(s.astype(np.float32) / 32768.0, 80).numpy()).max() <= 1e-4
+    assert np.all(emu.log_mel(np.zeros(16000, np.int16), 80) == -1.5)
+
+
+def test_emu_logmel_tc_tone_over_noise_floor(emu):
+    """the worst probed dynamic range for the f16-plane DFT: a full-scale tone over a +-2 LSB noise floor"""
+    rng = np.random.default_rng(7)
+    n = 16000 * 3
+    x = np.clip(np.rint(32000 * np.sin(2 * np.pi * 1234.5 * np.arange(n) / 16000) + rng.normal(0, 2, n)), -32768, 32767).astype(np.int16)
+    for nm in (80, 128):
+        assert np.abs(emu.log_mel(x, nm) - wl.log_mel_spectrogram(x.astype(np.float32) / 32768.0, nm).numpy()).max() <= 1e-4
+
+
+def test_emu_pipeline_tc_gather_window_overflow(emu):
+    """more than 32 kept ranges under one 128-frame tile (40 ms bursts): the producer's cached range window overflows and
+    the rows behind it take the per-sample path; result identical to the oracle's trimmed PCM and log-mel"""
+    rng = np.random.default_rng(8)
+    parts = []
+    for i in range(60):
+        parts.append((rng.standard_normal(16 * 25) * 5000).astype(np.int16))
+        parts.append((rng.standard_normal(16 * 30) * 2).astype(np.int16))
+    x = np.concatenate(parts)
+    kw = dict(min_silence_len=20, silence_thresh=-50, keep_silence=2, seek_step=1)
+    r = emu.pipeline(x, 16000, n_mels=80, padding=0, **kw)
+    assert r["kept"] == ps.kept_ranges_fast(x, 16000, **kw) and len(r["kept"]) >= 50
+    trimmed = ps.strip_silence_fast(x, 16000, **kw)
+    assert np.array_equal(r["pcm"], trimmed)
+    ref = wl.log_mel_spectrogram(trimmed.astype(np.float32) / 32768.0, 80).numpy()
+    assert r["mel"].shape == ref.shape and np.abs(r["mel"] - ref).max() <= 1e-4
