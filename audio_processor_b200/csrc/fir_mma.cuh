@@ -390,10 +390,10 @@ template <int IN_RATE, int CH>
 static inline int fir_mma_launch(const void* d_in, i64 n_in, int16_t* d_out_s16, u64* d_energy, FirMmaPlan* plan, cudaStream_t stream, i64 first_tile = 1) {
     using G = FirMmaGeom<IN_RATE, CH>;
     plan->out_lo = plan->out_hi = 0;
-    // tile t reads frames [t*RT*S - CENTER - AL, that + RAW_BYTES/4): t >= 1 keeps the start inside the clip; the first
+    // tile t reads frames [t*RT*S - CENTER - AL, that + RAW_BYTES/FB), FB = bytes per frame: t >= 1 keeps the start inside the clip; the first
     // 16 runs (reflect head) and the tail go to the table-driven kernel
     const i64 tile_lo = first_tile < 1 ? 1 : first_tile;       // (the tcgen05 kernel hands over the 16-run tiles behind its last span)
-    const i64 span_end = (i64)G::RAW_BYTES / 4 - G::CENTER - G::AL;          // relative to the tile's first run start
+    const i64 span_end = (i64)G::RAW_BYTES / G::FB - G::CENTER - G::AL;      // relative to the tile's first run start (round 1 divided by 4 for mono too: the last tile read past the clip on some lengths)
     const i64 tile_hi = (n_in - span_end) >= 0 ? (n_in - span_end) / ((i64)kFmRT * G::S) + 1 : 0;   // exclusive
     if (tile_hi <= tile_lo) return 0;
     const uint2* tab = get_fir_mma_table(IN_RATE);

@@ -17,12 +17,15 @@
 // restates the arithmetic (incl. the accumulator's truncation): max |err| 2e-5 .. 7.5e-5 against the float64 oracle on
 // tones over a noise floor, where torch.stft in f32 sits at 6e-5 .. 8e-5; the gate is 1e-4.
 //
-// One persistent CTA per SM, 18 warps coupled only by mbarriers:
-//   warp 17      producer: stages the tile's 20 720 raw samples (128 hops + 240) in shared memory as 130 padded rows of one hop
-//                (pitch 336 B: conflict-free 16-byte reads by thread = frame) with one 1-D bulk copy per row piece.  In the
-//                pipeline the rows are gathered through the kept-range table (fused stream compaction) and the tile's own
-//                samples go back out as the trimmed PCM with bulk stores; rows that touch the clip's edges (reflect pad,
-//                zero pad, a zero-filled last millisecond) are written by the lanes themselves.
+// One persistent CTA per SM, 17 warps coupled only by mbarriers:
+//   warps 8-15   loaders (idle while a tile is converted): fetch the NEXT tile's 20 720 raw samples (128 hops + 240) as 2 590
+//                16-byte chunks into registers while the current tile is converted, and drop them into shared memory the
+//                moment the converters release it: 130 padded rows of one hop (pitch 336 B: conflict-free 16-byte reads by
+//                thread = frame).  In the pipeline the chunks are gathered through the kept-range table (fused stream
+//                compaction) and the tile's own chunks go straight back out as the trimmed PCM; chunks that touch the clip's
+//                edges (reflect pad, zero pad, a zero-filled last millisecond) are assembled sample by sample.
+//                (A first version staged the rows with one 1-D bulk copy each: 130 small TMA requests per tile took 8 us,
+//                profiles/r02_logmel_tc.md.)
 //   warps 0-7    converters, thread = frame: role 0 / 1 = lower / upper 8 of a k-step's 16 n-values; LDS.128 of the four
 //                segments x[n], x[n+200], x[200-n], x[400-n], window + folds in f32, split into f16 planes, tcgen05.st into a
 //                ring of four 16-column operand slots in TMEM (slot = product), one full / free mbarrier pair per slot.
@@ -53,9 +56,12 @@ constexpr int kTcRows = kTcFrames + 2;               // hops staged per tile
 constexpr int kTcRowBytes = 336;                     // 160 samples + 8 of padding
 constexpr int kTcRawBytes = kTcRows * kTcRowBytes;
 constexpr int kTcLastRowSamples = 88;                // samples of row 129 a tile needs (x[400] of its last frame is sample 80)
-constexpr int kTcSegWin = 32;                        // kept ranges cached per tile by the gathering producer
-constexpr int kTcWorkers = 16, kTcIssuer = 16, kTcProducer = 17;
-constexpr int kTcThreads = 18 * 32;
+constexpr int kTcSegWin = 32;                        // kept ranges cached per tile by every gathering loader warp
+constexpr int kTcWorkers = 16, kTcIssuer = 16;
+constexpr int kTcThreads = 17 * 32;
+constexpr int kTcLoaders = 8 * 32;                   // loader threads (warps 8-15)
+constexpr int kTcChunks = (kTcFrames * kHop + 240) / 8;           // 16-byte chunks of a raw tile (2 590)
+constexpr int kTcChunkRounds = (kTcChunks + kTcLoaders - 1) / kTcLoaders;   // 11
 constexpr int kTcRingCol = kTcNP * kTcNB;            // 448
 constexpr unsigned kTcIdesc = (1u << 4) | ((unsigned)(kTcNB >> 3) << 17) | ((unsigned)(kTcFrames >> 4) << 24);
 // barriers
@@ -65,7 +71,7 @@ constexpr int kTcSmemWin = kTcBankBytes;
 constexpr int kTcSmemRaw = kTcBlobBytes;
 constexpr int kTcSmemBars = kTcSmemRaw + kTcRawBytes + 32;
 constexpr int kTcSmemSeg = kTcSmemBars + kTcNBars * kFmBarBytes;       // [33] kept_off window, [32] source sample of each range
-constexpr int kTcSmemMisc = kTcSmemSeg + (2 * kTcSegWin + 1) * 8;
+constexpr int kTcSmemMisc = kTcSmemSeg + 8 * (2 * kTcSegWin + 1) * 8;     // one window per loader warp
 constexpr int kTcSmemBytes = kTcSmemMisc + 64;
 static_assert(kTcBankBytes % 16 == 0 && kTcSmemRaw % 16 == 0 && kTcSmemBars % 8 == 0 && kTcSmemSeg % 8 == 0, "alignment");
 static_assert(kTcSmemBytes <= 232448, "shared-memory budget (227 KB per CTA)");
@@ -242,7 +248,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) logmel_tc_kernel(const LogMelTc
         for (int i = 0; i < kTcNP; i++) { mbar_init(BAR(kTcBarFull + i), 8); mbar_init(BAR(kTcBarFree + i), 1); }
         mbar_init(BAR(kTcBarAccFull), 1);
         mbar_init(BAR(kTcBarAccFree), kTcWorkers);
-        mbar_init(BAR(kTcBarRawFull), 32);
+        mbar_init(BAR(kTcBarRawFull), 8);
         mbar_init(BAR(kTcBarRawFree), 8);
         mbar_init(BAR(kTcBarBank), 1);
         mbar_fence_init();
@@ -294,129 +300,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) logmel_tc_kernel(const LogMelTc
             }
             umma_commit_warp(BAR(kTcBarAccFull));
         }
-    } else if (warp == kTcProducer) {
-        // ---------------- producer: raw tile -> shared memory (and the trimmed PCM back out) ----------------
-        i64* s_off = (i64*)(smem + kTcSmemSeg);                // kept_off[sg0 .. sg0 + 32]
-        i64* s_src = s_off + kTcSegWin + 1;                    // 16 * kept_ms[2 (sg0 + l)]
-        const int n_seg = GATHER ? (int)p.info[B2A_INFO_N_KEPT] : 0;
-        const i64 kInf = (i64)1 << 62;
-        auto seg_of_global = [&](i64 q) -> int {               // largest k with kept_off[k] <= q (n_seg > 0)
-            int lo = 0, hi = n_seg - 1;
-            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (p.kept_off[mid] <= q) lo = mid; else hi = mid - 1; }
-            return lo;
-        };
-        unsigned it = 0;
-        for (i64 work = blockIdx.x; work < n_work; work += gridDim.x, it++) {
-            int b;
-            i64 tile;
-            split_work(work, b, tile);
-            const int16_t* row = p.audio + (size_t)b * (size_t)p.row_stride;
-            const i64 q0 = tile * (kTcFrames * kHop) - 200;    // padded-domain index of raw sample 0
-            // kept ranges under this tile (looked up while the previous tile is still being converted)
-            int sg0 = 0;
-            if (GATHER && n_seg > 0) {
-                sg0 = seg_of_global(q0 > 0 ? q0 : 0);          // every lane runs the same search (uniform loads, L2 hits)
-                const int k = sg0 + lane;
-                const i64 off = k <= n_seg ? p.kept_off[k] : kInf;
-                const i64 src = k < n_seg ? (i64)p.kept_ms[2 * k] * 16 : 0;
-                if (it > 0) { mbar_wait(BAR(kTcBarRawFree), (it - 1) & 1u); bulk_store_wait_read(); }
-                __syncwarp();
-                s_off[lane] = off;
-                s_src[lane] = src;
-                if (lane == 0) s_off[kTcSegWin] = sg0 + kTcSegWin <= n_seg ? p.kept_off[sg0 + kTcSegWin] : kInf;
-                __syncwarp();
-            } else if (it > 0) {
-                mbar_wait(BAR(kTcBarRawFree), (it - 1) & 1u);
-                bulk_store_wait_read();
-            }
-            // source sample of trimmed index q (0 <= q < n_act); -1: zero (pydub zero-fills a rounded-up last millisecond)
-            auto src_index = [&](i64 q) -> i64 {
-                if (!GATHER) return q;
-                if (n_seg <= 0) return -1;
-                const int sg = seg_of_global(q);
-                const i64 si = (i64)p.kept_ms[2 * sg] * 16 + (q - p.kept_off[sg]);
-                return si < p.n_src ? si : -1;
-            };
-            unsigned tx = 0;
-            for (int i = lane; i < kTcRows; i += 32) {
-                const int len = i == kTcRows - 1 ? kTcLastRowSamples : kHop;
-                const i64 qs = q0 + (i64)kHop * i;
-                const saddr_t dst = s_base + kTcSmemRaw + (unsigned)(i * kTcRowBytes);
-                bool done = false;
-                if (qs >= 0 && qs + len <= n_act) {
-                    // interior row: one bulk copy per kept range under it
-                    if (!GATHER) {
-                        const int16_t* src = row + qs;
-                        if ((((uintptr_t)src) & 15) == 0) { bulk_load(dst, src, (unsigned)len * 2u, BAR(kTcBarRawFull)); tx += (unsigned)len * 2u; done = true; }
-                    } else if (n_seg > 0 && qs + len <= s_off[kTcSegWin]) {
-                        int e = 0;                              // largest e with s_off[e] <= qs
-                        for (int st = 16; st > 0; st >>= 1) if (e + st < kTcSegWin && s_off[e + st] <= qs) e += st;
-                        // dry run: every piece must come from inside the source buffer
-                        bool ok = true;
-                        { i64 q = qs; int ee = e;
-                          while (q < qs + len) { const i64 qe = s_off[ee + 1] < qs + len ? s_off[ee + 1] : qs + len; if (s_src[ee] + (qe - s_off[ee]) > p.n_src) ok = false; q = qe; ee++; } }
-                        if (ok) {
-                            i64 q = qs;
-                            while (q < qs + len) {
-                                const i64 qe = s_off[e + 1] < qs + len ? s_off[e + 1] : qs + len;
-                                const unsigned bytes = (unsigned)(qe - q) * 2u;
-                                bulk_load(dst + (unsigned)(q - qs) * 2u, p.audio + s_src[e] + (q - s_off[e]), bytes, BAR(kTcBarRawFull));
-                                tx += bytes;
-                                q = qe; e++;
-                            }
-                            done = true;
-                        }
-                    }
-                } else if (qs >= n_act && qs + len <= ltot) {
-                    for (int c = 0; c < kHop * 2; c += 16) sts_zero16(dst + (unsigned)c);     // right padding: zeros
-                    done = true;
-                } else if (qs >= ltot + 200) {
-                    done = true;                                 // behind the last frame's window: never read by a valid frame
-                }
-                if (!done) {
-                    // edge row: reflect at both ends of the padded clip, zeros past n_act; own samples also go to the trimmed PCM
-                    for (int c = 0; c < len; c++) {
-                        i64 q = qs + c;
-                        const bool own = GATHER && q >= 0 && q < n_act && (i64)kHop * i + c >= 200 && (i64)kHop * i + c < 200 + kTcFrames * kHop;
-                        if (q < 0) q = -q;
-                        if (q >= ltot) q = 2 * (ltot - 1) - q;
-                        int v = 0;
-                        if (q >= 0 && q < n_act) { const i64 si = src_index(q); if (si >= 0) v = (GATHER ? p.audio : row)[si]; }
-                        sts_u16(dst + (unsigned)c * 2u, (unsigned)v & 0xffffu);
-                        if (own) p.trim_out[q] = (int16_t)v;
-                    }
-                }
-            }
-            // one arrival per lane; lane 0 also posts the byte count of every lane's copies
-            unsigned tx_all = tx;
-            for (int o = 16; o > 0; o >>= 1) tx_all += __shfl_xor_sync(0xffffffffu, tx_all, o);
-            if (lane == 0) { if (tx_all) mbar_expect_tx_only(BAR(kTcBarRawFull), tx_all); }
-            __syncwarp();
-            mbar_arrive(BAR(kTcBarRawFull));
-            if (GATHER) {
-                // the tile's own 20 480 trimmed samples (raw samples 200 .. 20 679) leave through bulk stores, row by row
-                mbar_wait(BAR(kTcBarRawFull), it & 1u);
-                for (int i = 1 + lane; i < kTcRows; i += 32) {
-                    const int len = i == kTcRows - 1 ? kTcLastRowSamples : kHop;
-                    const i64 qs = q0 + (i64)kHop * i;
-                    if (!(qs >= 0 && qs + len <= n_act)) continue;                         // edge rows wrote their own samples above
-                    const int c0 = i == 1 ? 40 : 0, c1 = i == kTcRows - 1 ? 40 : kHop;     // own columns of this row
-                    // bulk rows only: same predicate as above (interior + every piece inside the source buffer)
-                    bool bulk = n_seg > 0 && qs + len <= s_off[kTcSegWin];
-                    if (bulk) {
-                        int e = 0;
-                        for (int st = 16; st > 0; st >>= 1) if (e + st < kTcSegWin && s_off[e + st] <= qs) e += st;
-                        i64 q = qs;
-                        while (q < qs + len) { const i64 qe = s_off[e + 1] < qs + len ? s_off[e + 1] : qs + len; if (s_src[e] + (qe - s_off[e]) > p.n_src) bulk = false; q = qe; e++; }
-                    }
-                    if (bulk) bulk_store(p.trim_out + qs + c0, s_base + kTcSmemRaw + (unsigned)(i * kTcRowBytes + 2 * c0), (unsigned)(c1 - c0) * 2u);
-                }
-                bulk_store_commit();
-            }
-        }
-        if (GATHER) bulk_store_wait_all();
     } else {
-        // ---------------- workers: converters (roles 0, 1) and epilogue (roles 0-3) ----------------
+        // ---------------- workers: converters (roles 0, 1), loaders (roles 2, 3), epilogue (all four roles) ----------------
         const int q = warp & 3, role = warp >> 2;
         const int f = 32 * q + lane;                                    // frame (row) of the tile
         const unsigned tlane = tbase + ((unsigned)(32 * q) << 16);
@@ -425,11 +310,120 @@ __global__ void __launch_bounds__(kTcThreads, 1) logmel_tc_kernel(const LogMelTc
         float run_max = -3.0e38f;
         unsigned g = 0, it = 0;
         if (role < 2) mbar_wait(BAR(kTcBarBank), 0);                    // window tables
+
+        // ---- loader state (roles 2, 3): the next tile's chunks travel global -> registers -> shared memory ----
+        const int lt = (warp - 8) * 32 + lane;                          // loader thread 0..255
+        i64* s_off = (i64*)(smem + kTcSmemSeg) + (warp >= 8 ? warp - 8 : 0) * (2 * kTcSegWin + 1);   // this warp's kept_off[sg0 .. sg0 + 32]
+        i64* s_src = s_off + kTcSegWin + 1;                              // 16 * kept_ms[2 (sg0 + l)]
+        const int n_seg = GATHER ? (int)p.info[B2A_INFO_N_KEPT] : 0;
+        uint4 pre[kTcChunkRounds];
+        auto seg_of_global = [&](i64 qq) -> int {                        // largest k with kept_off[k] <= qq (n_seg > 0), per lane
+            int lo = 0, hi = n_seg - 1;
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (p.kept_off[mid] <= qq) lo = mid; else hi = mid - 1; }
+            return lo;
+        };
+        // source sample of trimmed index qq (0 <= qq < n_act); -1: zero (pydub zero-fills a rounded-up last millisecond)
+        auto src_index = [&](i64 qq) -> i64 {
+            if (!GATHER) return qq;
+            if (n_seg <= 0) return -1;
+            const int sg = seg_of_global(qq);
+            const i64 si = (i64)p.kept_ms[2 * sg] * 16 + (qq - p.kept_off[sg]);
+            return si < p.n_src ? si : -1;
+        };
+        auto fetch_tile = [&](i64 work_n) {
+            int bn;
+            i64 tile_n;
+            split_work(work_n, bn, tile_n);
+            const int16_t* row = p.audio + (size_t)bn * (size_t)p.row_stride;
+            const i64 q0 = tile_n * (kTcFrames * kHop) - 200;            // padded-domain index of raw sample 0
+            if (GATHER && n_seg > 0) {
+                // kept range under the tile's first sample: 32-ary search (three rounds of parallel probes for 8 192 ranges),
+                // then the window of the next 32 ranges into this warp's shared-memory slots
+                const i64 qq = q0 > 0 ? q0 : 0;
+                int lo = 0, cnt = n_seg;                                   // the answer lies in [lo, lo + cnt); kept_off[lo] <= qq
+                while (cnt > 1) {
+                    const int stride = (cnt + 31) / 32;
+                    const int idx = lo + lane * stride;
+                    const bool le = idx < lo + cnt && p.kept_off[idx] <= qq;
+                    const int c = __popc(__ballot_sync(0xffffffffu, le));   // probes are monotone; lane 0 always holds
+                    const int nlo = lo + (c - 1) * stride;
+                    cnt = nlo + stride > lo + cnt ? lo + cnt - nlo : stride;
+                    lo = nlo;
+                }
+                const int k = lo + lane;
+                __syncwarp();
+                s_off[lane] = k <= n_seg ? p.kept_off[k] : ((i64)1 << 62);
+                s_src[lane] = k < n_seg ? (i64)p.kept_ms[2 * k] * 16 : 0;
+                if (lane == 0) s_off[kTcSegWin] = lo + kTcSegWin <= n_seg ? p.kept_off[lo + kTcSegWin] : ((i64)1 << 62);
+                __syncwarp();
+            }
+#pragma unroll
+            for (int r = 0; r < kTcChunkRounds; r++) {
+                const int c = lt + kTcLoaders * r;
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (c < kTcChunks) {
+                    const i64 qc = q0 + 8 * (i64)c;
+                    const int16_t* src = nullptr;
+                    if (qc >= 0 && qc + 8 <= n_act) {
+                        if (!GATHER) src = row + qc;
+                        else if (n_seg > 0) {
+                            if (qc < s_off[kTcSegWin]) {
+                                int e = 0;                               // largest e with s_off[e] <= qc
+#pragma unroll
+                                for (int st = 16; st > 0; st >>= 1) if (s_off[e + st] <= qc) e += st;
+                                src = p.audio + s_src[e] + (qc - s_off[e]);
+                            } else {
+                                const int sg = seg_of_global(qc);
+                                src = p.audio + (i64)p.kept_ms[2 * sg] * 16 + (qc - p.kept_off[sg]);
+                            }
+                            if (src + 8 > p.audio + p.n_src) src = nullptr;   // zero-filled last millisecond: sample by sample
+                        }
+                        if ((((uintptr_t)src) & 15) != 0) src = nullptr;
+                    }
+                    if (src) {
+                        v = *(const uint4*)src;
+                    } else if (!(qc >= n_act && qc + 8 <= ltot) && qc < ltot + 200) {
+                        // edge chunk: reflect at both ends of the padded clip, zeros past n_act
+                        unsigned w[4] = {0u, 0u, 0u, 0u};
+                        for (int j = 0; j < 8; j++) {
+                            i64 qq = qc + j;
+                            if (qq < 0) qq = -qq;
+                            if (qq >= ltot) qq = 2 * (ltot - 1) - qq;
+                            int sv = 0;
+                            if (qq >= 0 && qq < n_act) { const i64 si = src_index(qq); if (si >= 0) sv = (GATHER ? p.audio : row)[si]; }
+                            w[j >> 1] |= ((unsigned)sv & 0xffffu) << (16 * (j & 1));
+                        }
+                        v = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                    // the tile's own 20 480 trimmed samples (raw samples 200 .. 20 679) are the trimmed PCM
+                    if (GATHER && c >= 25 && c < 25 + kTcFrames * kHop / 8 && qc + 8 <= n_act) *(uint4*)(p.trim_out + qc) = v;
+                }
+                pre[r] = v;
+            }
+        };
+        auto store_tile = [&]() {
+#pragma unroll
+            for (int r = 0; r < kTcChunkRounds; r++) {
+                const int c = lt + kTcLoaders * r;
+                if (c < kTcChunks) *(uint4*)(smem + kTcSmemRaw + (c / 20) * kTcRowBytes + (c % 20) * 16) = pre[r];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(kTcBarRawFull));
+        };
+        if (role >= 2 && (i64)blockIdx.x < n_work) { fetch_tile(blockIdx.x); store_tile(); }
+
         for (i64 work = blockIdx.x; work < n_work; work += gridDim.x, it++) {
             int b;
             i64 tile;
             split_work(work, b, tile);
-            if (role < 2) {
+            if (role >= 2) {
+                // next tile: loads in flight while this one is converted, into shared memory once the converters are done with it
+                if (work + gridDim.x < n_work) {
+                    fetch_tile(work + gridDim.x);
+                    mbar_wait(BAR(kTcBarRawFree), it & 1u);
+                    store_tile();
+                }
+            } else {
                 mbar_wait(BAR(kTcBarRawFull), it & 1u);
 #pragma unroll 1
                 for (int s = 0; s < kTcKS; s++, g++) {

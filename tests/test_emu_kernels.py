@@ -275,3 +275,16 @@ def test_emu_pipeline_tc_gather_window_overflow(emu):
     assert np.array_equal(r["pcm"], trimmed)
     ref = wl.log_mel_spectrogram(trimmed.astype(np.float32) / 32768.0, 80).numpy()
     assert r["mel"].shape == ref.shape and np.abs(r["mel"] - ref).max() <= 1e-4
+
+
+@pytest.mark.parametrize("n", [7056 * 32 + 5000, 7056 * 32 + 3708, 7056 * 16 + 6990])
+def test_emu_fir_mono_last_tile_stays_inside_the_clip(emu, n):
+    """mono input: the last 16-run tile of the mma.sync kernel must not read past the clip (round 1 sized the tile count with
+    stereo's 4 bytes per frame: on lengths up to 3 600 frames behind a tile boundary the tail came out wrong)"""
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal(n) * 6000).clip(-32768, 32767).astype(np.int16)
+    y, en = emu.resample(x, 44100, want_energy=True)
+    assert np.abs(y.astype(int) - ro.convert(x, 44100).astype(int)).max() <= 1
+    if swr_ref.available():
+        _cmp16(y, swr_ref.convert(x, 44100), 0.998)
+    assert np.array_equal(en.astype(np.int64), H.energy_oracle(y))
