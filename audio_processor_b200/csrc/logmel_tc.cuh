@@ -17,24 +17,31 @@
 // restates the arithmetic (incl. the accumulator's truncation): max |err| 2e-5 .. 7.5e-5 against the float64 oracle on
 // tones over a noise floor, where torch.stft in f32 sits at 6e-5 .. 8e-5; the gate is 1e-4.
 //
-// One persistent CTA per SM, 17 warps coupled only by mbarriers:
-//   warps 8-15   loaders (idle while a tile is converted): fetch the NEXT tile's 20 720 raw samples (128 hops + 240) as 2 590
-//                16-byte chunks into registers while the current tile is converted, and drop them into shared memory the
-//                moment the converters release it: 130 padded rows of one hop (pitch 336 B: conflict-free 16-byte reads by
-//                thread = frame).  In the pipeline the chunks are gathered through the kept-range table (fused stream
-//                compaction) and the tile's own chunks go straight back out as the trimmed PCM; chunks that touch the clip's
-//                edges (reflect pad, zero pad, a zero-filled last millisecond) are assembled sample by sample.
-//                (A first version staged the rows with one 1-D bulk copy each: 130 small TMA requests per tile took 8 us,
-//                profiles/r02_logmel_tc.md.)
-//   warps 0-7    converters, thread = frame: role 0 / 1 = lower / upper 8 of a k-step's 16 n-values; LDS.128 of the four
-//                segments x[n], x[n+200], x[200-n], x[400-n], window + folds in f32, split into f16 planes, tcgen05.st into a
-//                ring of four 16-column operand slots in TMEM (slot = product), one full / free mbarrier pair per slot.
+// One persistent CTA per SM, coupled only by mbarriers:
+//   warps 0-15   workers, all alike: lane quadrant q = warp % 4 (thread = frame 32 q + lane of the tile), part r = warp / 4.
+//                 fetch    the NEXT tile's 20 720 raw samples (128 hops + 240) are 2 590 16-byte chunks, five or six per thread,
+//                          loaded into registers before the current tile is converted (gathered through the kept-range table
+//                          in the pipeline = fused stream compaction; chunks that touch the clip's edges - reflect pad, zero
+//                          pad, a zero-filled last millisecond - are assembled sample by sample) and dropped into shared
+//                          memory once every worker is done with the current tile: 130 padded rows of one hop (pitch 328 B:
+//                          conflict-free 8-byte reads by thread = frame).  The tile's own chunks also go out as the trimmed PCM.
+//                          (A first version staged the rows with one 1-D bulk copy each: 130 small TMA requests per tile took
+//                          8 us; a second one used eight dedicated loader warps and left eight converters: profiles/r02_logmel_tc.md.)
+//                 convert  part r = n-values 16 s + 4 r .. + 3 of k-step s: LDS.64 of the four segments x[n], x[n+200], x[200-n],
+//                          x[400-n], window + folds in f32, split into f16 planes, tcgen05.st into a ring of four 16-column
+//                          operand slots in TMEM (slot = product), one full / free mbarrier pair per slot.  k-steps run from
+//                          n = 96 down to 0 and only three plane products are accumulated (hi hi, hi lo, lo hi): with operands
+//                          split as floats the lo lo term is below f32 rounding, and every accumulation less is one truncation
+//                          of the tensor core's f32 accumulator less (tools/studies/logmel_tc_windowed.py: 8.1e-5 -> 5.2e-5 on
+//                          the worst probed signal).
+//                 epilogue part r = mel range r (mel_tc_tables_gen.inc): tcgen05.ld 16 bins of each accumulator at a time, power,
+//                          slaney weights as FFMA immediates, log10, coalesced stores along T, running clip maximum and
+//                          per-32-frame minimum for the floor pass (mel_floor_kernel).
 //   warp 16      MMA issuer (elected lane) + TMEM allocation; tcgen05.commit releases operand slots and hands the tile's
 //                accumulators (4 x 112 columns) to the epilogue.
-//   warps 0-15   epilogue, thread = frame, four roles per lane quadrant = four mel ranges (mel_tc_tables_gen.inc): tcgen05.ld
-//                16 bins of each accumulator at a time, power, slaney weights as FFMA immediates, log10, coalesced stores
-//                along T, running clip maximum and per-32-frame minimum for the floor pass (mel_floor_kernel).
-// TMEM: accumulators [0, 448), operand ring [448, 512).  Shared memory: basis 171 KB + window 2 KB + raw tile 43 KB.
+//   warp 17      scout (pipeline only): looks up the kept ranges under the next tile (32-ary search in the offset table) and
+//                publishes a window of 32 of them in shared memory, two tiles ahead of the converters.
+// TMEM: accumulators [0, 448), operand ring [448, 512).  Shared memory: basis 171 KB + window 2 KB + raw tile 42 KB.
 #pragma once
 #include <utility>
 
@@ -53,27 +60,29 @@ constexpr int kTcBankBytes = 2 * kTcNP * kTcPlaneBytes + kTcLbo + 128;   // + ze
 constexpr int kTcWinFloats = 4 * 112;                // window tables: x[n], x[n+200], x[200-n], x[400-n], n = 0..111
 constexpr int kTcBlobBytes = kTcBankBytes + kTcWinFloats * 4;
 constexpr int kTcRows = kTcFrames + 2;               // hops staged per tile
-constexpr int kTcRowBytes = 336;                     // 160 samples + 8 of padding
+constexpr int kTcRowBytes = 328;                     // 160 samples + 4 of padding: 82 words, conflict-free 8-byte reads by thread = frame
 constexpr int kTcRawBytes = kTcRows * kTcRowBytes;
 constexpr int kTcLastRowSamples = 88;                // samples of row 129 a tile needs (x[400] of its last frame is sample 80)
-constexpr int kTcSegWin = 32;                        // kept ranges cached per tile by every gathering loader warp
-constexpr int kTcWorkers = 16, kTcIssuer = 16;
-constexpr int kTcThreads = 17 * 32;
-constexpr int kTcLoaders = 8 * 32;                   // loader threads (warps 8-15)
+constexpr int kTcSegWin = 32;                        // kept ranges cached per tile (gather)
+constexpr int kTcWorkers = 16, kTcIssuer = 16, kTcScout = 17;
+constexpr int kTcThreads = 18 * 32;
+constexpr int kTcWorkerThreads = kTcWorkers * 32;
 constexpr int kTcChunks = (kTcFrames * kHop + 240) / 8;           // 16-byte chunks of a raw tile (2 590)
-constexpr int kTcChunkRounds = (kTcChunks + kTcLoaders - 1) / kTcLoaders;   // 11
+constexpr int kTcChunkRounds = (kTcChunks + kTcWorkerThreads - 1) / kTcWorkerThreads;   // 6
 constexpr int kTcRingCol = kTcNP * kTcNB;            // 448
 constexpr unsigned kTcIdesc = (1u << 4) | ((unsigned)(kTcNB >> 3) << 17) | ((unsigned)(kTcFrames >> 4) << 24);
 // barriers
-constexpr int kTcBarFull = 0, kTcBarFree = 4, kTcBarAccFull = 8, kTcBarAccFree = 9, kTcBarRawFull = 10, kTcBarRawFree = 11, kTcBarBank = 12, kTcNBars = 13;
+constexpr int kTcBarFull = 0, kTcBarFree = 4, kTcBarAccFull = 8, kTcBarAccFree = 9, kTcBarRawFull = 10, kTcBarRawFree = 11, kTcBarBank = 12,
+              kTcBarWinFull = 13, kTcBarWinFree = 15, kTcNBars = 17;
 constexpr int kTcSmemBank = 0;
 constexpr int kTcSmemWin = kTcBankBytes;
 constexpr int kTcSmemRaw = kTcBlobBytes;
 constexpr int kTcSmemBars = kTcSmemRaw + kTcRawBytes + 32;
-constexpr int kTcSmemSeg = kTcSmemBars + kTcNBars * kFmBarBytes;       // [33] kept_off window, [32] source sample of each range
-constexpr int kTcSmemMisc = kTcSmemSeg + 8 * (2 * kTcSegWin + 1) * 8;     // one window per loader warp
+constexpr int kTcSmemSeg = kTcSmemBars + kTcNBars * kFmBarBytes;       // 2 x { i64 src[32]; int off[33] (relative to the tile's first raw sample); int pad }
+constexpr int kTcSegBytes = kTcSegWin * 8 + (kTcSegWin + 1) * 4 + 4;
+constexpr int kTcSmemMisc = kTcSmemSeg + 2 * kTcSegBytes;
 constexpr int kTcSmemBytes = kTcSmemMisc + 64;
-static_assert(kTcBankBytes % 16 == 0 && kTcSmemRaw % 16 == 0 && kTcSmemBars % 8 == 0 && kTcSmemSeg % 8 == 0, "alignment");
+static_assert(kTcBankBytes % 16 == 0 && kTcSmemRaw % 16 == 0 && kTcSmemBars % 8 == 0 && kTcSmemSeg % 8 == 0 && kTcSegBytes % 8 == 0, "alignment");
 static_assert(kTcSmemBytes <= 232448, "shared-memory budget (227 KB per CTA)");
 
 #ifndef B2A_MEL_TC_TABLES_INCLUDED
@@ -145,6 +154,21 @@ __device__ __forceinline__ void bulk_store(void* dst, saddr_t src, unsigned byte
 __device__ __forceinline__ void bulk_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ uint2 lds64(saddr_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts64(saddr_t a, unsigned x, unsigned y) { asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(x), "r"(y) : "memory"); }
+__device__ __forceinline__ void tmem_st2(unsigned taddr, unsigned r0, unsigned r1) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(r0), "r"(r1) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ uint4 ldg_nc16(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void sts_u16(saddr_t a, unsigned v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
 __device__ __forceinline__ void sts_zero16(saddr_t a) { asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(a), "r"(0u) : "memory"); }
 __device__ __forceinline__ void mbar_expect_tx_only(saddr_t bar, unsigned bytes) {
@@ -164,6 +188,15 @@ static inline void bulk_store(void* dst, saddr_t src, unsigned bytes) { memcpy(d
 static inline void bulk_store_commit() {}
 static inline void bulk_store_wait_read() {}
 static inline void bulk_store_wait_all() {}
+static inline uint2 lds64(saddr_t a) { return *(const uint2*)a; }
+static inline void sts64(saddr_t a, unsigned x, unsigned y) { ((unsigned*)a)[0] = x; ((unsigned*)a)[1] = y; }
+static inline void tmem_st2(unsigned taddr, unsigned r0, unsigned r1) {
+    const int lane0 = (int)(taddr >> 16), col0 = (int)(taddr & 0xffffu);
+    g_emu_tmem[lane0 + emu_lane()][col0] = __uint_as_float(r0);
+    g_emu_tmem[lane0 + emu_lane()][col0 + 1] = __uint_as_float(r1);
+}
+static inline void prefetch_l2(const void*) {}
+static inline uint4 ldg_nc16(const void* p) { return *(const uint4*)p; }
 static inline void sts_u16(saddr_t a, unsigned v) { *(unsigned short*)a = (unsigned short)v; }
 static inline void sts_zero16(saddr_t a) { memset((void*)a, 0, 16); }
 static inline void mbar_expect_tx_only(saddr_t bar, unsigned bytes) { unsigned* b = (unsigned*)bar; b[3] += bytes; }
@@ -225,6 +258,30 @@ __device__ __forceinline__ void tc_epi_role(TcEpi& e, unsigned tacc) {
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------------------------
+// one 16-byte chunk that touches an edge of the padded clip (reflect at both ends, zeros past n_act, zero-filled last millisecond):
+// assembled sample by sample; out of line, it runs for a handful of chunks per clip
+template <bool GATHER>
+__device__ __noinline__ uint4 tc_edge_chunk(const LogMelTcParams& p, const int16_t* row, i64 qc, i64 n_act, i64 ltot, int n_seg) {
+    unsigned w[4] = {0u, 0u, 0u, 0u};
+    for (int j = 0; j < 8; j++) {
+        i64 qq = qc + j;
+        if (qq < 0) qq = -qq;
+        if (qq >= ltot) qq = 2 * (ltot - 1) - qq;
+        int sv = 0;
+        if (qq >= 0 && qq < n_act) {
+            if (!GATHER) sv = row[qq];
+            else if (n_seg > 0) {
+                int lo = 0, hi = n_seg - 1;                       // largest k with kept_off[k] <= qq
+                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (p.kept_off[mid] <= qq) lo = mid; else hi = mid - 1; }
+                const i64 si = (i64)p.kept_ms[2 * lo] * 16 + (qq - p.kept_off[lo]);
+                if (si < p.n_src) sv = p.audio[si];
+            }
+        }
+        w[j >> 1] |= ((unsigned)sv & 0xffffu) << (16 * (j & 1));
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 template <int NM, bool GATHER>
 __global__ void __launch_bounds__(kTcThreads, 1) logmel_tc_kernel(const LogMelTcParams p) {
     B2A_DYN_SMEM(smem);
@@ -243,14 +300,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) logmel_tc_kernel(const LogMelTc
     if (GATHER && tiles * (kTcFrames * kHop) < n_act) tiles++;        // a last partial hop still has trimmed samples to write
     const i64 n_work = tiles * p.batch;
     if (blockIdx.x == 0 && tid == 0 && p.d_frames_out) *p.d_frames_out = T;
+    const int n_seg = GATHER ? (int)p.info[B2A_INFO_N_KEPT] : 0;
 
     if (tid == 0) {
-        for (int i = 0; i < kTcNP; i++) { mbar_init(BAR(kTcBarFull + i), 8); mbar_init(BAR(kTcBarFree + i), 1); }
+        for (int i = 0; i < kTcNP; i++) { mbar_init(BAR(kTcBarFull + i), kTcWorkers); mbar_init(BAR(kTcBarFree + i), 1); }
         mbar_init(BAR(kTcBarAccFull), 1);
         mbar_init(BAR(kTcBarAccFree), kTcWorkers);
-        mbar_init(BAR(kTcBarRawFull), 8);
-        mbar_init(BAR(kTcBarRawFree), 8);
+        mbar_init(BAR(kTcBarRawFull), kTcWorkers);
+        mbar_init(BAR(kTcBarRawFree), kTcWorkers);
         mbar_init(BAR(kTcBarBank), 1);
+        for (int i = 0; i < 2; i++) { mbar_init(BAR(kTcBarWinFull + i), 1); mbar_init(BAR(kTcBarWinFree + i), kTcWorkers); }
         mbar_fence_init();
     }
     if (warp == kTcIssuer) tmem_alloc(smem_addr(tmem_slot), 512);
@@ -265,6 +324,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) logmel_tc_kernel(const LogMelTc
         else { b = (int)(work / tiles); tile = work - (i64)b * tiles; }
     };
 
+    // registers: the launch gives every thread 96 (18 warps: five on two of the four sub-partitions); the issuer / scout
+    // warpgroup hands most of its share back and the workers take 112 (4 x 32 x 112 + 32 x 40 <= 16 384 per sub-partition)
+    // (setmaxnreg rebalancing was tried: ptxas spilled more with it than without, see profiles/r02_logmel_tc.md)
     if (warp == kTcIssuer) {
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
@@ -282,7 +344,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) logmel_tc_kernel(const LogMelTc
         for (i64 work = blockIdx.x; work < n_work; work += gridDim.x, it++) {
             if (it > 0) { mbar_wait(BAR(kTcBarAccFree), (it - 1) & 1u); tc_fence_after(); }
 #pragma unroll 1
-            for (int s = 0; s < kTcKS; s++, g++) {
+            for (int s = kTcKS - 1; s >= 0; s--, g++) {                // n = 96 .. 111 first (see the header: accumulation order)
 #pragma unroll
                 for (int pr = 0; pr < kTcNP; pr++) {
                     mbar_wait(BAR(kTcBarFull + pr), g & 1u);
@@ -291,197 +353,176 @@ __global__ void __launch_bounds__(kTcThreads, 1) logmel_tc_kernel(const LogMelTc
                     const unsigned ah = tbase + (unsigned)(kTcRingCol + 16 * pr), al = ah + 8u;
                     const unsigned bh = b_lo0 + (unsigned)(((2 * pr) * kTcPlaneBytes + 2 * s * kTcLbo) >> 4);
                     const unsigned bl = b_lo0 + (unsigned)(((2 * pr + 1) * kTcPlaneBytes + 2 * s * kTcLbo) >> 4);
-                    umma_ts_warp(d, ah, bh, b_hi, kTcIdesc, s > 0 ? 1u : 0u);
+                    umma_ts_warp(d, ah, bh, b_hi, kTcIdesc, s < kTcKS - 1 ? 1u : 0u);
                     umma_ts_warp(d, ah, bl, b_hi, kTcIdesc, 1u);
                     umma_ts_warp(d, al, bh, b_hi, kTcIdesc, 1u);
-                    umma_ts_warp(d, al, bl, b_hi, kTcIdesc, 1u);
                     umma_commit_warp(BAR(kTcBarFree + pr));
                 }
             }
             umma_commit_warp(BAR(kTcBarAccFull));
         }
-    } else {
-        // ---------------- workers: converters (roles 0, 1), loaders (roles 2, 3), epilogue (all four roles) ----------------
-        const int q = warp & 3, role = warp >> 2;
-        const int f = 32 * q + lane;                                    // frame (row) of the tile
-        const unsigned tlane = tbase + ((unsigned)(32 * q) << 16);
-        const saddr_t rowp = s_base + kTcSmemRaw + (unsigned)(f * kTcRowBytes);
-        const saddr_t winp = s_base + kTcSmemWin;
-        float run_max = -3.0e38f;
-        unsigned g = 0, it = 0;
-        if (role < 2) mbar_wait(BAR(kTcBarBank), 0);                    // window tables
-
-        // ---- loader state (roles 2, 3): the next tile's chunks travel global -> registers -> shared memory ----
-        const int lt = (warp - 8) * 32 + lane;                          // loader thread 0..255
-        i64* s_off = (i64*)(smem + kTcSmemSeg) + (warp >= 8 ? warp - 8 : 0) * (2 * kTcSegWin + 1);   // this warp's kept_off[sg0 .. sg0 + 32]
-        i64* s_src = s_off + kTcSegWin + 1;                              // 16 * kept_ms[2 (sg0 + l)]
-        const int n_seg = GATHER ? (int)p.info[B2A_INFO_N_KEPT] : 0;
-        uint4 pre[kTcChunkRounds];
-        auto seg_of_global = [&](i64 qq) -> int {                        // largest k with kept_off[k] <= qq (n_seg > 0), per lane
-            int lo = 0, hi = n_seg - 1;
-            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (p.kept_off[mid] <= qq) lo = mid; else hi = mid - 1; }
-            return lo;
-        };
-        // source sample of trimmed index qq (0 <= qq < n_act); -1: zero (pydub zero-fills a rounded-up last millisecond)
-        auto src_index = [&](i64 qq) -> i64 {
-            if (!GATHER) return qq;
-            if (n_seg <= 0) return -1;
-            const int sg = seg_of_global(qq);
-            const i64 si = (i64)p.kept_ms[2 * sg] * 16 + (qq - p.kept_off[sg]);
-            return si < p.n_src ? si : -1;
-        };
-        auto fetch_tile = [&](i64 work_n) {
-            int bn;
-            i64 tile_n;
-            split_work(work_n, bn, tile_n);
-            const int16_t* row = p.audio + (size_t)bn * (size_t)p.row_stride;
-            const i64 q0 = tile_n * (kTcFrames * kHop) - 200;            // padded-domain index of raw sample 0
-            if (GATHER && n_seg > 0) {
-                // kept range under the tile's first sample: 32-ary search (three rounds of parallel probes for 8 192 ranges),
-                // then the window of the next 32 ranges into this warp's shared-memory slots
+    } else if (warp == kTcScout) {
+        // ---------------- scout: kept ranges under the tiles this CTA will fetch, two fetches ahead ----------------
+        if (GATHER && n_seg > 0) {
+            unsigned j = 0;
+            for (i64 work = blockIdx.x; work < n_work; work += gridDim.x, j++) {
+                int b;
+                i64 tile;
+                split_work(work, b, tile);
+                const i64 q0 = tile * (kTcFrames * kHop) - 200;
                 const i64 qq = q0 > 0 ? q0 : 0;
-                int lo = 0, cnt = n_seg;                                   // the answer lies in [lo, lo + cnt); kept_off[lo] <= qq
-                while (cnt > 1) {
+                int lo = 0, cnt = n_seg;                               // the range holding qq lies in [lo, lo + cnt); kept_off[lo] <= qq
+                while (cnt > 1) {                                      // 32-ary search: three rounds of parallel probes for 8 192 ranges
                     const int stride = (cnt + 31) / 32;
                     const int idx = lo + lane * stride;
                     const bool le = idx < lo + cnt && p.kept_off[idx] <= qq;
-                    const int c = __popc(__ballot_sync(0xffffffffu, le));   // probes are monotone; lane 0 always holds
+                    const int c = __popc(__ballot_sync(0xffffffffu, le));
                     const int nlo = lo + (c - 1) * stride;
                     cnt = nlo + stride > lo + cnt ? lo + cnt - nlo : stride;
                     lo = nlo;
                 }
                 const int k = lo + lane;
+                const i64 off = k <= n_seg ? p.kept_off[k] - q0 : (i64)0x7fffffff;
+                const i64 off32 = lo + kTcSegWin <= n_seg ? p.kept_off[lo + kTcSegWin] - q0 : (i64)0x7fffffff;
+                const i64 src = k < n_seg ? (i64)p.kept_ms[2 * k] * 16 : 0;
+                const unsigned buf = j & 1u, use = j >> 1;
+                if (use > 0) mbar_wait(BAR(kTcBarWinFree + buf), (use - 1) & 1u);
+                i64* w_src = (i64*)(smem + kTcSmemSeg + buf * kTcSegBytes);
+                int* w_off = (int*)(w_src + kTcSegWin);
+                w_src[lane] = src;
+                w_off[lane] = off > 0x7fffffff ? 0x7fffffff : (int)off;
+                if (lane == 0) w_off[kTcSegWin] = off32 > 0x7fffffff ? 0x7fffffff : (int)off32;
                 __syncwarp();
-                s_off[lane] = k <= n_seg ? p.kept_off[k] : ((i64)1 << 62);
-                s_src[lane] = k < n_seg ? (i64)p.kept_ms[2 * k] * 16 : 0;
-                if (lane == 0) s_off[kTcSegWin] = lo + kTcSegWin <= n_seg ? p.kept_off[lo + kTcSegWin] : ((i64)1 << 62);
-                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(kTcBarWinFull + buf));
             }
-#pragma unroll
-            for (int r = 0; r < kTcChunkRounds; r++) {
-                const int c = lt + kTcLoaders * r;
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (c < kTcChunks) {
-                    const i64 qc = q0 + 8 * (i64)c;
-                    const int16_t* src = nullptr;
-                    if (qc >= 0 && qc + 8 <= n_act) {
-                        if (!GATHER) src = row + qc;
-                        else if (n_seg > 0) {
-                            if (qc < s_off[kTcSegWin]) {
-                                int e = 0;                               // largest e with s_off[e] <= qc
-#pragma unroll
-                                for (int st = 16; st > 0; st >>= 1) if (s_off[e + st] <= qc) e += st;
-                                src = p.audio + s_src[e] + (qc - s_off[e]);
-                            } else {
-                                const int sg = seg_of_global(qc);
-                                src = p.audio + (i64)p.kept_ms[2 * sg] * 16 + (qc - p.kept_off[sg]);
-                            }
-                            if (src + 8 > p.audio + p.n_src) src = nullptr;   // zero-filled last millisecond: sample by sample
-                        }
-                        if ((((uintptr_t)src) & 15) != 0) src = nullptr;
-                    }
-                    if (src) {
-                        v = *(const uint4*)src;
-                    } else if (!(qc >= n_act && qc + 8 <= ltot) && qc < ltot + 200) {
-                        // edge chunk: reflect at both ends of the padded clip, zeros past n_act
-                        unsigned w[4] = {0u, 0u, 0u, 0u};
-                        for (int j = 0; j < 8; j++) {
-                            i64 qq = qc + j;
-                            if (qq < 0) qq = -qq;
-                            if (qq >= ltot) qq = 2 * (ltot - 1) - qq;
-                            int sv = 0;
-                            if (qq >= 0 && qq < n_act) { const i64 si = src_index(qq); if (si >= 0) sv = (GATHER ? p.audio : row)[si]; }
-                            w[j >> 1] |= ((unsigned)sv & 0xffffu) << (16 * (j & 1));
-                        }
-                        v = make_uint4(w[0], w[1], w[2], w[3]);
-                    }
-                    // the tile's own 20 480 trimmed samples (raw samples 200 .. 20 679) are the trimmed PCM
-                    if (GATHER && c >= 25 && c < 25 + kTcFrames * kHop / 8 && qc + 8 <= n_act) *(uint4*)(p.trim_out + qc) = v;
-                }
-                pre[r] = v;
-            }
-        };
-        auto store_tile = [&]() {
-#pragma unroll
-            for (int r = 0; r < kTcChunkRounds; r++) {
-                const int c = lt + kTcLoaders * r;
-                if (c < kTcChunks) *(uint4*)(smem + kTcSmemRaw + (c / 20) * kTcRowBytes + (c % 20) * 16) = pre[r];
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(kTcBarRawFull));
-        };
-        if (role >= 2 && (i64)blockIdx.x < n_work) { fetch_tile(blockIdx.x); store_tile(); }
+        }
+    } else {
+        // ---------------- workers ----------------
+        const int q = warp & 3, part = warp >> 2;
+        const int f = 32 * q + lane;                                    // frame (row) of the tile
+        const int wt = warp * 32 + lane;                                // worker thread 0..511
+        const unsigned tlane = tbase + ((unsigned)(32 * q) << 16);
+        const saddr_t rowp = s_base + kTcSmemRaw + (unsigned)(f * kTcRowBytes);
+        const saddr_t winp = s_base + kTcSmemWin;
+        float run_max = -3.0e38f;
+        unsigned g = 0, it = 0, nfetch = 0;
+        mbar_wait(BAR(kTcBarBank), 0);                                  // window tables
+        // what the fetch of the next tile leaves behind for the store: per chunk the source (in units of 8 samples from
+        // p.audio; the line is already on its way into L2) or a mark that it is an edge chunk
+        unsigned pre_off[kTcChunkRounds];
+        unsigned src_mask = 0, edge_mask = 0, own_mask = 0;              // per round: has a global source / edge chunk / also trimmed PCM (gather); neither source nor edge = zeros
+        i64 pre_q0 = 0;
+        const int16_t* pre_row = p.audio;
 
-        for (i64 work = blockIdx.x; work < n_work; work += gridDim.x, it++) {
-            int b;
-            i64 tile;
-            split_work(work, b, tile);
-            if (role >= 2) {
-                // next tile: loads in flight while this one is converted, into shared memory once the converters are done with it
-                if (work + gridDim.x < n_work) {
-                    fetch_tile(work + gridDim.x);
-                    mbar_wait(BAR(kTcBarRawFree), it & 1u);
-                    store_tile();
+        // iteration -1 only primes the pipeline (fetch + store of the CTA's first tile)
+#pragma unroll 1
+        for (i64 work = (i64)blockIdx.x - (i64)gridDim.x; work < n_work; work += gridDim.x) {
+            const bool live = work >= (i64)blockIdx.x;
+            const i64 next = work + gridDim.x;
+            const bool have_next = next < n_work;
+            int b = 0;
+            i64 tile = 0;
+            if (live) split_work(work, b, tile);
+
+            // ---- fetch: where the next tile's chunks come from; their lines start moving into L2 while this tile is converted ----
+            if (have_next) {
+                int bn;
+                i64 tile_n;
+                split_work(next, bn, tile_n);
+                pre_row = p.audio + (size_t)bn * (size_t)p.row_stride;
+                const i64 q0 = tile_n * (kTcFrames * kHop) - 200;        // padded-domain index of raw sample 0
+                pre_q0 = q0;
+                src_mask = edge_mask = own_mask = 0;
+                const unsigned buf = nfetch & 1u;
+                const i64* w_src = (const i64*)(smem + kTcSmemSeg + buf * kTcSegBytes);
+                const int* w_off = (const int*)(w_src + kTcSegWin);
+                if (GATHER && n_seg > 0) mbar_wait(BAR(kTcBarWinFull + buf), (nfetch >> 1) & 1u);
+#pragma unroll
+                for (int r = 0; r < kTcChunkRounds; r++) {
+                    const int c = wt + kTcWorkerThreads * r;
+                    pre_off[r] = 0u;
+                    if (c < kTcChunks) {
+                        const int qr = 8 * c;
+                        const i64 qc = q0 + qr;
+                        const int16_t* src = nullptr;
+                        if (qc >= 0 && qc + 8 <= n_act) {
+                            if (!GATHER) src = pre_row + qc;
+                            else if (n_seg > 0 && qr < w_off[kTcSegWin]) {
+                                int e = 0;                               // largest e with w_off[e] <= qr
+#pragma unroll
+                                for (int st = 16; st > 0; st >>= 1) if (w_off[e + st] <= qr) e += st;
+                                const i64 si = w_src[e] + (qr - w_off[e]);
+                                if (si + 8 <= p.n_src) src = p.audio + si;
+                            }
+                            if ((((uintptr_t)src) & 15) != 0 || ((src - p.audio) & 7) != 0) src = nullptr;
+                            if (GATHER && c >= 25 && c < 25 + kTcFrames * kHop / 8) own_mask |= 1u << r;
+                        }
+                        if (src) {
+                            prefetch_l2(src);
+                            pre_off[r] = (unsigned)((src - p.audio) >> 3);
+                            src_mask |= 1u << r;
+                        } else if (!(qc >= n_act && qc + 8 <= ltot) && qc < ltot + 200) {
+                            edge_mask |= 1u << r;                        // (else: zeros - right padding, or behind the last frame's window)
+                        }
+                    }
                 }
-            } else {
+                if (GATHER && n_seg > 0) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(BAR(kTcBarWinFree + buf));
+                }
+                nfetch++;
+            }
+
+            // ---- convert this tile ----
+            if (live) {
                 mbar_wait(BAR(kTcBarRawFull), it & 1u);
 #pragma unroll 1
-                for (int s = 0; s < kTcKS; s++, g++) {
-                    const int n0 = 16 * s + 8 * role;
-                    const int a1 = 192 - n0, b1 = 200 - n0, a2 = 392 - n0, b2 = 400 - n0;
-                    const uint4 f1 = lds128(rowp + (unsigned)(2 * n0));
-                    const uint4 f2 = lds128(rowp + (unsigned)(kTcRowBytes + 80 + 2 * n0));
-                    const uint4 r1 = lds128(rowp + (unsigned)(a1 >= 160 ? kTcRowBytes + 2 * (a1 - 160) : 2 * a1));
+                for (int s = kTcKS - 1; s >= 0; s--, g++) {
+                    const int n0 = 16 * s + 4 * part;
+                    const int a1 = 196 - n0, b1 = 200 - n0, a2 = 396 - n0, b2 = 400 - n0;
+                    const uint2 f1 = lds64(rowp + (unsigned)(2 * n0));
+                    const uint2 f2 = lds64(rowp + (unsigned)(kTcRowBytes + 80 + 2 * n0));
+                    const uint2 r1 = lds64(rowp + (unsigned)(a1 >= 160 ? kTcRowBytes + 2 * (a1 - 160) : 2 * a1));
                     const unsigned r1x = lds_u16(rowp + (unsigned)(b1 >= 160 ? kTcRowBytes + 2 * (b1 - 160) : 2 * b1));
-                    const uint4 r2 = lds128(rowp + (unsigned)(a2 >= 320 ? 2 * kTcRowBytes + 2 * (a2 - 320) : kTcRowBytes + 2 * (a2 - 160)));
+                    const uint2 r2 = lds64(rowp + (unsigned)(a2 >= 320 ? 2 * kTcRowBytes + 2 * (a2 - 320) : kTcRowBytes + 2 * (a2 - 160)));
                     const unsigned r2x = lds_u16(rowp + (unsigned)(b2 >= 320 ? 2 * kTcRowBytes + 2 * (b2 - 320) : kTcRowBytes + 2 * (b2 - 160)));
-                    if (s == kTcKS - 1) {                                // last read of the raw tile by this warp
+                    const float4 w1 = lds_f4(winp + (unsigned)(4 * (0 * 112 + n0)));
+                    const float4 w2 = lds_f4(winp + (unsigned)(4 * (1 * 112 + n0)));
+                    const float4 w3 = lds_f4(winp + (unsigned)(4 * (2 * 112 + n0)));
+                    const float4 w4 = lds_f4(winp + (unsigned)(4 * (3 * 112 + n0)));
+                    if (s == 0) {                                        // last read of the raw tile by this warp
                         __syncwarp();
                         if (lane == 0) mbar_arrive(BAR(kTcBarRawFree));
                     }
-                    const unsigned fw1[4] = {f1.x, f1.y, f1.z, f1.w}, fw2[4] = {f2.x, f2.y, f2.z, f2.w};
-                    const unsigned rw1[4] = {r1.x, r1.y, r1.z, r1.w}, rw2[4] = {r2.x, r2.y, r2.z, r2.w};
-                    auto s16_at = [](const unsigned (&w)[4], int i) -> float {           // sample i of an 8-sample quad
-                        const unsigned v = w[i >> 1];
-                        return (i & 1) ? (float)((int)v >> 16) : (float)(short)(v & 0xffffu);
-                    };
-                    unsigned hw[kTcNP][4], lw[kTcNP][4];
+                    auto lo16 = [](unsigned v) -> float { return (float)(short)(v & 0xffffu); };
+                    auto hi16 = [](unsigned v) -> float { return (float)((int)v >> 16); };
+                    const float x1[4] = {lo16(f1.x), hi16(f1.x), lo16(f1.y), hi16(f1.y)};
+                    const float x2[4] = {lo16(f2.x), hi16(f2.x), lo16(f2.y), hi16(f2.y)};
+                    const float y1[4] = {(float)(short)r1x, hi16(r1.y), lo16(r1.y), hi16(r1.x)};     // x[200 - n0 - i]
+                    const float y2[4] = {(float)(short)r2x, hi16(r2.y), lo16(r2.y), hi16(r2.x)};     // x[400 - n0 - i]
+                    const float wa[4] = {w1.x, w1.y, w1.z, w1.w}, wb[4] = {w2.x, w2.y, w2.z, w2.w};
+                    const float wc[4] = {w3.x, w3.y, w3.z, w3.w}, wd[4] = {w4.x, w4.y, w4.z, w4.w};
+                    float v[kTcNP][4];
 #pragma unroll
-                    for (int h = 0; h < 2; h++) {                                         // two halves of four n-values
-                        const float4 w1 = lds_f4(winp + (unsigned)(4 * (0 * 112 + n0 + 4 * h)));
-                        const float4 w2 = lds_f4(winp + (unsigned)(4 * (1 * 112 + n0 + 4 * h)));
-                        const float4 w3 = lds_f4(winp + (unsigned)(4 * (2 * 112 + n0 + 4 * h)));
-                        const float4 w4 = lds_f4(winp + (unsigned)(4 * (3 * 112 + n0 + 4 * h)));
-                        const float wa[4] = {w1.x, w1.y, w1.z, w1.w}, wb[4] = {w2.x, w2.y, w2.z, w2.w};
-                        const float wc[4] = {w3.x, w3.y, w3.z, w3.w}, wd[4] = {w4.x, w4.y, w4.z, w4.w};
-                        float v[kTcNP][4];
-#pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            const int i = 4 * h + e;
-                            const float x1 = s16_at(fw1, i), x2 = s16_at(fw2, i);
-                            const float y1 = i == 0 ? (float)(short)r1x : s16_at(rw1, 8 - i);
-                            const float y2 = i == 0 ? (float)(short)r2x : s16_at(rw2, 8 - i);
-                            const float t1 = wa[e] * x1, u1 = wc[e] * y1;
-                            const float ge = fmaf(wb[e], x2, t1), go = fmaf(-wb[e], x2, t1);
-                            const float he = fmaf(wd[e], y2, u1), ho = fmaf(-wd[e], y2, u1);
-                            v[0][e] = ge + he; v[1][e] = ge - he; v[2][e] = go - ho; v[3][e] = go + ho;
-                        }
-#pragma unroll
-                        for (int pr = 0; pr < kTcNP; pr++)
-#pragma unroll
-                            for (int c = 0; c < 2; c++) {
-                                const unsigned hi = pack_f16x2(v[pr][2 * c], v[pr][2 * c + 1]);
-                                const float2 hf = unpack_f16x2(hi);
-                                hw[pr][2 * h + c] = hi;
-                                lw[pr][2 * h + c] = pack_f16x2(v[pr][2 * c] - hf.x, v[pr][2 * c + 1] - hf.y);
-                            }
+                    for (int e = 0; e < 4; e++) {
+                        const float t1 = wa[e] * x1[e], u1 = wc[e] * y1[e];
+                        const float ge = fmaf(wb[e], x2[e], t1), go = fmaf(-wb[e], x2[e], t1);
+                        const float he = fmaf(wd[e], y2[e], u1), ho = fmaf(-wd[e], y2[e], u1);
+                        v[0][e] = ge + he; v[1][e] = ge - he; v[2][e] = go - ho; v[3][e] = go + ho;
                     }
 #pragma unroll
                     for (int pr = 0; pr < kTcNP; pr++) {
+                        unsigned hw[2], lw[2];
+#pragma unroll
+                        for (int c = 0; c < 2; c++) {
+                            hw[c] = pack_f16x2(v[pr][2 * c], v[pr][2 * c + 1]);
+                            const float2 hf = unpack_f16x2(hw[c]);
+                            lw[c] = pack_f16x2(v[pr][2 * c] - hf.x, v[pr][2 * c + 1] - hf.y);
+                        }
                         if (g > 0) { mbar_wait(BAR(kTcBarFree + pr), (g - 1) & 1u); tc_fence_after(); }
-                        const unsigned ts = tlane + (unsigned)(kTcRingCol + 16 * pr + 4 * role);
-                        tmem_st4(ts, hw[pr][0], hw[pr][1], hw[pr][2], hw[pr][3]);
-                        tmem_st4(ts + 8u, lw[pr][0], lw[pr][1], lw[pr][2], lw[pr][3]);
+                        const unsigned ts = tlane + (unsigned)(kTcRingCol + 16 * pr + 2 * part);
+                        tmem_st2(ts, hw[0], hw[1]);
+                        tmem_st2(ts + 8u, lw[0], lw[1]);
                         tmem_st_wait();
                         tc_fence_before();
                         __syncwarp();
@@ -489,31 +530,60 @@ __global__ void __launch_bounds__(kTcThreads, 1) logmel_tc_kernel(const LogMelTc
                     }
                 }
             }
+
+            // ---- store: the next tile's chunks (L2 hits by now) into shared memory once every worker is done with this tile ----
+            if (have_next) {
+                uint4 v[kTcChunkRounds];
+#pragma unroll
+                for (int r = 0; r < kTcChunkRounds; r++) {
+                    const int c = wt + kTcWorkerThreads * r;
+                    v[r] = make_uint4(0u, 0u, 0u, 0u);
+                    if ((src_mask >> r) & 1u) v[r] = ldg_nc16(p.audio + ((size_t)pre_off[r] << 3));
+                    else if ((edge_mask >> r) & 1u) v[r] = tc_edge_chunk<GATHER>(p, pre_row, pre_q0 + 8 * c, n_act, ltot, n_seg);
+                }
+                if (live) mbar_wait(BAR(kTcBarRawFree), it & 1u);
+#pragma unroll
+                for (int r = 0; r < kTcChunkRounds; r++) {
+                    const int c = wt + kTcWorkerThreads * r;
+                    if (c < kTcChunks) {
+                        const saddr_t dst = s_base + kTcSmemRaw + (unsigned)((c / 20) * kTcRowBytes + (c % 20) * 16);
+                        sts64(dst, v[r].x, v[r].y);
+                        sts64(dst + 8u, v[r].z, v[r].w);
+                        if (GATHER && ((own_mask >> r) & 1u)) *(uint4*)(p.trim_out + pre_q0 + 8 * c) = v[r];   // the tile's own samples = trimmed PCM
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(kTcBarRawFull));
+            }
+
             // ---- epilogue of this tile ----
-            mbar_wait(BAR(kTcBarAccFull), it & 1u);
-            tc_fence_after();
-            const i64 t = tile * kTcFrames + f;
-            TcEpi e;
-            e.a0 = 0.0f; e.a1 = 0.0f; e.lmax = -3.0e38f; e.lmin = 3.0e38f;
-            e.valid = t < T;
-            e.T = (size_t)T;
-            e.out = p.out + (size_t)b * (size_t)NM * (size_t)T + (e.valid ? t : 0);
-            if (role == 0) tc_epi_role<NM, 0>(e, tlane);
-            else if (role == 1) tc_epi_role<NM, 1>(e, tlane);
-            else if (role == 2) tc_epi_role<NM, 2>(e, tlane);
-            else tc_epi_role<NM, 3>(e, tlane);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(kTcBarAccFree));
-            // clip maximum and the minimum of this 32-frame group (lets the floor pass skip groups above the floor)
-            const float gmin = warp_reduce_min_f(e.valid ? e.lmin : 3.0e38f);
-            if (e.valid) run_max = fmaxf(run_max, e.lmax * 0.30102999566398120f);
-            if (lane == 0 && tile * kTcFrames + 32 * q < T)
-                atomicMin(p.tile_min_key + (size_t)b * (size_t)p.groups_cap + (size_t)(tile * 4 + q), float_to_key(fmaf(gmin * 0.30102999566398120f, 0.25f, 1.0f)));
-            if (p.per_clip) {
-                const float bm = warp_reduce_max_f(run_max);
-                if (lane == 0 && bm > -1.0e38f) atomicMax(p.gmax_key + b, float_to_key(bm));
-                run_max = -3.0e38f;
+            if (live) {
+                mbar_wait(BAR(kTcBarAccFull), it & 1u);
+                tc_fence_after();
+                const i64 t = tile * kTcFrames + f;
+                TcEpi e;
+                e.a0 = 0.0f; e.a1 = 0.0f; e.lmax = -3.0e38f; e.lmin = 3.0e38f;
+                e.valid = t < T;
+                e.T = (size_t)T;
+                e.out = p.out + (size_t)b * (size_t)NM * (size_t)T + (e.valid ? t : 0);
+                if (part == 0) tc_epi_role<NM, 0>(e, tlane);
+                else if (part == 1) tc_epi_role<NM, 1>(e, tlane);
+                else if (part == 2) tc_epi_role<NM, 2>(e, tlane);
+                else tc_epi_role<NM, 3>(e, tlane);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(kTcBarAccFree));
+                // clip maximum and the minimum of this 32-frame group (lets the floor pass skip groups above the floor)
+                const float gmin = warp_reduce_min_f(e.valid ? e.lmin : 3.0e38f);
+                if (e.valid) run_max = fmaxf(run_max, e.lmax * 0.30102999566398120f);
+                if (lane == 0 && tile * kTcFrames + 32 * q < T)
+                    atomicMin(p.tile_min_key + (size_t)b * (size_t)p.groups_cap + (size_t)(tile * 4 + q), float_to_key(fmaf(gmin * 0.30102999566398120f, 0.25f, 1.0f)));
+                if (p.per_clip) {
+                    const float bm = warp_reduce_max_f(run_max);
+                    if (lane == 0 && bm > -1.0e38f) atomicMax(p.gmax_key + b, float_to_key(bm));
+                    run_max = -3.0e38f;
+                }
+                it++;
             }
         }
         if (!p.per_clip) {

@@ -12,19 +12,20 @@
 //   ranges    = runs of starts with gaps <= W (or == step) -> [first, last_start + W)
 //   nonsilent = complement; kept = nonsilent +- keep_silence, overlapping neighbours meet at the midpoint
 //
-// Kernels: cover_kernel (windowed energy test + coverage mask + per-tile run counts, all from
-// shared-memory prefix sums over a tile with a W-ms halo), ranges_kernel (ordered scatter of the
-// run boundaries), kept_kernel (one block: keep_silence padding, midpoints, clamps, exclusive scan of
-// lengths), compact_kernel (gather kept milliseconds; warp-per-32-ms binary search in the offset table).
+// Kernels: silence_kernel (ONE launch for the windowed energy test, the coverage of the silent starts, the ordered range
+// tables and split_on_silence's kept ranges; see the comment above it), compact_kernel (standalone stream compaction:
+// gather kept milliseconds; binary search in the offset table; inside b2a_pipeline the log-mel tile loader gathers itself).
 #include "b2a_common.cuh"
 
 #include <cmath>
 
 namespace b2a {
 
-constexpr int SIL_TS = 2048;        // milliseconds per tile (4096 was measured: fewer halo re-reads but 3 instead of 5 blocks per SM, 38 vs 33.5 us)
-constexpr int SIL_THREADS = 256;
-constexpr int SIL_PER_THREAD = SIL_TS / SIL_THREADS;   // 8 consecutive ms per thread
+constexpr int SIL_THREADS = 1024;           // one block per SM
+constexpr int SIL_WARPS = SIL_THREADS / 32;
+constexpr int SIL_MIN_CHUNK = 4096;         // milliseconds per block, at least (short clips use fewer blocks)
+constexpr int SIL_MAX_CHUNK = 1 << 18;      // shared-memory bound: 148 blocks x 262 144 ms = 10.7 hours per clip
+constexpr int SIL_MAX_BLOCKS = 148;         // every block resident at once (the run-count exchange spins on its predecessors)
 
 struct SilenceCfg {
     i64 n_samples;      // F
@@ -37,7 +38,8 @@ struct SilenceCfg {
     i64 last;           // len_ms - W  (< 0: clip shorter than the window -> nothing is silent)
     u64 limit;          // n_win * (floor(thr)+1)^2
     int cap;
-    int n_tiles;
+    int chunk;          // cover positions per block (multiple of 32)
+    int n_blocks;
 };
 
 // ---- per-ms energy of an existing s16 mono buffer ------------------------------------------
@@ -55,9 +57,9 @@ __global__ void __launch_bounds__(256) energy_ms_kernel(const int16_t* __restric
     e[t] = acc;
 }
 
-// block-wide exclusive prefix over per-thread values (256 threads); returns exclusive prefix, total in *total
+// block-wide exclusive prefix over per-thread values (SIL_THREADS threads); returns exclusive prefix, total in *total
 template <class T>
-__device__ __forceinline__ T block_exclusive_scan(T v, T* s_warp /*[8]*/, T* total) {
+__device__ __forceinline__ T block_exclusive_scan(T v, T* s_warp /*[SIL_WARPS]*/, T* total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     T inc = v;
 #pragma unroll
@@ -70,7 +72,7 @@ __device__ __forceinline__ T block_exclusive_scan(T v, T* s_warp /*[8]*/, T* tot
     __syncthreads();
     T wpre = 0, tot = 0;
 #pragma unroll
-    for (int w = 0; w < SIL_THREADS / 32; w++) {
+    for (int w = 0; w < SIL_WARPS; w++) {
         T x = s_warp[w];
         if (w < warp) wpre += x;
         tot += x;
@@ -78,191 +80,33 @@ __device__ __forceinline__ T block_exclusive_scan(T v, T* s_warp /*[8]*/, T* tot
     *total = tot;
     return wpre + inc - v;
 }
-
-// cover[t] for t in [0, len_ms): 1 if millisecond t lies inside a (merged) silent range.
-// counts[tile*2+0] = nonsilent runs starting in the tile, counts[tile*2+1] = silent runs starting in the tile.
-__global__ void __launch_bounds__(SIL_THREADS) cover_kernel(const u64* __restrict__ e, SilenceCfg c,
-                                                            unsigned char* __restrict__ cover, int* __restrict__ counts) {
-    B2A_DYN_SMEM(smem_raw);
-    const int W = c.W;
-    const int NE = SIL_TS + 2 * W + 1;          // energies e[t0-W-1 .. t0+TS+W-1]  (+1 slot for the prefix)
-    u64* s_p = (u64*)smem_raw;                  // NE+1 : exclusive prefix of energies
-    int* s_c = (int*)(s_p + NE + 1);            // SIL_TS + W + 2 : exclusive prefix of start flags f[t0-W-1 ..]
-    __shared__ u64 s_w64[SIL_THREADS / 32];
-    __shared__ int s_w32[SIL_THREADS / 32];
-    __shared__ int s_cnt[2];
-
-    const int tid = threadIdx.x;
-    const i64 t0 = (i64)blockIdx.x * SIL_TS;
-    const i64 ebase = t0 - W - 1;               // energy index of local slot 0
-    if (tid < 2) s_cnt[tid] = 0;
-
-    // ---- exclusive prefix of energies over the tile + halos ----
-    // coalesced load of the raw energies (slot j+1), then each thread scans a contiguous chunk; the chunk length is odd
-    // so that the 8-byte shared-memory accesses of a warp (stride = chunk) fall in distinct banks
-    for (int j = tid; j < NE; j += SIL_THREADS) {
-        const i64 t = ebase + j;
-        s_p[j + 1] = (t >= 0 && t < c.len_ms && t < c.n_energy) ? e[t] : 0ull;
-    }
-    __syncthreads();
-    {
-        const int per = ((NE + SIL_THREADS - 1) / SIL_THREADS) | 1;
-        const int lo = min(tid * per, NE), hi = min(lo + per, NE);
-        u64 sum = 0;
-        for (int j = lo; j < hi; j++) sum += s_p[j + 1];
-        u64 tot;
-        u64 pre = block_exclusive_scan<u64>(sum, s_w64, &tot);
-        // turn the raw values into an exclusive prefix: s_p[j] = sum of slots < j
-        u64 run = pre;
-        for (int j = lo; j < hi; j++) {
-            u64 v = s_p[j + 1];
-            s_p[j + 1] = run + v;                // inclusive at j -> exclusive at j+1
-            run += v;
-        }
-        if (tid == 0) s_p[0] = 0;
-    }
-    __syncthreads();
-
-    // ---- start flags f[i] for i in [t0-W-1, t0+TS), then their exclusive prefix ----
-    {
-        const int NF = SIL_TS + W + 1;
-        const int per = ((NF + SIL_THREADS - 1) / SIL_THREADS) | 1;      // odd: conflict-free strided shared-memory access
-        const int lo = min(tid * per, NF), hi = min(lo + per, NF);
-        int sum = 0;
-        for (int j = lo; j < hi; j++) {
-            i64 i = ebase + j;                   // flag slot j <-> start ms i (same origin as energies)
-            int f = 0;
-            if (i >= 0 && i <= c.last && (c.step == 1 || (i % c.step) == 0 || i == c.last)) {
-                u64 E = s_p[j + W] - s_p[j];     // sum e[i .. i+W-1]
-                f = E < c.limit;
-            }
-            s_c[j + 1] = f;
-            sum += f;
-        }
-        int tot;
-        int pre = block_exclusive_scan<int>(sum, s_w32, &tot);
-        int run = pre;
-        for (int j = lo; j < hi; j++) {
-            int v = s_c[j + 1];
-            s_c[j + 1] = run + v;
-            run += v;
-        }
-        if (tid == 0) s_c[0] = 0;
-    }
-    __syncthreads();
-
-    // ---- coverage for t in [t0-1, t0+TS): any start in (t-W, t]  (+ the seek_step > W continuity rule) ----
-    // local flag slot of start i is j = i - ebase; covered(t) <=> C[j(t)+1] - C[j(t-W+1)] > 0
-    auto covered = [&](i64 t) -> int {
-        if (t < 0 || t >= c.len_ms) return 0;
-        int jt = (int)(t - ebase);
-        int jl = jt - W + 1;
-        if (jl < 0) jl = 0;
-        int cov = (s_c[jt + 1] - s_c[jl]) > 0;
-        if (!cov && c.step > W) {
-            // consecutive candidates p, p+step both silent are "continuous" in pydub and merge
-            i64 pc = (t / c.step) * c.step;
-            i64 nc = pc + c.step;
-            if (nc <= c.last) {
-                u64 E0 = 0, E1 = 0;
-                for (int k = 0; k < W; k++) { E0 += e[pc + k]; E1 += e[nc + k]; }
-                cov = (E0 < c.limit) && (E1 < c.limit);
-            }
-        }
-        return cov;
-    };
-    int ns_starts = 0, s_starts = 0;
-    {
-        const i64 tb = t0 + (i64)tid * SIL_PER_THREAD;
-        int prev = (tb == 0) ? -1 : covered(tb - 1);     // -1 = before the clip
+// the same with max (values >= -2^30)
+__device__ __forceinline__ int block_exclusive_max(int v, int* s_warp /*[SIL_WARPS]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kNone = -(1 << 30);
+    int inc = v;
 #pragma unroll
-        for (int k = 0; k < SIL_PER_THREAD; k++) {
-            i64 t = tb + k;
-            if (t < c.len_ms) {
-                int cv = covered(t);
-                cover[t] = (unsigned char)cv;
-                if (!cv && (prev != 0)) ns_starts++;  // nonsilent run starts: uncovered and (t==0 or previous covered)
-                if (cv && (prev != 1)) s_starts++;    // silent run starts: covered and (t==0 or previous uncovered)
-                prev = cv;
-            }
-        }
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc = max(inc, y);
     }
-    ns_starts = warp_reduce_sum_i(ns_starts);
-    s_starts = warp_reduce_sum_i(s_starts);
-    if ((tid & 31) == 0) { atomicAdd(&s_cnt[0], ns_starts); atomicAdd(&s_cnt[1], s_starts); }
     __syncthreads();
-    if (tid < 2) counts[blockIdx.x * 2 + tid] = s_cnt[tid];
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    int wpre = kNone;
+#pragma unroll
+    for (int w = 0; w < SIL_WARPS; w++) if (w < warp) wpre = max(wpre, s_warp[w]);
+    int ex = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) ex = kNone;
+    return max(wpre, ex);
 }
 
-// ordered scatter of run boundaries.  A run containing ms t has index (#run starts at positions <= t) - 1.
-__global__ void __launch_bounds__(SIL_THREADS) ranges_kernel(const unsigned char* __restrict__ cover, const int* __restrict__ counts,
-                                                             SilenceCfg c, int32_t* __restrict__ silent_ms,
-                                                             int32_t* __restrict__ nonsilent_ms, i64* __restrict__ info) {
-    __shared__ int s_w32[SIL_THREADS / 32];
-    __shared__ int s_base[2];
-    const int tid = threadIdx.x;
-    const i64 t0 = (i64)blockIdx.x * SIL_TS;
-
-    // runs that started in earlier tiles
-    int a0 = 0, a1 = 0, g0 = 0, g1 = 0;
-    for (int i = tid; i < c.n_tiles; i += SIL_THREADS) {
-        int x0 = counts[i * 2], x1 = counts[i * 2 + 1];
-        g0 += x0; g1 += x1;
-        if (i < (int)blockIdx.x) { a0 += x0; a1 += x1; }
-    }
-    int tot;
-    block_exclusive_scan<int>(a0, s_w32, &tot); if (tid == 0) s_base[0] = tot;
-    block_exclusive_scan<int>(a1, s_w32, &tot); if (tid == 0) s_base[1] = tot;
-    int gt0, gt1;
-    block_exclusive_scan<int>(g0, s_w32, &gt0);
-    block_exclusive_scan<int>(g1, s_w32, &gt1);
-    __syncthreads();
-    if (blockIdx.x == 0 && tid == 0) {
-        info[B2A_INFO_N_NONSILENT] = gt0 < c.cap ? gt0 : c.cap;
-        info[B2A_INFO_N_SILENT] = gt1 < c.cap ? gt1 : c.cap;
-        info[B2A_INFO_OVERFLOW] = (gt0 > c.cap || gt1 > c.cap) ? 1 : 0;
-        info[B2A_INFO_LEN_MS] = c.len_ms;
-    }
-
-    const i64 tb = t0 + (i64)tid * SIL_PER_THREAD;
-    int cv[SIL_PER_THREAD + 2];
-#pragma unroll
-    for (int k = 0; k < SIL_PER_THREAD + 2; k++) {
-        i64 t = tb - 1 + k;
-        cv[k] = (t >= 0 && t < c.len_ms) ? (int)cover[t] : -1;   // -1 = outside the clip
-    }
-    int n0 = 0, n1 = 0;
-#pragma unroll
-    for (int k = 1; k <= SIL_PER_THREAD; k++) {
-        if (cv[k] == 0 && cv[k - 1] != 0) n0++;
-        if (cv[k] == 1 && cv[k - 1] != 1) n1++;
-    }
-    int e0 = block_exclusive_scan<int>(n0, s_w32, &tot) + s_base[0];
-    int e1 = block_exclusive_scan<int>(n1, s_w32, &tot) + s_base[1];
-    // e0/e1 = number of nonsilent/silent run starts strictly before this thread's first ms
-#pragma unroll
-    for (int k = 1; k <= SIL_PER_THREAD; k++) {
-        const i64 t = tb - 1 + k;
-        if (cv[k] < 0) continue;
-        if (cv[k] == 0) {
-            if (cv[k - 1] != 0) { if (e0 < c.cap && nonsilent_ms) nonsilent_ms[2 * e0] = (int32_t)t; e0++; }
-            if (cv[k + 1] != 0) { int r = e0 - 1; if (r < c.cap && nonsilent_ms) nonsilent_ms[2 * r + 1] = (int32_t)(t + 1); }
-        } else {
-            if (cv[k - 1] != 1) { if (e1 < c.cap && silent_ms) silent_ms[2 * e1] = (int32_t)t; e1++; }
-            if (cv[k + 1] != 1) { int r = e1 - 1; if (r < c.cap && silent_ms) silent_ms[2 * r + 1] = (int32_t)(t + 1); }
-        }
-    }
-}
-
-// one block: split_on_silence's range arithmetic + exclusive scan of kept lengths (in samples)
-__global__ void __launch_bounds__(SIL_THREADS) kept_kernel(const int32_t* __restrict__ nonsilent_ms, SilenceCfg c,
-                                                           int32_t* __restrict__ kept_ms, i64* __restrict__ kept_off,
-                                                           i64* __restrict__ info) {
-    __shared__ i64 s_w64[SIL_THREADS / 32];
-    __shared__ i64 s_carry;
+// split_on_silence's range arithmetic + exclusive scan of kept lengths (in samples); one block
+__device__ void silence_kept_pass(const int32_t* __restrict__ nonsilent_ms, const SilenceCfg& c, int32_t* __restrict__ kept_ms,
+                                  i64* __restrict__ kept_off, i64* __restrict__ info, i64* s_w64, i64* s_carry_p) {
     const int tid = threadIdx.x;
     const int n = (int)info[B2A_INFO_N_NONSILENT];
-    if (tid == 0) s_carry = 0;
+    if (tid == 0) *s_carry_p = 0;
     __syncthreads();
     for (int base = 0; base < n || base == 0; base += SIL_THREADS) {
         const int k = base + tid;
@@ -288,18 +132,249 @@ __global__ void __launch_bounds__(SIL_THREADS) kept_kernel(const int32_t* __rest
         }
         i64 tot;
         i64 pre = block_exclusive_scan<i64>(len, s_w64, &tot);
-        const i64 carry = s_carry;
+        const i64 carry = *s_carry_p;
         if (k < n) kept_off[k] = carry + pre;
         __syncthreads();
-        if (tid == 0) s_carry = carry + tot;
+        if (tid == 0) *s_carry_p = carry + tot;
         __syncthreads();
         if (n == 0) break;
     }
     if (tid == 0) {
-        kept_off[n] = s_carry;
+        kept_off[n] = *s_carry_p;
         info[B2A_INFO_N_KEPT] = n;
-        info[B2A_INFO_N_KEEP] = s_carry;
+        info[B2A_INFO_N_KEEP] = *s_carry_p;
     }
+}
+
+// ---- the whole of pydub's detect_silence / detect_nonsilent / split_on_silence range logic in ONE launch -----------------
+// Block b owns the cover positions [c0, c0 + chunk) (chunk = len_ms / blocks, a multiple of 32) and evaluates the
+// window starts i in [c0 - W, c0 + chunk) it needs for them:
+//   1. S[j] = sum of 32 consecutive energies (one warp-reduce per 32 ms) over the block's range + halos, in shared memory;
+//   2. every warp streams a contiguous span of starts: E(i) = sum e[i .. i+W) follows from E of the span's first start
+//      (a few S values + a partial block) by ONE warp scan per 32 starts of d[l] = e[i+W+l] - e[i+l]; the silent-start flags
+//      of 32 starts are one ballot word in shared memory;
+//   3. a start covers the W ms behind it: cover(t) <=> t - (last flagged start <= t) < W, i.e. a block-wide prefix MAXIMUM of
+//      flag positions and a few bit operations per word of 32 ms;
+//   4. run starts (covered <-> uncovered transitions) are counted per word; the blocks exchange their counts through a status
+//      word each (every block is resident: a block waits only for blocks of lower index) and scatter their run boundaries
+//      into the ordered range tables: a silent run's start is the end of the nonsilent run before it, and vice versa;
+//   5. the block that finishes last (ticket counter) does split_on_silence's keep_silence / midpoint / clamp arithmetic and
+//      the exclusive scan of the kept lengths.
+// Exact-integer throughout (uint64 energies; differences wrap consistently).
+struct SilenceWs {            // global workspace, zeroed on the stream before the launch
+    unsigned long long status[SIL_MAX_BLOCKS];    // bit 63 valid | nonsilent starts << 31 | silent starts
+    unsigned int ticket;
+    unsigned int pad;
+};
+
+__global__ void __launch_bounds__(SIL_THREADS, 1) silence_kernel(const u64* __restrict__ e, SilenceCfg c, int32_t* __restrict__ silent_ms,
+                                                                 int32_t* __restrict__ nonsilent_ms, int32_t* __restrict__ kept_ms,
+                                                                 i64* __restrict__ kept_off, i64* __restrict__ info, SilenceWs* __restrict__ ws) {
+    B2A_DYN_SMEM(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int W = c.W, Wr = (W + 31) & ~31;
+    const int chunk = c.chunk;
+    const i64 c0 = (i64)blockIdx.x * chunk;             // first cover position of this block
+    const i64 f_lo = c0 - Wr;                           // first window start evaluated (32-aligned, <= c0 - W; may be negative)
+    const int n_fw = (chunk + Wr) / 32;                 // flag words: starts [f_lo, c0 + chunk)
+    const int n_cw = chunk / 32;                        // cover words: positions [c0, c0 + chunk)
+    const int n_S = (chunk + 2 * Wr) / 32 + 1;          // 32-ms sums over energies [f_lo, c0 + chunk + Wr + 32)
+    u64* s_S = (u64*)smem_raw;                          // [n_S]
+    unsigned* s_flag = (unsigned*)(s_S + n_S);          // [n_fw]
+    unsigned* s_cov = s_flag + n_fw;                    // [n_cw]
+    int* s_last = (int*)(s_cov + n_cw);                 // [n_fw]: last flagged start (relative to f_lo) before word fw
+    __shared__ i64 s_w64[SIL_WARPS];
+    __shared__ int s_w32[SIL_WARPS];
+    __shared__ i64 s_carry;
+    __shared__ i64 s_base;                              // packed run counts of the blocks before this one
+    __shared__ int s_is_last;
+
+    auto energy = [&](i64 t) -> u64 { return (t >= 0 && t < c.len_ms && t < c.n_energy) ? e[t] : 0ull; };
+
+    // ---- 1. 32-ms sums ----
+    for (int j = warp; j < n_S; j += SIL_WARPS) {
+        u64 v = energy(f_lo + 32 * (i64)j + lane);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_S[j] = v;
+    }
+    __syncthreads();
+
+    // ---- 2. silent-start flags, one warp per contiguous span of flag words ----
+    {
+        const int span = (n_fw + SIL_WARPS - 1) / SIL_WARPS;
+        const int w0 = warp * span, w1 = min(n_fw, w0 + span);
+        if (w0 < w1) {
+            // E of the span's first start: W / 32 whole 32-ms sums + W % 32 energies
+            u64 D = 0;
+            for (int j = lane; j < W / 32; j += 32) D += s_S[w0 + j];
+            {
+                const i64 t = f_lo + 32 * (i64)(w0 + W / 32) + lane;
+                if (lane < (W & 31)) D += energy(t);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) D += __shfl_xor_sync(0xffffffffu, D, o);
+            for (int fw = w0; fw < w1; fw++) {
+                const i64 i = f_lo + 32 * (i64)fw + lane;                 // this lane's window start
+                const u64 d = energy(i + W) - energy(i);                  // wraps; the running sum is exact mod 2^64
+                u64 inc = d;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const u64 y = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += y;
+                }
+                const u64 E = D + inc - d;                                 // sum e[i .. i + W)
+                const bool cand = i >= 0 && i <= c.last && (c.step == 1 || (i % c.step) == 0 || i == c.last);
+                const unsigned word = __ballot_sync(0xffffffffu, cand && E < c.limit);
+                if (lane == 0) s_flag[fw] = word;
+                D += __shfl_sync(0xffffffffu, inc, 31);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- 3. last flagged start before every flag word (exclusive prefix maximum), then the cover words ----
+    const int kNone = -(1 << 30);
+    {
+        const int per = (n_fw + SIL_THREADS - 1) / SIL_THREADS;
+        const int lo = min(tid * per, n_fw), hi = min(lo + per, n_fw);
+        int mx = kNone;
+        for (int fw = lo; fw < hi; fw++) {
+            const unsigned f = s_flag[fw];
+            if (f) mx = 32 * fw + 31 - __clz((int)f);
+        }
+        int run = block_exclusive_max(mx, s_w32);
+        for (int fw = lo; fw < hi; fw++) {
+            s_last[fw] = run;
+            const unsigned f = s_flag[fw];
+            if (f) run = 32 * fw + 31 - __clz((int)f);
+        }
+    }
+    __syncthreads();
+    auto window_silent = [&](i64 i) -> bool {            // direct evaluation (only for the seek_step > W continuity rule)
+        u64 E = 0;
+        for (int k = 0; k < W; k++) E += energy(i + k);
+        return E < c.limit;
+    };
+    for (int cw = tid; cw < n_cw; cw += SIL_THREADS) {
+        const int fw = cw + Wr / 32;
+        const unsigned f = s_flag[fw];
+        const int nb = s_last[fw] + W - 32 * fw;          // leading positions of the word still covered by an earlier start
+        unsigned cov = nb >= 32 ? 0xffffffffu : nb <= 0 ? 0u : ((1u << nb) - 1u);
+        if (W >= 32) {
+            if (f) cov |= 0xffffffffu << (__ffs((int)f) - 1);   // a start covers the rest of its word
+        } else {
+            for (int k = 0; k < W; k++) cov |= f << k;
+        }
+        const i64 t0 = c0 + 32 * (i64)cw;
+        if (c.step > W && cov != 0xffffffffu) {
+            // pydub merges consecutive candidates p, p + step that are both silent even though no window covers the gap
+            for (int b = 0; b < 32; b++) {
+                const i64 t = t0 + b;
+                if (((cov >> b) & 1u) || t >= c.len_ms) continue;
+                const i64 pc = (t / c.step) * c.step, nc = pc + c.step;
+                if (nc <= c.last && window_silent(pc) && window_silent(nc)) cov |= 1u << b;
+            }
+        }
+        const i64 left = c.len_ms - t0;                   // positions of this word inside the clip
+        if (left < 32) cov &= left <= 0 ? 0u : ((1u << (int)left) - 1u);
+        s_cov[cw] = cov;
+    }
+    __syncthreads();
+
+    // ---- 4. run starts per word, counts, exchange between blocks ----
+    // cover(c0 - 1): any flagged start in [c0 - W, c0 - 1]
+    const bool prev_block_cov = c0 > 0 && (n_cw > 0) && (s_last[Wr / 32] >= Wr - W);
+    const int per_c = (n_cw + SIL_THREADS - 1) / SIL_THREADS;
+    const int lo_c = min(tid * per_c, n_cw), hi_c = min(lo_c + per_c, n_cw);
+    auto start_masks = [&](int cw, unsigned& ns, unsigned& ss) {
+        const unsigned cov = s_cov[cw];
+        const i64 t0 = c0 + 32 * (i64)cw;
+        const i64 left = c.len_ms - t0;
+        const unsigned valid = left >= 32 ? 0xffffffffu : left <= 0 ? 0u : ((1u << (int)left) - 1u);
+        unsigned pbit;                                     // cover(t0 - 1)
+        if (cw > 0) pbit = s_cov[cw - 1] >> 31;
+        else pbit = prev_block_cov ? 1u : 0u;
+        unsigned prev_ns = (cov << 1) | pbit, prev_ss = prev_ns;
+        if (t0 == 0) { prev_ns |= 1u; prev_ss &= ~1u; }    // before the clip: a nonsilent run starts if t = 0 is uncovered, a silent one if covered
+        ns = ~cov & prev_ns & valid;
+        ss = cov & ~prev_ss & valid;
+    };
+    i64 cnt = 0;                                           // nonsilent starts << 32 | silent starts
+    for (int cw = lo_c; cw < hi_c; cw++) {
+        unsigned ns, ss;
+        start_masks(cw, ns, ss);
+        cnt += ((i64)__popc(ns) << 32) | (i64)__popc(ss);
+    }
+    i64 tot;
+    const i64 pre = block_exclusive_scan<i64>(cnt, s_w64, &tot);
+    if (warp == 0) {
+        if (lane == 0) {
+            const unsigned long long st = (1ull << 63) | ((unsigned long long)(tot >> 32) << 31) | (unsigned long long)(tot & 0x7fffffffLL);
+            atomicExch(&ws->status[blockIdx.x], st);
+        }
+        i64 base = 0;
+        for (int p0 = 0; p0 < (int)blockIdx.x; p0 += 32) {
+            const int pidx = p0 + lane;
+            unsigned long long st = 0;
+            if (pidx < (int)blockIdx.x) {
+                do { st = *(volatile unsigned long long*)&ws->status[pidx]; } while (!(st >> 63));
+                base += (i64)(((st >> 31) & 0xffffffffull) << 32) | (i64)(st & 0x7fffffffull);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) base += __shfl_xor_sync(0xffffffffu, base, o);
+        if (lane == 0) s_base = base;
+    }
+    __syncthreads();
+
+    // ---- 5. scatter: every run start is also the end of the run of the other kind before it ----
+    {
+        i64 at = s_base + pre;
+        int i0 = (int)(at >> 32), i1 = (int)(at & 0xffffffffLL);     // nonsilent / silent starts before this thread's first word
+        for (int cw = lo_c; cw < hi_c; cw++) {
+            unsigned ns, ss;
+            start_masks(cw, ns, ss);
+            const i64 t0 = c0 + 32 * (i64)cw;
+            unsigned both = ns | ss;                                   // never both at one position
+            while (both) {
+                const int b = __ffs((int)both) - 1;
+                both &= both - 1;
+                const int32_t t = (int32_t)(t0 + b);
+                if ((ns >> b) & 1u) {
+                    if (i0 < c.cap && nonsilent_ms) nonsilent_ms[2 * i0] = t;
+                    if (t > 0 && i1 - 1 < c.cap && silent_ms) silent_ms[2 * (i1 - 1) + 1] = t;      // ends the silent run before it
+                    i0++;
+                } else {
+                    if (i1 < c.cap && silent_ms) silent_ms[2 * i1] = t;
+                    if (t > 0 && i0 - 1 < c.cap && nonsilent_ms) nonsilent_ms[2 * (i0 - 1) + 1] = t;
+                    i1++;
+                }
+            }
+        }
+    }
+    if (blockIdx.x == gridDim.x - 1 && tid == 0) {
+        // totals, and the end of the run that is open at the end of the clip
+        const i64 all = s_base + tot;
+        const int g0 = (int)(all >> 32), g1 = (int)(all & 0xffffffffLL);
+        const i64 tl = c.len_ms - 1 - c0;                              // last position of the clip, relative to this block
+        const bool last_cov = tl >= 0 && ((s_cov[tl / 32] >> (tl % 32)) & 1u);
+        if (last_cov) { if (g1 >= 1 && g1 - 1 < c.cap && silent_ms) silent_ms[2 * (g1 - 1) + 1] = (int32_t)c.len_ms; }
+        else { if (g0 >= 1 && g0 - 1 < c.cap && nonsilent_ms) nonsilent_ms[2 * (g0 - 1) + 1] = (int32_t)c.len_ms; }
+        info[B2A_INFO_N_NONSILENT] = g0 < c.cap ? g0 : c.cap;
+        info[B2A_INFO_N_SILENT] = g1 < c.cap ? g1 : c.cap;
+        info[B2A_INFO_OVERFLOW] = (g0 > c.cap || g1 > c.cap) ? 1 : 0;
+        info[B2A_INFO_LEN_MS] = c.len_ms;
+    }
+
+    // ---- 6. the block that finishes last derives the kept ranges ----
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_is_last = atomicAdd(&ws->ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_is_last) return;
+    __threadfence();
+    silence_kept_pass(nonsilent_ms, c, kept_ms, kept_off, info, s_w64, &s_carry);
 }
 
 // gather: one thread per kept millisecond.  Segments start on ms boundaries in both source and destination,
@@ -355,12 +430,8 @@ static i64 pydub_len_ms(i64 n_frames, int sample_rate) {
     return (i64)std::nearbyint(v);
 }
 
-// workspace: [cover: len_ms bytes][counts: 2*n_tiles ints][nonsilent scratch when the caller passes NULL]
-static size_t silence_ws_bytes(i64 n_samples, int sample_rate) {
-    i64 len_ms = pydub_len_ms(n_samples, sample_rate) + 2;
-    i64 n_tiles = (len_ms + SIL_TS - 1) / SIL_TS + 1;
-    return align_up((size_t)len_ms, 256) + align_up((size_t)n_tiles * 8, 256) + 256;
-}
+// workspace: the blocks' status words and the ticket counter
+static size_t silence_ws_bytes(i64, int) { return align_up(sizeof(SilenceWs), 256) + 256; }
 
 int silence_build_cfg(i64 n_samples, int sample_rate, const b2a_silence_params* prm, int cap, SilenceCfg* c) {
     if (!prm) { set_error("silence: null params"); return B2A_EINVAL; }
@@ -388,7 +459,16 @@ int silence_build_cfg(i64 n_samples, int sample_rate, const b2a_silence_params* 
     u64 k = (u64)kf;
     c->limit = (u64)c->W * (u64)c->spm * k * k;
     c->cap = cap;
-    c->n_tiles = (int)((c->len_ms + SIL_TS - 1) / SIL_TS);
+    // one chunk of cover positions per block: at most one block per SM, at least SIL_MIN_CHUNK ms each
+    i64 blocks = (c->len_ms + SIL_MIN_CHUNK - 1) / SIL_MIN_CHUNK;
+    if (blocks > SIL_MAX_BLOCKS) blocks = SIL_MAX_BLOCKS;
+    if (blocks < 1) blocks = 1;
+    i64 chunk = ((c->len_ms + blocks - 1) / blocks + 31) / 32 * 32;
+    if (chunk < 32) chunk = 32;
+    if (chunk > SIL_MAX_CHUNK) { set_error("silence: clips longer than %d x %d ms are unsupported", SIL_MAX_BLOCKS, SIL_MAX_CHUNK); return B2A_EUNSUPPORTED; }
+    c->chunk = (int)chunk;
+    c->n_blocks = (int)((c->len_ms + chunk - 1) / chunk);
+    if (c->n_blocks < 1) c->n_blocks = 1;
     return B2A_OK;
 }
 
@@ -407,20 +487,28 @@ int silence_launch(const u64* d_energy, i64 n_samples, int sample_rate, const b2
         B2A_CHECK_LAUNCH("silence_empty_kernel");
         return B2A_OK;
     }
-    unsigned char* cover = (unsigned char*)d_ws;
-    int* counts = (int*)((char*)d_ws + align_up((size_t)c.len_ms + 2, 256));
-    size_t smem = (size_t)(SIL_TS + 2 * c.W + 2) * 8 + (size_t)(SIL_TS + c.W + 2) * 4 + 64;
-    auto k1 = cover_kernel;
-    cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(cover_kernel)");
-    B2A_LAUNCH(k1, c.n_tiles, SIL_THREADS, smem, stream, d_energy, c, cover, counts);
-    B2A_CHECK_LAUNCH("cover_kernel");
-    auto k2 = ranges_kernel;
-    B2A_LAUNCH(k2, c.n_tiles, SIL_THREADS, 0, stream, (const unsigned char*)cover, (const int*)counts, c, d_silent, d_nonsilent, d_info);
-    B2A_CHECK_LAUNCH("ranges_kernel");
-    auto k3 = kept_kernel;
-    B2A_LAUNCH(k3, 1, SIL_THREADS, 0, stream, (const int32_t*)d_nonsilent, c, d_kept, d_kept_off, d_info);
-    B2A_CHECK_LAUNCH("kept_kernel");
+    if (((uintptr_t)d_ws) & 7) { set_error("silence: workspace must be 8-byte aligned"); return B2A_EINVAL; }
+    SilenceWs* wsp = (SilenceWs*)d_ws;
+    cudaError_t e = cudaMemsetAsync(wsp, 0, sizeof(SilenceWs), stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(silence workspace)");
+    const int Wr = (c.W + 31) & ~31;
+    const size_t smem = (size_t)((c.chunk + 2 * Wr) / 32 + 1) * 8 + (size_t)((c.chunk + Wr) / 32) * 8 + (size_t)(c.chunk / 32) * 4 + 64;
+    static const size_t kSmemMax = (size_t)((SIL_MAX_CHUNK + 2 * 10016) / 32 + 1) * 8 + (size_t)((SIL_MAX_CHUNK + 10016) / 32) * 8 + (size_t)(SIL_MAX_CHUNK / 32) * 4 + 64;
+    auto k1 = silence_kernel;
+    {
+        // the opt-in to large dynamic shared memory is set ONCE per device to the largest size any call can need
+        // (concurrent callers with different min_silence_len must not lower each other's limit)
+        static unsigned long long attr_mask = 0;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !((attr_mask >> dev) & 1ull)) {
+            e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(silence_kernel)");
+            if (dev >= 0 && dev < 64) attr_mask |= 1ull << dev;
+        }
+    }
+    B2A_LAUNCH(k1, c.n_blocks, SIL_THREADS, smem, stream, d_energy, c, d_silent, d_nonsilent, d_kept, d_kept_off, d_info, wsp);
+    B2A_CHECK_LAUNCH("silence_kernel");
     return B2A_OK;
 }
 
