@@ -53,6 +53,8 @@ SIGNATURES = {
                               C.c_size_t, P]),
     "b2a_mel_windows": (C.c_int, [P, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, P, P]),
     "b2a_mel_filters": (C.c_int, [C.c_int, P, C.c_size_t]),
+    "b2a_kept_offsets": (C.c_int, [P, P, C.c_int, C.c_int32, P, P]),
+    "b2a_remap_times": (C.c_int, [P, C.c_int64, P, P, P, C.c_int, P, P]),
     "b2a_pipeline_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int64, C.c_int32]),
     "b2a_pipeline": (C.c_int, [P, C.c_int, C.c_int, C.c_int, C.c_int64, C.POINTER(SilenceParams), C.c_int, C.c_int64,
                                C.c_int32, P, P, P, P, P, P, C.c_size_t, P]),

@@ -21,7 +21,7 @@ OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libb2a.so")
 
 SOURCES = [
-    "b2a_host.cu", "logmel.cu", "silence.cu", "resample.cu", "pipeline.cu", "fir_dispatch.cu",
+    "b2a_host.cu", "logmel.cu", "silence.cu", "resample.cu", "pipeline.cu", "remap.cu", "fir_dispatch.cu",
     "fir_mma_44100.cu", "fir_mma_48000.cu", "fir_tmem_44100.cu", "fir_tmem_48000.cu",
 ]
 
@@ -61,9 +61,11 @@ def gen_mel(force: bool = False) -> None:
 
 
 def gen_mel_tc(force: bool = False) -> None:
-    """csrc/mel_tc_tables_gen.inc (the filterbank as the tensor-core epilogue unrolls it) from tools/gen_mel_tc_tables.cpp."""
-    out = os.path.join(CSRC, "mel_tc_tables_gen.inc")
-    src = os.path.join(ROOT, "tools", "gen_mel_tc_tables.cpp")
+    """tools/probes/_bin/mel_tc_tables_gen.inc (the filterbank as the tensor-core PROBE's epilogue unrolls it) from
+    tools/probes/gen_mel_tc_tables.cpp: needed by profiling builds and the test-only emulation library, not by libb2a.so."""
+    os.makedirs(os.path.join(ROOT, "tools", "probes", "_bin"), exist_ok=True)
+    out = os.path.join(ROOT, "tools", "probes", "_bin", "mel_tc_tables_gen.inc")
+    src = os.path.join(ROOT, "tools", "probes", "gen_mel_tc_tables.cpp")
     dep = max(os.path.getmtime(src), os.path.getmtime(os.path.join(CSRC, "mel_design.h")))
     if not force and os.path.exists(out) and os.path.getmtime(out) >= dep:
         return
@@ -77,7 +79,6 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
     gen_mel(force)
-    gen_mel_tc(force)
     dep_m = _deps_mtime()
     jobs = []
     for s in SOURCES:

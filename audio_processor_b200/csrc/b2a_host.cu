@@ -96,7 +96,8 @@ const LogMelTables* get_logmel_tables(int n_mels) {
     return d;
 }
 
-// ---- basis bank + window tables of the tensor-core log-mel (logmel_tc.cuh) ----------------------------------------------
+#if defined(B2A_PROFILE) || defined(B2A_EMU)
+// ---- basis bank + window tables of the tensor-core log-mel PROBE (tools/probes/logmel_tc.cuh; not in the release library) ----
 // Eight f16 planes (product p = even-cos, even-sin, odd-cos, odd-sin; hi = f16(c), lo = f16(c - hi)) in the canonical
 // no-swizzle K-major UMMA layout: element (k = n, row = j) of a plane at (n / 8) * kTcLbo + (j / 8) * 128 + (j % 8) * 16 +
 // (n % 8) * 2 bytes, 13 x 13 blocks of 8 x 8 stored (n, j <= 103; the MMAs' K = N = 112 read one block further, which aliases
@@ -147,6 +148,7 @@ const unsigned char* get_logmel_tc_blob() {
     g_logmel_tc[dev] = d;
     return d;
 }
+#endif
 
 const ResampleDesign* get_resample_design(int in_rate, int out_rate) {
     if (in_rate <= 0 || out_rate <= 0) { set_error("bad sample rate %d -> %d", in_rate, out_rate); return nullptr; }

@@ -27,7 +27,10 @@
 
 #include "b2a_tables.cuh"
 #include "f16_bits.h"
-#include "logmel_tc.cuh"
+#if defined(B2A_PROFILE) || defined(B2A_EMU)
+#include "../../tools/probes/logmel_tc.cuh"      // the tensor-core variant (probe; measured, not faster: see its header)
+#define B2A_HAVE_LOGMEL_TC 1
+#endif
 
 namespace b2a {
 
@@ -674,14 +677,19 @@ int logmel_launch(const void* d_audio, int fmt, i64 batch, i64 n, i64 row_stride
     if (work <= 0) { if (d_frames_out) cudaMemsetAsync(d_frames_out, 0, 8, stream); return B2A_OK; }
     int nkeys = (int)batch;
     const bool s16 = fmt == B2A_FMT_S16;
+    bool use_tc = false;
+#ifdef B2A_HAVE_LOGMEL_TC
+    if (s16) { const char* impl = getenv("B2A_LM_IMPL"); use_tc = impl && impl[0] == 't'; }   // profiling / emulation builds only
+#endif
     auto kinit = logmel_init_kernel;
     {
-        const i64 n_groups = s16 ? p.tiles_cap * batch : 0;      // the tensor-core kernel needs the minima initialised
+        const i64 n_groups = use_tc ? p.tiles_cap * batch : 0;   // (the tensor-core probe lowers the group minima with atomicMin)
         const i64 n_init = n_groups > nkeys ? n_groups : nkeys;
-        B2A_LAUNCH(kinit, (unsigned)((n_init + 255) / 256), 256, 0, stream, p.gmax_key, nkeys, s16 ? p.tile_min : (int*)nullptr, n_groups);
+        B2A_LAUNCH(kinit, (unsigned)((n_init + 255) / 256), 256, 0, stream, p.gmax_key, nkeys, use_tc ? p.tile_min : (int*)nullptr, n_groups);
     }
-    if (s16) {
-        // 16-bit input: the tensor-core kernel (logmel_tc.cuh); 128-frame tiles, minima per 32-frame group as before
+#ifdef B2A_HAVE_LOGMEL_TC
+    if (use_tc) {
+        // the tensor-core probe kernel: 128-frame tiles, minima per 32-frame group as the FFT kernel
         const unsigned char* blob = get_logmel_tc_blob();
         if (!blob) return B2A_ECUDA;
         LogMelTcParams q;
@@ -719,15 +727,18 @@ int logmel_launch(const void* d_audio, int fmt, i64 batch, i64 n, i64 row_stride
             }
             B2A_CHECK_LAUNCH("logmel_tc_kernel");
         }
-    } else {
-    // float input: the CUDA-core FFT kernel (its 83 KB f32 tile does not fit next to the tensor-core kernel's basis bank)
-    size_t smem = logmel_smem_bytes<B2A_FMT_F32>();
-    auto k4 = n_mels == 80 ? stft_mel_kernel<80, B2A_FMT_F32, false> : stft_mel_kernel<128, B2A_FMT_F32, false>;
+    } else
+#endif
+    {
+    size_t smem = s16 ? logmel_smem_bytes<B2A_FMT_S16>() : logmel_smem_bytes<B2A_FMT_F32>();
+    auto k4 = gather ? (n_mels == 80 ? stft_mel_kernel<80, B2A_FMT_S16, true> : stft_mel_kernel<128, B2A_FMT_S16, true>)
+              : n_mels == 80 ? (s16 ? stft_mel_kernel<80, B2A_FMT_S16, false> : stft_mel_kernel<80, B2A_FMT_F32, false>)
+                             : (s16 ? stft_mel_kernel<128, B2A_FMT_S16, false> : stft_mel_kernel<128, B2A_FMT_F32, false>);
     {
         cudaError_t e = cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // idempotent, cheap
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(stft_mel)");
     }
-    const i64 resident = 148 * LmSmem<B2A_FMT_F32>::CTAS;   // persistent: every CTA resident
+    const i64 resident = 148 * (s16 ? LmSmem<B2A_FMT_S16>::CTAS : LmSmem<B2A_FMT_F32>::CTAS);   // persistent: every CTA resident
     i64 grid = work < resident ? work : resident;
     B2A_LAUNCH(k4, (unsigned)grid, LM_THREADS, smem, stream, p);
     B2A_CHECK_LAUNCH("stft_mel_kernel");
@@ -809,6 +820,15 @@ int mel_windows_launch(const float* d_mel, int n_mels, i64 T, i64 content, i64 s
 }
 
 }  // namespace b2a
+
+#if defined(B2A_PROFILE) && !defined(B2A_EMU)
+// profiling builds only: the event trace of logmel_tc_kernel's CTA 0 (tools/probes/logmel_tc_trace.py)
+extern "C" int b2a_debug_tc_trace(unsigned long long* h_out, int n, int reset) {
+    if (h_out && n > 0) cudaMemcpyFromSymbol(h_out, b2a::g_tc_trace, sizeof(unsigned long long) * (size_t)(n < 16384 ? n : 16384));
+    if (reset) { unsigned long long z = 0; cudaMemcpyToSymbol(b2a::g_tc_trace, &z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 extern "C" {
 

@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(SIL_THREADS, 1) silence_kernel(const u64* __re
         for (int k = 0; k < W; k++) E += energy(i + k);
         return E < c.limit;
     };
-    for (int cw = tid; cw < n_cw; cw += SIL_THREADS) {
+    auto cover_word = [&](int cw) -> unsigned {          // cw >= -1: positions [c0 + 32 cw, +32)
         const int fw = cw + Wr / 32;
         const unsigned f = s_flag[fw];
         const int nb = s_last[fw] + W - 32 * fw;          // leading positions of the word still covered by an earlier start
@@ -271,20 +271,22 @@ __global__ void __launch_bounds__(SIL_THREADS, 1) silence_kernel(const u64* __re
             // pydub merges consecutive candidates p, p + step that are both silent even though no window covers the gap
             for (int b = 0; b < 32; b++) {
                 const i64 t = t0 + b;
-                if (((cov >> b) & 1u) || t >= c.len_ms) continue;
+                if (((cov >> b) & 1u) || t >= c.len_ms || t < 0) continue;
                 const i64 pc = (t / c.step) * c.step, nc = pc + c.step;
                 if (nc <= c.last && window_silent(pc) && window_silent(nc)) cov |= 1u << b;
             }
         }
         const i64 left = c.len_ms - t0;                   // positions of this word inside the clip
         if (left < 32) cov &= left <= 0 ? 0u : ((1u << (int)left) - 1u);
-        s_cov[cw] = cov;
-    }
+        return cov;
+    };
+    for (int cw = tid; cw < n_cw; cw += SIL_THREADS) s_cov[cw] = cover_word(cw);
+    __shared__ unsigned s_prev_cov;                       // cover(c0 - 1), by the same rule (the word before the chunk)
+    if (tid == 0) s_prev_cov = c0 > 0 ? (cover_word(-1) >> 31) : 0u;
     __syncthreads();
 
     // ---- 4. run starts per word, counts, exchange between blocks ----
-    // cover(c0 - 1): any flagged start in [c0 - W, c0 - 1]
-    const bool prev_block_cov = c0 > 0 && (n_cw > 0) && (s_last[Wr / 32] >= Wr - W);
+    const bool prev_block_cov = s_prev_cov != 0u;
     const int per_c = (n_cw + SIL_THREADS - 1) / SIL_THREADS;
     const int lo_c = min(tid * per_c, n_cw), hi_c = min(lo_c + per_c, n_cw);
     auto start_masks = [&](int cw, unsigned& ns, unsigned& ss) {

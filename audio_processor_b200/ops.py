@@ -239,6 +239,25 @@ def mel_windows(mel, n_frames: int = 3000, *, content_frames: Optional[int] = No
     return out
 
 
+def remap_times(times, kept_ms, info, kept_off=None, sample_rate: int = SAMPLE_RATE):
+    """Seconds on the silence-stripped timeline -> seconds on the original recording, on the device (b2a_remap_times).
+    ``times``: float64 tensor / array of any shape; ``kept_ms`` [cap, 2] int32 and ``info`` int64[8] as produced by
+    detect() / PipelinePlan (device tensors); ``kept_off`` int64[cap + 1] if the caller has it (SilenceResult.kept_off),
+    else it is derived from the range table."""
+    torch = require_cuda()
+    dev = kept_ms.device
+    t = torch.as_tensor(times, dtype=torch.float64).to(dev).contiguous()
+    out = torch.empty_like(t)
+    with torch.cuda.device(dev):
+        cap = int(kept_ms.shape[0])
+        if kept_off is None:
+            kept_off = torch.empty(cap + 1, dtype=torch.int64, device=dev)
+            check(lib().b2a_kept_offsets(_ptr(kept_ms), _ptr(info), int(sample_rate), cap, _ptr(kept_off), _stream(torch)))
+        check(lib().b2a_remap_times(_ptr(t), int(t.numel()), _ptr(kept_ms), _ptr(kept_off), _ptr(info), int(sample_rate), _ptr(out),
+                                    _stream(torch)))
+    return out
+
+
 class PipelinePlan:
     """Pre-allocated buffers for running the whole path on clips of one shape (no allocation per call)."""
 
@@ -290,7 +309,9 @@ class PipelinePlan:
             if not graph:
                 launch()
                 return PipelineResult(self)
-            key = (x.data_ptr(), bool(trim), int(min_silence_len), float(silence_thresh), keep_silence, int(seek_step))
+            # keyed on the RESOLVED parameter struct: keep_silence=True (keep everything, -1) and keep_silence=1 (1 ms) hash
+            # alike as Python values but bake different parameters into the captured graph
+            key = (x.data_ptr(), bool(trim)) + ((prm.min_silence_len, prm.keep_silence, prm.seek_step, prm.silence_thresh) if prm is not None else ())
             g = self._graphs.get(key)
             if g is None:
                 if key not in self._warm:                # first use: run eagerly (builds the device tables, sets kernel attributes)

@@ -13,6 +13,7 @@ from __future__ import annotations
 import logging
 import os
 import subprocess
+import threading
 from typing import List, Optional, Tuple, Union
 
 import numpy as np
@@ -34,8 +35,21 @@ class AudioFrontend:
         self.n_mels = n_mels
         self.strip_silence = strip_silence
         self.device = device
-        self.last_segments: Optional[List[List[int]]] = None   # kept [start_ms, end_ms] of the last preprocess_audio
-        self._plans = {}                                        # PipelinePlan per clip shape (buffers reused across calls)
+        # The reference calls these helpers from a 3-thread ThreadPoolExecutor (audio_processor.py:56) on ONE shared instance:
+        # everything a call leaves behind (the kept table, the cached plans and their buffers) is per thread.
+        self._tls = threading.local()
+
+    @property
+    def last_segments(self) -> Optional[List[List[int]]]:
+        """kept [start_ms, end_ms] of the last preprocess_audio / process_pcm made by THIS thread (a job runs on one worker
+        thread from convert to remap, audio_processor.py:1150-1179); prefer the table the call itself returns"""
+        return getattr(self._tls, "last_segments", None)
+
+    def _thread_plans(self) -> dict:
+        plans = getattr(self._tls, "plans", None)
+        if plans is None:
+            plans = self._tls.plans = {}                        # PipelinePlan per clip shape (buffers reused across this thread's calls)
+        return plans
 
     # -- convert_to_wav (audio_processor.py:901-930) ----------------------------------------------------
     def convert_to_wav(self, input_path: str) -> str:
@@ -59,46 +73,61 @@ class AudioFrontend:
     def preprocess_audio(self, audio_path: str) -> str:
         """預處理音頻: ensure 16 kHz mono WAV, then strip silence.  Returns the same path when nothing changed, else
         a new ``<stem>.trimmed.wav`` (the caller removes the old file when the path differs, :1048-1051)."""
+        return self.preprocess_audio_segments(audio_path)[0]
+
+    def preprocess_audio_segments(self, audio_path: str) -> Tuple[str, List[List[int]]]:
+        """preprocess_audio that also RETURNS the kept [start_ms, end_ms] table (what remap_segments needs), instead of
+        leaving it on the shared instance."""
         logging.info(f"🔄 預處理音頻: {os.path.basename(audio_path)}")
         if not audio_path.lower().endswith(".wav"):
             audio_path = self.convert_to_wav(audio_path)
         if not self.strip_silence:
-            return audio_path
+            return audio_path, []
         pcm, rate = wavio.read_wav(audio_path)
         if rate != ops.SAMPLE_RATE or pcm.ndim != 1 or pcm.dtype != np.int16:
             audio_path = self.convert_to_wav(audio_path)
             pcm, rate = wavio.read_wav(audio_path)
         dev = self._to_device(pcm)
         res = ops.detect(dev, rate, self.min_silence_len, self.silence_thresh, self.keep_silence, self.seek_step)
-        self.last_segments = res.kept
+        kept = res.kept
+        self._tls.last_segments = kept
         if res.n_keep == len(pcm):
             logging.info("✅ 音頻預處理完成")
-            return audio_path
+            return audio_path, kept
         out = ops.compact(dev, res, rate)[: res.n_keep]
         new_path = os.path.splitext(audio_path)[0] + ".trimmed.wav"
         wavio.write_wav_s16(new_path, out.cpu().numpy(), rate)
         logging.info("✅ 音頻預處理完成")
-        return new_path
+        return new_path, kept
 
     # -- what model.transcribe computes first (audio_processor.py:1076) ------------------------------------
     def log_mel(self, audio_path: str, padding: int = whisper_audio.N_SAMPLES):
         return whisper_audio.log_mel_spectrogram(audio_path, n_mels=self.n_mels, padding=padding, device=self.device)
 
     # -- all three without touching the filesystem in between ---------------------------------------------------
-    def process_pcm(self, pcm, in_rate: int, padding: int = 0) -> Tuple["object", "object", List[List[int]]]:
-        """(trimmed 16 kHz s16 PCM, log-mel, kept [start_ms, end_ms]) for raw PCM, one fused device pass."""
+    def process_pcm(self, pcm, in_rate: int, padding: int = 0, copy: bool = True) -> Tuple["object", "object", List[List[int]]]:
+        """(trimmed 16 kHz s16 PCM, log-mel, kept [start_ms, end_ms]) for raw PCM, one fused device pass.
+
+        The work buffers are cached per thread and clip shape; the results are returned as fresh tensors (``copy=True``),
+        so earlier results stay valid when the next clip of the same shape runs.  ``copy=False`` returns views of the
+        thread's plan buffers, valid until this thread's next call with the same shape."""
         x = self._to_device(pcm).contiguous()
         ch = 1 if x.dim() == 1 else int(x.shape[1])
         key = (int(x.shape[0]), int(in_rate), ch, x.dtype, self.n_mels, int(padding), str(x.device))
-        plan = self._plans.get(key)
+        plans = self._thread_plans()
+        plan = plans.get(key)
         if plan is None:
-            if len(self._plans) >= 4:
-                self._plans.clear()
-            plan = self._plans[key] = ops.PipelinePlan(key[0], in_rate, ch, x.dtype, n_mels=self.n_mels, padding=padding,
-                                                       device=x.device)
+            if len(plans) >= 4:
+                plans.clear()
+            plan = plans[key] = ops.PipelinePlan(key[0], in_rate, ch, x.dtype, n_mels=self.n_mels, padding=padding,
+                                                 device=x.device)
         r = plan.run(x, trim=self.strip_silence, min_silence_len=self.min_silence_len, silence_thresh=self.silence_thresh,
                      keep_silence=self.keep_silence, seek_step=self.seek_step)
-        return r.pcm, r.mel, r.kept
+        kept = r.kept
+        self._tls.last_segments = kept
+        if copy:
+            return r.pcm.clone(), r.mel.clone(), kept
+        return r.pcm, r.mel, kept
 
     def stream(self, n_in: int, in_rate: int, channels: int = 2, dtype=None, padding: int = 0, depth: int = 2) -> "ClipStream":
         """pipelined submit()/result() front-end for many same-shaped clips (uploads overlap kernels and downloads)"""

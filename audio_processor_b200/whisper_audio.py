@@ -114,11 +114,21 @@ def mel_windows(mel, n_frames: int = N_FRAMES, dtype=None):
 
 
 def patch_whisper() -> None:
-    """Rebind openai-whisper's front-end to this module (transcribe imports the names directly)."""
-    import whisper  # type: ignore
-    import whisper.audio as wa  # type: ignore
-    import whisper.transcribe as wt  # type: ignore
-    for mod in (wa, wt, whisper):
+    """Rebind openai-whisper's front-end to this module.
+
+    ``whisper/transcribe.py`` does ``from .audio import log_mel_spectrogram, pad_or_trim, ...`` and ``whisper/__init__.py``
+    does ``from .transcribe import transcribe``: the names live in three module namespaces, and ``whisper.transcribe`` as an
+    attribute of the package is the FUNCTION, not the submodule — so the submodules are fetched from ``sys.modules`` by
+    their dotted names (importlib), and every one that binds a name gets it replaced."""
+    import importlib
+    import sys
+    importlib.import_module("whisper")
+    for modname in ("whisper.audio", "whisper.transcribe", "whisper"):
+        try:
+            mod = importlib.import_module(modname)
+        except ImportError:
+            continue
+        mod = sys.modules.get(modname, mod)
         for name in ("log_mel_spectrogram", "load_audio", "pad_or_trim"):
             if hasattr(mod, name):
                 setattr(mod, name, globals()[name])

@@ -185,6 +185,22 @@ int b2a_pipeline(const void* d_in, int fmt, int channels, int in_rate, int64_t n
                  int16_t* d_pcm_out, float* d_mel_out, int32_t* d_nonsilent_ms, int32_t* d_kept_ms,
                  int64_t* d_info, void* d_ws, size_t ws_bytes, b2a_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Timestamps on the silence-stripped timeline -> the original recording: what the speaker-overlap loop of
+ * process_audio (/root/reference/app/services/audio_processor.py:1114-1145) needs once preprocess_audio
+ * (:1046-1051) has removed silence — Whisper's segment start / end refer to the trimmed audio, diarization to the
+ * original.  d_t_in / d_t_out: double[n] seconds; d_kept_ms / d_kept_off / d_info: the tables of
+ * b2a_detect_silence or b2a_pipeline (kept_off in samples of the trimmed clip at sample_rate).  A time exactly on a
+ * cut maps to the end of the earlier kept range; times behind the last range map to its end.
+ * ------------------------------------------------------------------------------------------ */
+/* d_kept_off[k] (int64[cap + 1]) = samples of the trimmed clip before kept range k, from the range table alone
+ * (b2a_detect_silence returns it; b2a_pipeline keeps its copy inside the workspace) */
+int b2a_kept_offsets(const int32_t* d_kept_ms, const int64_t* d_info, int sample_rate, int32_t cap, int64_t* d_kept_off,
+                     b2a_stream_t stream);
+
+int b2a_remap_times(const double* d_t_in, int64_t n, const int32_t* d_kept_ms, const int64_t* d_kept_off,
+                    const int64_t* d_info, int sample_rate, double* d_t_out, b2a_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,7 +28,7 @@ def build(force: bool = False) -> str:
     gen_mel()
     gen_mel_tc()
     dep_m = 0.0
-    for d in (CSRC, HERE, os.path.join(ROOT, "include")):
+    for d in (CSRC, HERE, os.path.join(ROOT, "include"), os.path.join(ROOT, "tools", "probes")):       # probes: the tensor-core log-mel variant
         for f in os.listdir(d):
             if f.endswith((".cuh", ".h", ".inc")):
                 dep_m = max(dep_m, os.path.getmtime(os.path.join(d, f)))

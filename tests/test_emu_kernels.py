@@ -220,9 +220,12 @@ def test_emu_pipeline_fused_compaction_many_short_segments(emu, keep, pad, extra
     assert r["mel"].shape == ref.shape and np.abs(r["mel"] - ref).max() <= 1e-4
 
 
+# ---- the tensor-core log-mel PROBE (tools/probes/logmel_tc.cuh): compiled into the emulation library only, selected with
+# B2A_LM_IMPL=tc; the release library ships the FFT kernel for every input (profiles/r02_logmel_tc.md) ----
 def test_emu_logmel_tc_many_tiles_per_cta(emu, monkeypatch):
-    """the tensor-core log-mel (logmel_tc.cuh) with 2 persistent CTAs over 7 tiles of 128 frames: operand-ring and
+    """the tensor-core log-mel probe with 2 persistent CTAs over 7 tiles of 128 frames: operand-ring and
     accumulator barrier parities across tiles, raw-tile reuse, a partial last tile, whole-call maximum"""
+    monkeypatch.setenv("B2A_LM_IMPL", "tc")
     monkeypatch.setenv("B2A_LM_GRID", "2")
     rng = np.random.default_rng(5)
     n = 160 * 128 * 6 + 160 * 50 + 77
@@ -237,7 +240,16 @@ def test_emu_logmel_tc_many_tiles_per_cta(emu, monkeypatch):
     assert got.shape == ref.shape and np.abs(got - ref).max() <= 1e-4
 
 
-def test_emu_logmel_tc_batch_unaligned_and_short(emu):
+def test_emu_logmel_tc_batch_unaligned_and_short(emu, monkeypatch):
+    monkeypatch.setenv("B2A_LM_IMPL", "tc")
+    _logmel_batch_unaligned_and_short(emu)
+
+
+def test_emu_logmel_s16_batch_unaligned_and_short(emu):
+    _logmel_batch_unaligned_and_short(emu)
+
+
+def _logmel_batch_unaligned_and_short(emu):
     """batches of 16-bit clips (work item = clip x tile, per-clip and whole-call maximum), rows whose stride breaks the
     16-byte alignment of the bulk copies (lanes copy those rows themselves), clips shorter than one tile"""
     rng = np.random.default_rng(6)
@@ -250,7 +262,16 @@ def test_emu_logmel_tc_batch_unaligned_and_short(emu):
     assert np.all(emu.log_mel(np.zeros(16000, np.int16), 80) == -1.5)
 
 
-def test_emu_logmel_tc_tone_over_noise_floor(emu):
+def test_emu_logmel_tc_tone_over_noise_floor(emu, monkeypatch):
+    monkeypatch.setenv("B2A_LM_IMPL", "tc")
+    _logmel_tone_over_noise_floor(emu)
+
+
+def test_emu_logmel_s16_tone_over_noise_floor(emu):
+    _logmel_tone_over_noise_floor(emu)
+
+
+def _logmel_tone_over_noise_floor(emu):
     """the worst probed dynamic range for the f16-plane DFT: a full-scale tone over a +-2 LSB noise floor"""
     rng = np.random.default_rng(7)
     n = 16000 * 3
@@ -259,7 +280,16 @@ def test_emu_logmel_tc_tone_over_noise_floor(emu):
         assert np.abs(emu.log_mel(x, nm) - wl.log_mel_spectrogram(x.astype(np.float32) / 32768.0, nm).numpy()).max() <= 1e-4
 
 
-def test_emu_pipeline_tc_gather_window_overflow(emu):
+def test_emu_pipeline_tc_gather_window_overflow(emu, monkeypatch):
+    monkeypatch.setenv("B2A_LM_IMPL", "tc")
+    _pipeline_many_ranges_under_one_tile(emu)
+
+
+def test_emu_pipeline_many_ranges_under_one_tile(emu):
+    _pipeline_many_ranges_under_one_tile(emu)
+
+
+def _pipeline_many_ranges_under_one_tile(emu):
     """more than 32 kept ranges under one 128-frame tile (40 ms bursts): the producer's cached range window overflows and
     the rows behind it take the per-sample path; result identical to the oracle's trimmed PCM and log-mel"""
     rng = np.random.default_rng(8)
@@ -288,3 +318,25 @@ def test_emu_fir_mono_last_tile_stays_inside_the_clip(emu, n):
     if swr_ref.available():
         _cmp16(y, swr_ref.convert(x, 44100), 0.998)
     assert np.array_equal(en.astype(np.int64), H.energy_oracle(y))
+
+
+def test_emu_silence_many_blocks_and_sparse_seek(emu):
+    """the one-launch silence kernel over several blocks (>= 4 096 ms each): run counts exchanged between blocks, runs that
+    cross block boundaries, seek_step larger than min_silence_len (pydub still merges consecutive silent candidates, also
+    across a block boundary), windows longer than a block's halo rounding"""
+    rng = np.random.default_rng(21)
+    for trial, (W, th, keep, step) in enumerate([(100, -40, 50, 300), (250, -30, 0, 1200), (1000, -40, 200, 1), (500, -50, True, 25),
+                                                 (100, -40, 100, 4100), (2500, -40, 700, 3)]):
+        n = 16 * int(rng.integers(20000, 42000)) + int(rng.integers(0, 16))
+        x = H.random_speechlike(rng, n, min_span=800, max_span=60000)
+        r = emu.detect(x, 16000, W, th, keep, step)
+        assert r["silent"] == ps.detect_silence_fast(x, 16000, W, th, step), (trial, W, th, step)
+        assert r["nonsilent"] == ps.detect_nonsilent_fast(x, 16000, W, th, step), (trial, W, th, step)
+        assert r["kept"] == ps.kept_ranges_fast(x, 16000, W, th, keep, step), (trial, W, th, keep, step)
+
+
+@pytest.mark.parametrize("keep,pad,extra", [(0, 0, 37), (30, 480, 0)])
+def test_emu_pipeline_tc_fused_compaction(emu, keep, pad, extra, monkeypatch):
+    """the probe's gathering fetch + trimmed-PCM write-back on bursts of 120-300 ms (several kept ranges per tile)"""
+    monkeypatch.setenv("B2A_LM_IMPL", "tc")
+    test_emu_pipeline_fused_compaction_many_short_segments(emu, keep, pad, extra)

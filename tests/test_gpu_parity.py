@@ -347,7 +347,7 @@ def test_pipeline_tail_millisecond_follows_library_length(ops, T):
         for n in range(n0, n0 + 2000):
             old = -((-n * L) // M)
             new = ro.out_len(n, rate, 16000)
-            if old == new or not ((new % 16) < 8 <= (old % 16) or (old % 16) < 8 <= (new % 16)):
+            if old == new or ps.len_ms(new, 16000) == ps.len_ms(old, 16000):     # need: the extra sample changed pydub's clip length
                 continue
             found += 1
             t = np.arange(n) / rate
@@ -370,11 +370,11 @@ def test_pipeline_tail_millisecond_follows_library_length(ops, T):
     assert found >= 2
 
 
-def test_logmel_tensor_core_cases(ops, T):
-    """16-bit input = the tcgen05 kernel (csrc/logmel_tc.cuh): full-scale tone over a +-2 LSB noise floor (the worst
-    probed dynamic range of the f16-plane DFT), many tiles per persistent CTA with a partial last tile, batches with
-    whole-call and per-clip maxima, a row stride that breaks the 16-byte alignment of the bulk copies, a clip shorter
-    than one tile, zeros, transcribe's 30-second zero padding"""
+def test_logmel_s16_cases(ops, T):
+    """16-bit input (what the pipeline feeds: Whisper reads the WAV back as int16 / 32768): full-scale tone over a +-2 LSB
+    noise floor (the worst probed dynamic range), hundreds of tiles per persistent CTA with a partial last tile, batches
+    with whole-call and per-clip maxima, rows off the 16-byte grid, a clip shorter than one tile, zeros, transcribe's
+    30-second zero padding"""
     from oracle import whisper_logmel as wl
     rng = np.random.default_rng(7)
     n = 16000 * 3
@@ -401,9 +401,8 @@ def test_logmel_tensor_core_cases(ops, T):
     assert np.all(ops.log_mel(T.zeros(16000, dtype=T.int16, device="cuda"), 80).cpu().numpy() == -1.5)
 
 
-def test_pipeline_gather_window_overflow(ops, T):
-    """more than 32 kept ranges under one 128-frame tile: the producer's cached range window overflows and the rows
-    behind it take the per-sample path"""
+def test_pipeline_many_ranges_under_one_tile(ops, T):
+    """hundreds of 25 ms bursts: many kept ranges under every log-mel tile (the gathering tile loader's per-sample path)"""
     from oracle import pydub_silence as ps, whisper_logmel as wl
     rng = np.random.default_rng(8)
     parts = []

@@ -1,0 +1,18 @@
+"""Build tools/probes/_bin/libb2a_prof.so: the product sources with -DB2A_PROFILE (event traces, phase knobs, grid knobs).
+Never loaded by the package; tools/probes/*.py load it explicitly."""
+import os, subprocess, sys
+from concurrent.futures import ThreadPoolExecutor
+HERE = os.path.dirname(os.path.abspath(__file__)); ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from audio_processor_b200 import build as B
+OBJ = os.path.join(HERE, "_bin", "prof_obj"); LIB = os.path.join(HERE, "_bin", "libb2a_prof.so")
+os.makedirs(OBJ, exist_ok=True)
+B.gen_mel(); B.gen_mel_tc()
+def one(s):
+    obj = os.path.join(OBJ, s[:-3] + ".o")
+    r = subprocess.run([B._nvcc(), *B.NVCC_FLAGS, "-DB2A_PROFILE", "-I", os.path.join(ROOT, "include"), "-c", os.path.join(B.CSRC, s), "-o", obj], capture_output=True, text=True)
+    if r.returncode: raise RuntimeError(r.stderr)
+    return obj
+with ThreadPoolExecutor(8) as ex: objs = list(ex.map(one, B.SOURCES))
+subprocess.run([B._nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcudart"], check=True)
+print(LIB)

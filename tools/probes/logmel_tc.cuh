@@ -1,4 +1,13 @@
-// logmel_tc.cuh — Whisper log-mel of 16-bit PCM on the 5th-generation tensor cores (tcgen05 + TMEM + bulk TMA), sm_100a.
+// logmel_tc.cuh — Whisper log-mel of 16-bit PCM on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// PROBE, NOT IN THE RELEASE LIBRARY.  Round 2 built this kernel to replace the CUDA-core FFT (csrc/logmel.cu) for 16-bit
+// input; it is parity-green on hardware (all GPU log-mel / pipeline tests at <= 1e-4) but NOT faster: 178 us against 177 us
+// for the cfg2 clip's 288 000 frames, and 40 us slower inside b2a_pipeline (profiles/r02_logmel_tc.md has the timeline
+// and the reasons: the work around the MMAs - window, folds, f16 splits, the 201-bin epilogue - is 7.5 k thread instructions
+// per frame against 14 k for the FFT, but one CTA per SM of lockstep phases issues at half the FFT kernel's rate, and TMEM
+// (448 of 512 columns are accumulators) leaves no room to overlap the phases).  BASELINE.json's rule applies: tensor cores only
+// if the DFT-as-GEMM beats the FFT on measured evidence.  It is compiled into profiling builds (-DB2A_PROFILE,
+// tools/probes/build_profile_lib.py) and into the TEST-ONLY emulation library, selected there with B2A_LM_IMPL=tc.
 //
 // Replaces whisper.audio.log_mel_spectrogram (openai-whisper whisper/audio.py), reached from model.transcribe at
 // /root/reference/app/services/audio_processor.py:1076-1080, for every 16-bit input (the pipeline's case: Whisper reads the
@@ -45,8 +54,8 @@
 #pragma once
 #include <utility>
 
-#include "fir_tc_common.cuh"
-#include "fir_tmem.cuh"
+#include "../../audio_processor_b200/csrc/fir_tc_common.cuh"
+#include "../../audio_processor_b200/csrc/fir_tmem.cuh"
 
 namespace b2a {
 
@@ -87,7 +96,7 @@ static_assert(kTcSmemBytes <= 232448, "shared-memory budget (227 KB per CTA)");
 
 #ifndef B2A_MEL_TC_TABLES_INCLUDED
 #define B2A_MEL_TC_TABLES_INCLUDED
-#include "mel_tc_tables_gen.inc"
+#include "_bin/mel_tc_tables_gen.inc"
 #endif
 
 const unsigned char* get_logmel_tc_blob();           // device copy of the basis bank + window tables (b2a_host.cu)
@@ -257,6 +266,40 @@ __device__ __forceinline__ void tc_epi_role(TcEpi& e, unsigned tacc) {
     tc_epi_chunk<NM, R, 4>(e, tacc); tc_epi_chunk<NM, R, 5>(e, tacc); tc_epi_chunk<NM, R, 6>(e, tacc);
 }
 
+// ---- profiling builds only (-DB2A_PROFILE, tools/probes/logmel_tc_trace.py): CTA 0 records clock64 at pipeline events ----
+#if defined(B2A_PROFILE) && !defined(B2A_EMU)
+__device__ unsigned long long g_tc_trace[16384];      // [0] = records written; record = event << 56 | warp << 48 | clock
+#define TC_TRACE(ev)                                                                                              \
+    do {                                                                                                          \
+        if (blockIdx.x == 0 && lane == 0) {                                                                       \
+            const unsigned long long i_ = atomicAdd(&g_tc_trace[0], 1ull) + 1ull;                                  \
+            if (i_ < 16384ull) g_tc_trace[i_] = ((unsigned long long)(ev) << 56) | ((unsigned long long)warp << 48) | ((unsigned long long)clock64() & 0xffffffffffffull); \
+        }                                                                                                         \
+    } while (0)
+#else
+#define TC_TRACE(ev) do { } while (0)
+#endif
+
+// waits that usually last thousands of cycles (a whole phase of the tile) back off between polls, so that the waiting warps
+// do not take issue slots from the working ones
+#ifndef TC_WAIT_SLEEP
+#define TC_WAIT_SLEEP 0
+#endif
+#if TC_WAIT_SLEEP && !defined(B2A_EMU)
+__device__ __forceinline__ void mbar_wait_backoff(saddr_t bar, unsigned parity) {
+    unsigned ok;
+    for (;;) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) break;
+        __nanosleep(TC_WAIT_SLEEP);
+    }
+}
+#define TC_WAIT_LONG(bar, par) mbar_wait_backoff(bar, par)
+#else
+#define TC_WAIT_LONG(bar, par) mbar_wait(bar, par)
+#endif
+#define TC_WAIT(bar, par) mbar_wait(bar, par)
+
 // ---- the kernel ------------------------------------------------------------------------------------------------------
 // one 16-byte chunk that touches an edge of the padded clip (reflect at both ends, zeros past n_act, zero-filled last millisecond):
 // assembled sample by sample; out of line, it runs for a handful of chunks per clip
@@ -303,7 +346,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) logmel_tc_kernel(const LogMelTc
     const int n_seg = GATHER ? (int)p.info[B2A_INFO_N_KEPT] : 0;
 
     if (tid == 0) {
-        for (int i = 0; i < kTcNP; i++) { mbar_init(BAR(kTcBarFull + i), kTcWorkers); mbar_init(BAR(kTcBarFree + i), 1); }
+        mbar_init(BAR(kTcBarFull), kTcWorkers / 2);                     // one group of eight warps per k-step
+        mbar_init(BAR(kTcBarFree), 1);                                  // two "ring free" barriers, one per k-step parity: a converter
+        mbar_init(BAR(kTcBarFree + 1), 1);                              // skips every other k-step, so it must never be two phases behind one barrier
         mbar_init(BAR(kTcBarAccFull), 1);
         mbar_init(BAR(kTcBarAccFree), kTcWorkers);
         mbar_init(BAR(kTcBarRawFull), kTcWorkers);
@@ -342,13 +387,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) logmel_tc_kernel(const LogMelTc
         const unsigned b_lo0 = desc_start(s_base + kTcSmemBank) | ((unsigned)(kTcLbo >> 4) << 16);
         unsigned g = 0, it = 0;
         for (i64 work = blockIdx.x; work < n_work; work += gridDim.x, it++) {
-            if (it > 0) { mbar_wait(BAR(kTcBarAccFree), (it - 1) & 1u); tc_fence_after(); }
+            if (it > 0) { TC_WAIT_LONG(BAR(kTcBarAccFree), (it - 1) & 1u); tc_fence_after(); }
+            TC_TRACE(10);
 #pragma unroll 1
             for (int s = kTcKS - 1; s >= 0; s--, g++) {                // n = 96 .. 111 first (see the header: accumulation order)
+                mbar_wait(BAR(kTcBarFull), g & 1u);
+                tc_fence_after();
+                TC_TRACE(9);
 #pragma unroll
                 for (int pr = 0; pr < kTcNP; pr++) {
-                    mbar_wait(BAR(kTcBarFull + pr), g & 1u);
-                    tc_fence_after();
                     const unsigned d = tbase + (unsigned)(pr * kTcNB);
                     const unsigned ah = tbase + (unsigned)(kTcRingCol + 16 * pr), al = ah + 8u;
                     const unsigned bh = b_lo0 + (unsigned)(((2 * pr) * kTcPlaneBytes + 2 * s * kTcLbo) >> 4);
@@ -356,10 +403,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) logmel_tc_kernel(const LogMelTc
                     umma_ts_warp(d, ah, bh, b_hi, kTcIdesc, s < kTcKS - 1 ? 1u : 0u);
                     umma_ts_warp(d, ah, bl, b_hi, kTcIdesc, 1u);
                     umma_ts_warp(d, al, bh, b_hi, kTcIdesc, 1u);
-                    umma_commit_warp(BAR(kTcBarFree + pr));
                 }
+                umma_commit_warp(BAR(kTcBarFree + (g & 1u)));
             }
             umma_commit_warp(BAR(kTcBarAccFull));
+            TC_TRACE(11);
         }
     } else if (warp == kTcScout) {
         // ---------------- scout: kept ranges under the tiles this CTA will fetch, two fetches ahead ----------------
@@ -398,7 +446,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) logmel_tc_kernel(const LogMelTc
         }
     } else {
         // ---------------- workers ----------------
-        const int q = warp & 3, part = warp >> 2;
+        const int q = warp & 3, part = warp >> 2;                       // part: mel range of the epilogue
+        const int grp = part & 1, half = part >> 1;                     // conversion: k-step group and n-half (see the k-step loop)
         const int f = 32 * q + lane;                                    // frame (row) of the tile
         const int wt = warp * 32 + lane;                                // worker thread 0..511
         const unsigned tlane = tbase + ((unsigned)(32 * q) << 16);
@@ -425,6 +474,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) logmel_tc_kernel(const LogMelTc
             if (live) split_work(work, b, tile);
 
             // ---- fetch: where the next tile's chunks come from; their lines start moving into L2 while this tile is converted ----
+            TC_TRACE(1);
             if (have_next) {
                 int bn;
                 i64 tile_n;
@@ -474,60 +524,81 @@ __global__ void __launch_bounds__(kTcThreads, 1) logmel_tc_kernel(const LogMelTc
             }
 
             // ---- convert this tile ----
+            TC_TRACE(2);
             if (live) {
-                mbar_wait(BAR(kTcBarRawFull), it & 1u);
+                TC_WAIT_LONG(BAR(kTcBarRawFull), it & 1u);
+                TC_TRACE(3);
+                // Two groups of eight warps take the k-steps in turns (group = (warp / 4) % 2 converts the k-steps whose index g in
+                // issue order has its parity): while one group's operands sit in the ring and the tensor core consumes them, the
+                // other group is already computing the next k-step in registers, so the 4-slot ring no longer forces all sixteen
+                // warps through every k-step in lockstep (profiles/r02_logmel_tc.md: 2.0 k cycles per k-step before).
+                // Within a group a warp covers eight n-values: half = warp / 8 selects n = 16 s + 8 half .. + 7.
 #pragma unroll 1
                 for (int s = kTcKS - 1; s >= 0; s--, g++) {
-                    const int n0 = 16 * s + 4 * part;
-                    const int a1 = 196 - n0, b1 = 200 - n0, a2 = 396 - n0, b2 = 400 - n0;
-                    const uint2 f1 = lds64(rowp + (unsigned)(2 * n0));
-                    const uint2 f2 = lds64(rowp + (unsigned)(kTcRowBytes + 80 + 2 * n0));
-                    const uint2 r1 = lds64(rowp + (unsigned)(a1 >= 160 ? kTcRowBytes + 2 * (a1 - 160) : 2 * a1));
-                    const unsigned r1x = lds_u16(rowp + (unsigned)(b1 >= 160 ? kTcRowBytes + 2 * (b1 - 160) : 2 * b1));
-                    const uint2 r2 = lds64(rowp + (unsigned)(a2 >= 320 ? 2 * kTcRowBytes + 2 * (a2 - 320) : kTcRowBytes + 2 * (a2 - 160)));
-                    const unsigned r2x = lds_u16(rowp + (unsigned)(b2 >= 320 ? 2 * kTcRowBytes + 2 * (b2 - 320) : kTcRowBytes + 2 * (b2 - 160)));
-                    const float4 w1 = lds_f4(winp + (unsigned)(4 * (0 * 112 + n0)));
-                    const float4 w2 = lds_f4(winp + (unsigned)(4 * (1 * 112 + n0)));
-                    const float4 w3 = lds_f4(winp + (unsigned)(4 * (2 * 112 + n0)));
-                    const float4 w4 = lds_f4(winp + (unsigned)(4 * (3 * 112 + n0)));
-                    if (s == 0) {                                        // last read of the raw tile by this warp
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(BAR(kTcBarRawFree));
-                    }
-                    auto lo16 = [](unsigned v) -> float { return (float)(short)(v & 0xffffu); };
-                    auto hi16 = [](unsigned v) -> float { return (float)((int)v >> 16); };
-                    const float x1[4] = {lo16(f1.x), hi16(f1.x), lo16(f1.y), hi16(f1.y)};
-                    const float x2[4] = {lo16(f2.x), hi16(f2.x), lo16(f2.y), hi16(f2.y)};
-                    const float y1[4] = {(float)(short)r1x, hi16(r1.y), lo16(r1.y), hi16(r1.x)};     // x[200 - n0 - i]
-                    const float y2[4] = {(float)(short)r2x, hi16(r2.y), lo16(r2.y), hi16(r2.x)};     // x[400 - n0 - i]
-                    const float wa[4] = {w1.x, w1.y, w1.z, w1.w}, wb[4] = {w2.x, w2.y, w2.z, w2.w};
-                    const float wc[4] = {w3.x, w3.y, w3.z, w3.w}, wd[4] = {w4.x, w4.y, w4.z, w4.w};
-                    float v[kTcNP][4];
+                    if ((g & 1u) != (unsigned)grp) continue;            // the other group's k-step
+#ifndef TC_UNROLL_H
+#define TC_UNROLL_H 0
+#endif
+#if TC_UNROLL_H
 #pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const float t1 = wa[e] * x1[e], u1 = wc[e] * y1[e];
-                        const float ge = fmaf(wb[e], x2[e], t1), go = fmaf(-wb[e], x2[e], t1);
-                        const float he = fmaf(wd[e], y2[e], u1), ho = fmaf(-wd[e], y2[e], u1);
-                        v[0][e] = ge + he; v[1][e] = ge - he; v[2][e] = go - ho; v[3][e] = go + ho;
-                    }
+#else
+#pragma unroll 1
+#endif
+                    for (int h = 0; h < 2; h++) {
+                        const int n0 = 16 * s + 8 * half + 4 * h;
+                        const int a1 = 196 - n0, b1 = 200 - n0, a2 = 396 - n0, b2 = 400 - n0;
+                        const uint2 f1 = lds64(rowp + (unsigned)(2 * n0));
+                        const uint2 f2 = lds64(rowp + (unsigned)(kTcRowBytes + 80 + 2 * n0));
+                        const uint2 r1 = lds64(rowp + (unsigned)(a1 >= 160 ? kTcRowBytes + 2 * (a1 - 160) : 2 * a1));
+                        const unsigned r1x = lds_u16(rowp + (unsigned)(b1 >= 160 ? kTcRowBytes + 2 * (b1 - 160) : 2 * b1));
+                        const uint2 r2 = lds64(rowp + (unsigned)(a2 >= 320 ? 2 * kTcRowBytes + 2 * (a2 - 320) : kTcRowBytes + 2 * (a2 - 160)));
+                        const unsigned r2x = lds_u16(rowp + (unsigned)(b2 >= 320 ? 2 * kTcRowBytes + 2 * (b2 - 320) : kTcRowBytes + 2 * (b2 - 160)));
+                        const float4 w1 = lds_f4(winp + (unsigned)(4 * (0 * 112 + n0)));
+                        const float4 w2 = lds_f4(winp + (unsigned)(4 * (1 * 112 + n0)));
+                        const float4 w3 = lds_f4(winp + (unsigned)(4 * (2 * 112 + n0)));
+                        const float4 w4 = lds_f4(winp + (unsigned)(4 * (3 * 112 + n0)));
+                        auto lo16 = [](unsigned v) -> float { return (float)(short)(v & 0xffffu); };
+                        auto hi16 = [](unsigned v) -> float { return (float)((int)v >> 16); };
+                        const float x1[4] = {lo16(f1.x), hi16(f1.x), lo16(f1.y), hi16(f1.y)};
+                        const float x2[4] = {lo16(f2.x), hi16(f2.x), lo16(f2.y), hi16(f2.y)};
+                        const float y1[4] = {(float)(short)r1x, hi16(r1.y), lo16(r1.y), hi16(r1.x)};     // x[200 - n0 - i]
+                        const float y2[4] = {(float)(short)r2x, hi16(r2.y), lo16(r2.y), hi16(r2.x)};     // x[400 - n0 - i]
+                        const float wa[4] = {w1.x, w1.y, w1.z, w1.w}, wb[4] = {w2.x, w2.y, w2.z, w2.w};
+                        const float wc[4] = {w3.x, w3.y, w3.z, w3.w}, wd[4] = {w4.x, w4.y, w4.z, w4.w};
+                        float v[kTcNP][4];
 #pragma unroll
-                    for (int pr = 0; pr < kTcNP; pr++) {
-                        unsigned hw[2], lw[2];
-#pragma unroll
-                        for (int c = 0; c < 2; c++) {
-                            hw[c] = pack_f16x2(v[pr][2 * c], v[pr][2 * c + 1]);
-                            const float2 hf = unpack_f16x2(hw[c]);
-                            lw[c] = pack_f16x2(v[pr][2 * c] - hf.x, v[pr][2 * c + 1] - hf.y);
+                        for (int e = 0; e < 4; e++) {
+                            const float t1 = wa[e] * x1[e], u1 = wc[e] * y1[e];
+                            const float ge = fmaf(wb[e], x2[e], t1), go = fmaf(-wb[e], x2[e], t1);
+                            const float he = fmaf(wd[e], y2[e], u1), ho = fmaf(-wd[e], y2[e], u1);
+                            v[0][e] = ge + he; v[1][e] = ge - he; v[2][e] = go - ho; v[3][e] = go + ho;
                         }
-                        if (g > 0) { mbar_wait(BAR(kTcBarFree + pr), (g - 1) & 1u); tc_fence_after(); }
-                        const unsigned ts = tlane + (unsigned)(kTcRingCol + 16 * pr + 2 * part);
-                        tmem_st2(ts, hw[0], hw[1]);
-                        tmem_st2(ts + 8u, lw[0], lw[1]);
-                        tmem_st_wait();
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(BAR(kTcBarFull + pr));
+                        unsigned hw[kTcNP][2], lw[kTcNP][2];
+#pragma unroll
+                        for (int pr = 0; pr < kTcNP; pr++)
+#pragma unroll
+                            for (int c = 0; c < 2; c++) {
+                                hw[pr][c] = pack_f16x2(v[pr][2 * c], v[pr][2 * c + 1]);
+                                const float2 hf = unpack_f16x2(hw[pr][c]);
+                                lw[pr][c] = pack_f16x2(v[pr][2 * c] - hf.x, v[pr][2 * c + 1] - hf.y);
+                            }
+                        // the ring slots (one k-step: four products) are free once the tensor core has consumed the previous k-step
+                        if (h == 0 && g > 0) { TC_WAIT(BAR(kTcBarFree + ((g - 1) & 1u)), ((g - 1) >> 1) & 1u); tc_fence_after(); }
+#pragma unroll
+                        for (int pr = 0; pr < kTcNP; pr++) {
+                            const unsigned ts = tlane + (unsigned)(kTcRingCol + 16 * pr + 4 * half + 2 * h);
+                            tmem_st2(ts, hw[pr][0], hw[pr][1]);
+                            tmem_st2(ts + 8u, lw[pr][0], lw[pr][1]);
+                        }
                     }
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(BAR(kTcBarFull));
+                        if (s <= 1) mbar_arrive(BAR(kTcBarRawFree));     // this warp's last k-step of the tile (s = 0, or s = 1 for the other group)
+                    }
+                    TC_TRACE(4);
                 }
             }
 
@@ -535,13 +606,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) logmel_tc_kernel(const LogMelTc
             if (have_next) {
                 uint4 v[kTcChunkRounds];
 #pragma unroll
-                for (int r = 0; r < kTcChunkRounds; r++) {
-                    const int c = wt + kTcWorkerThreads * r;
+                for (int r = 0; r < kTcChunkRounds; r++) {                     // all loads first (L2 hits), no call in between
                     v[r] = make_uint4(0u, 0u, 0u, 0u);
                     if ((src_mask >> r) & 1u) v[r] = ldg_nc16(p.audio + ((size_t)pre_off[r] << 3));
-                    else if ((edge_mask >> r) & 1u) v[r] = tc_edge_chunk<GATHER>(p, pre_row, pre_q0 + 8 * c, n_act, ltot, n_seg);
                 }
-                if (live) mbar_wait(BAR(kTcBarRawFree), it & 1u);
+                if (edge_mask) {
+#pragma unroll
+                    for (int r = 0; r < kTcChunkRounds; r++)
+                        if ((edge_mask >> r) & 1u) v[r] = tc_edge_chunk<GATHER>(p, pre_row, pre_q0 + 8 * (wt + kTcWorkerThreads * r), n_act, ltot, n_seg);
+                }
+                TC_TRACE(5);
+                if (live) TC_WAIT_LONG(BAR(kTcBarRawFree), it & 1u);
+                TC_TRACE(6);
 #pragma unroll
                 for (int r = 0; r < kTcChunkRounds; r++) {
                     const int c = wt + kTcWorkerThreads * r;
@@ -557,9 +633,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) logmel_tc_kernel(const LogMelTc
             }
 
             // ---- epilogue of this tile ----
+            TC_TRACE(7);
             if (live) {
-                mbar_wait(BAR(kTcBarAccFull), it & 1u);
+                TC_WAIT_LONG(BAR(kTcBarAccFull), it & 1u);
                 tc_fence_after();
+                TC_TRACE(8);
                 const i64 t = tile * kTcFrames + f;
                 TcEpi e;
                 e.a0 = 0.0f; e.a1 = 0.0f; e.lmax = -3.0e38f; e.lmin = 3.0e38f;
@@ -573,6 +651,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) logmel_tc_kernel(const LogMelTc
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(kTcBarAccFree));
+                TC_TRACE(12);
                 // clip maximum and the minimum of this 32-frame group (lets the floor pass skip groups above the floor)
                 const float gmin = warp_reduce_min_f(e.valid ? e.lmin : 3.0e38f);
                 if (e.valid) run_max = fmaxf(run_max, e.lmax * 0.30102999566398120f);
