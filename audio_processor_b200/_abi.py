@@ -32,6 +32,14 @@ class SilenceParams(C.Structure):
 
 P = C.c_void_p
 
+
+class ClipDesc(C.Structure):
+    """b2a_clip_desc (include/b2a.h)"""
+    _fields_ = [("d_in", C.c_void_p), ("fmt", C.c_int32), ("channels", C.c_int32), ("in_rate", C.c_int32), ("reserved", C.c_int32),
+                ("n_in", C.c_int64), ("d_pcm_out", C.c_void_p), ("d_mel_out", C.c_void_p), ("d_nonsilent_ms", C.c_void_p),
+                ("d_kept_ms", C.c_void_p), ("d_info", C.c_void_p), ("d_ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
+
+
 SIGNATURES = {
     "b2a_version": (C.c_int, []),
     "b2a_last_error": (C.c_char_p, []),
@@ -53,6 +61,7 @@ SIGNATURES = {
                               C.c_size_t, P]),
     "b2a_mel_windows": (C.c_int, [P, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, P, P]),
     "b2a_mel_filters": (C.c_int, [C.c_int, P, C.c_size_t]),
+    "b2a_pipeline_batch": (C.c_int, [C.POINTER(ClipDesc), C.c_int, C.POINTER(SilenceParams), C.c_int, C.c_int64, C.c_int32, P]),
     "b2a_kept_offsets": (C.c_int, [P, P, C.c_int, C.c_int32, P, P]),
     "b2a_remap_times": (C.c_int, [P, C.c_int64, P, P, P, C.c_int, P, P]),
     "b2a_pipeline_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int64, C.c_int32]),

@@ -6,6 +6,8 @@
 // N_KEEP slot of d_info, so nothing waits for the host between stages.
 #include "b2a_common.cuh"
 
+#include <mutex>
+
 namespace b2a {
 
 int resample_launch(const void* d_in, int fmt, int channels, int in_rate, i64 n_in, int out_rate, int16_t* d_out_s16,
@@ -94,9 +96,69 @@ int pipeline_launch(const void* d_in, int fmt, int channels, int in_rate, i64 n_
                          d_mel_out, d_info + B2A_INFO_N_FRAMES, ws_logmel, ws_logmel_bytes, stream, &g);
 }
 
+// ---- many clips per call: fork / join over a small pool of internal streams --------------------------------------
+constexpr int kBatchLanes = 4;             // clip i runs on lane i % 4; lane 0 is the caller's stream
+struct BatchPool {
+    cudaStream_t side[kBatchLanes - 1];
+    cudaEvent_t fork, join[kBatchLanes - 1];
+    bool ready;
+};
+static std::mutex g_batch_mu;
+static BatchPool g_batch_pool[64];        // per device
+
+static BatchPool* batch_pool() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    BatchPool* bp = &g_batch_pool[dev];
+    if (!bp->ready) {
+        for (int i = 0; i < kBatchLanes - 1; i++) {
+            if (cudaStreamCreateWithFlags(&bp->side[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&bp->join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        }
+        if (cudaEventCreateWithFlags(&bp->fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        bp->ready = true;
+    }
+    return bp;
+}
+
+int pipeline_batch_launch(const b2a_clip_desc* clips, int n_clips, const b2a_silence_params* prm, int n_mels, i64 padding, int cap,
+                          cudaStream_t stream) {
+    if (n_clips < 0 || (n_clips > 0 && !clips)) { set_error("pipeline_batch: bad clip list"); return B2A_EINVAL; }
+    auto one = [&](const b2a_clip_desc& c, cudaStream_t s) {
+        return pipeline_launch(c.d_in, c.fmt, c.channels, c.in_rate, c.n_in, prm, n_mels, padding, cap, c.d_pcm_out, c.d_mel_out,
+                               c.d_nonsilent_ms, c.d_kept_ms, (i64*)c.d_info, c.d_ws, c.ws_bytes, s);
+    };
+    if (n_clips <= 1) return n_clips == 1 ? one(clips[0], stream) : B2A_OK;
+    // the pool (and its fork / join events) is shared by every caller on this device: enqueue under the lock
+    std::lock_guard<std::mutex> lk(g_batch_mu);
+    BatchPool* bp = batch_pool();
+    if (!bp) { set_error("pipeline_batch: cannot create the internal streams"); return B2A_ECUDA; }
+    const int lanes = n_clips < kBatchLanes ? n_clips : kBatchLanes;
+    cudaError_t e = cudaEventRecord(bp->fork, stream);
+    for (int l = 1; l < lanes && e == cudaSuccess; l++) e = cudaStreamWaitEvent(bp->side[l - 1], bp->fork, 0);
+    if (e != cudaSuccess) return cuda_fail(e, "pipeline_batch: fork");
+    int rc = B2A_OK;
+    for (int i = 0; i < n_clips && rc == B2A_OK; i++) {
+        const int l = i % lanes;
+        rc = one(clips[i], l == 0 ? stream : bp->side[l - 1]);
+    }
+    // always join, also after an error: the caller's stream must not run ahead of work already enqueued on the side streams
+    for (int l = 1; l < lanes; l++) {
+        e = cudaEventRecord(bp->join[l - 1], bp->side[l - 1]);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, bp->join[l - 1], 0);
+        if (e != cudaSuccess && rc == B2A_OK) rc = cuda_fail(e, "pipeline_batch: join");
+    }
+    return rc;
+}
+
 }  // namespace b2a
 
 extern "C" {
+
+int b2a_pipeline_batch(const b2a_clip_desc* clips, int n_clips, const b2a_silence_params* params, int n_mels, int64_t padding,
+                       int32_t cap, b2a_stream_t stream) {
+    return b2a::pipeline_batch_launch(clips, n_clips, params, n_mels, padding, cap, (cudaStream_t)stream);
+}
 
 size_t b2a_pipeline_workspace_bytes(int64_t n_in, int in_rate, int64_t padding, int32_t cap) {
     if (n_in <= 0 || in_rate <= 0 || padding < 0 || cap <= 0) return 0;

@@ -333,6 +333,72 @@ class PipelinePlan:
         return PipelineResult(self)
 
 
+class PipelineBatch:
+    """A rank's shard of clips through ONE b2a_pipeline_batch call per pass (one CUDA-graph replay with graph=True).
+
+    ``plans[i]`` holds clip i's buffers (clips may differ in length, rate and channel count; n_mels, padding and cap are
+    shared).  The library forks the clips over its internal streams and joins them back into the current stream."""
+
+    def __init__(self, plans: List["PipelinePlan"]):
+        if not plans:
+            raise ValueError("PipelineBatch needs at least one plan")
+        p0 = plans[0]
+        for p in plans:
+            if (p.n_mels, p.padding, p.cap, p.device) != (p0.n_mels, p0.padding, p0.cap, p0.device):
+                raise ValueError("plans of one batch share n_mels, padding, cap and device")
+        self.plans = plans
+        self.torch = p0.torch
+        self._graphs = {}
+        self._warm = set()
+
+    def run(self, inputs, *, trim: bool = True, min_silence_len: int = 1000, silence_thresh: float = -40,
+            keep_silence: Union[int, bool] = 200, seek_step: int = 1, graph: bool = False) -> List["PipelineResult"]:
+        global _graph_launches
+        torch = self.torch
+        if len(inputs) != len(self.plans):
+            raise ValueError("one input per plan")
+        descs = (_abi.ClipDesc * len(inputs))()
+        for d, p, x in zip(descs, self.plans, inputs):
+            if (not x.is_cuda) or x.dtype != p.dtype or not x.is_contiguous() or int(x.shape[0]) != p.n_in:
+                raise ValueError("every input must be a contiguous CUDA tensor of its plan's shape and dtype")
+            d.d_in, d.fmt, d.channels, d.in_rate, d.n_in = x.data_ptr(), p.fmt, p.channels, p.in_rate, p.n_in
+            d.d_pcm_out, d.d_mel_out = p.pcm.data_ptr(), p.mel.data_ptr()
+            d.d_nonsilent_ms, d.d_kept_ms, d.d_info = p.nonsilent.data_ptr(), p.kept.data_ptr(), p.info.data_ptr()
+            d.d_ws, d.ws_bytes = p._ws_ptr.value, p.ws_bytes
+        prm = _params(min_silence_len, silence_thresh, keep_silence, seek_step) if trim else None
+        p0 = self.plans[0]
+
+        def launch():
+            check(lib().b2a_pipeline_batch(descs, len(inputs), C.byref(prm) if prm is not None else None, p0.n_mels, p0.padding,
+                                           p0.cap, _stream(torch)))
+
+        with torch.cuda.device(p0.device):
+            if not graph:
+                launch()
+            else:
+                key = tuple(x.data_ptr() for x in inputs) + (bool(trim),) + \
+                    ((prm.min_silence_len, prm.keep_silence, prm.seek_step, prm.silence_thresh) if prm is not None else ())
+                g = self._graphs.get(key)
+                if g is None and key not in self._warm:      # first use: eager (device tables, kernel attributes, internal streams)
+                    self._warm.add(key)
+                    launch()
+                else:
+                    if g is None:
+                        g = torch.cuda.CUDAGraph()
+                        cap_stream = torch.cuda.Stream(device=p0.device)
+                        cap_stream.wait_stream(torch.cuda.current_stream())
+                        n0 = int(lib().b2a_launch_count())
+                        with torch.cuda.graph(g, stream=cap_stream, capture_error_mode="thread_local"):
+                            launch()
+                        torch.cuda.current_stream().wait_stream(cap_stream)
+                        g = (g, int(lib().b2a_launch_count()) - n0)
+                        self._graphs[key] = g
+                        _graph_launches -= g[1]
+                    g[0].replay()
+                    _graph_launches += g[1]
+        return [PipelineResult(p) for p in self.plans]
+
+
 class PipelineResult:
     """View over a PipelinePlan's output buffers (valid until the plan runs again)."""
 

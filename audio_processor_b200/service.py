@@ -59,7 +59,7 @@ class AudioFrontend:
         output_filename = f"{os.path.splitext(os.path.basename(input_path))[0]}.wav"
         output_path = os.path.join(output_dir, output_filename)
         try:
-            pcm, rate = wavio.read_wav(input_path)
+            pcm, rate = wavio.read_audio(input_path)           # WAV parsed here; m4a / mp3 / ... decoded on the host by libavcodec
             s16, _, _ = ops.resample(self._to_device(pcm), rate, ops.SAMPLE_RATE)
             wavio.write_wav_s16(output_path, s16.cpu().numpy(), ops.SAMPLE_RATE)
             logging.info(f"✅ 檔案轉換完成: {output_filename}")
@@ -83,10 +83,10 @@ class AudioFrontend:
             audio_path = self.convert_to_wav(audio_path)
         if not self.strip_silence:
             return audio_path, []
-        pcm, rate = wavio.read_wav(audio_path)
+        pcm, rate = wavio.read_audio(audio_path)
         if rate != ops.SAMPLE_RATE or pcm.ndim != 1 or pcm.dtype != np.int16:
             audio_path = self.convert_to_wav(audio_path)
-            pcm, rate = wavio.read_wav(audio_path)
+            pcm, rate = wavio.read_audio(audio_path)
         dev = self._to_device(pcm)
         res = ops.detect(dev, rate, self.min_silence_len, self.silence_thresh, self.keep_silence, self.seek_step)
         kept = res.kept

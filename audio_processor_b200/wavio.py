@@ -26,7 +26,7 @@ def read_wav(path: str) -> Tuple[np.ndarray, int]:
     with open(path, "rb") as f:
         data = f.read()
     if len(data) < 12 or data[0:4] != b"RIFF" or data[8:12] != b"WAVE":
-        raise UnsupportedAudio(f"{path}: not a RIFF/WAVE file (compressed containers need a decoder; out of scope)")
+        raise UnsupportedAudio(f"{path}: not a RIFF/WAVE file")
     pos = 12
     fmt = None
     payload = None
@@ -73,3 +73,20 @@ def write_wav_s16(path: str, samples: np.ndarray, sample_rate: int = 16000) -> N
     with open(path, "wb") as f:
         f.write(hdr)
         f.write(payload)
+
+
+def read_audio(path: str) -> Tuple[np.ndarray, int]:
+    """Any input the service accepts -> (PCM [n] or [n, C] as int16 or float32, sample_rate).
+
+    WAV (s16 / s24 / f32) is parsed here; everything else — the m4a / mp3 downloads ``process_audio`` hands to
+    ``convert_to_wav`` (/root/reference/app/services/audio_processor.py:1040-1044), flac, ogg, WAV flavours this parser does
+    not know — is demuxed and decoded on the host by the bundled libavformat / libavcodec (avdecode.py), as the reference's
+    ``ffmpeg -i`` does (:912-920).  Resampling, downmix and quantisation stay on the GPU."""
+    try:
+        return read_wav(path)
+    except UnsupportedAudio as wav_err:
+        from . import avdecode
+        try:
+            return avdecode.decode_audio(path)
+        except avdecode.DecodeError as e:
+            raise UnsupportedAudio(f"{wav_err}; decoder: {e}") from e

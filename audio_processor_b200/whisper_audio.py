@@ -29,10 +29,11 @@ TOKENS_PER_SECOND = SAMPLE_RATE // N_SAMPLES_PER_TOKEN
 def load_audio(file: str, sr: int = SAMPLE_RATE) -> np.ndarray:
     """whisper.audio.load_audio: file -> mono float32 waveform at ``sr`` in [-1, 1].
 
-    whisper shells out to ``ffmpeg -i file -f s16le -ac 1 -acodec pcm_s16le -ar sr -``; here the WAV is parsed on
-    the host and downmix + resampling + s16 quantisation run on the GPU, then ``/ 32768.0`` as whisper does."""
+    whisper shells out to ``ffmpeg -i file -f s16le -ac 1 -acodec pcm_s16le -ar sr -``; here the file is parsed (WAV) or
+    decoded (m4a, mp3, flac, ...: bundled libavcodec, avdecode.py) on the host and downmix + resampling + s16 quantisation
+    run on the GPU, then ``/ 32768.0`` as whisper does."""
     torch = ops.require_cuda()
-    pcm, rate = wavio.read_wav(file)
+    pcm, rate = wavio.read_audio(file)
     s16, _, _ = ops.resample(pcm, rate, sr)
     return (s16.to(torch.float32) / 32768.0).cpu().numpy()
 

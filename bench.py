@@ -11,7 +11,8 @@ One JSON line on rank 0.  A "step" = one pass of the hot path over one batch of 
     cfg2 (default)  1 x 1-hour 44.1 kHz stereo s16 clip per GPU -> 16 kHz mono + trim + 80-mel   (configs[1])
     cfg1            1 x 60 s 16 kHz mono s16 clip -> trim + 80-mel                                  (configs[0])
     cfg3            [4096, 480000] f32 chunks -> 128-mel, log-mel only                               (configs[2])
-    cfg4            8 x 600 s 48 kHz stereo s16 clips per GPU, ~50 % silence -> full path            (configs[3])
+    cfg4            64 x 600 s 48 kHz stereo s16 clips, ~50 % silence, sharded over the GPUs -> full path (configs[3]; strong scaling)
+    cfg5            128 x 1-hour 44.1 kHz stereo clips RESIDENT per GPU (1024 on 8 GPUs), full path      (configs[4]; the default for --gpus > 1)
 
 Scaling is weak: every rank processes its own clips (sharded by clip, no collective on the data path);
 `value` = audio-hours all ranks processed / max-over-ranks device time.
@@ -49,7 +50,8 @@ WORKLOADS = {
     # name: (description, in_rate, channels, seconds per clip, silence fraction, clips per GPU, n_mels, seed)
     "cfg1": ("1 x 60 s 16 kHz mono s16 clip: trim + 80-mel", 16000, 1, 60.0, 0.25, 1, 80, 1),
     "cfg2": ("1 x 1-hour 44.1 kHz stereo s16 clip per GPU: resample to 16 kHz mono + trim + 80-mel", 44100, 2, 3600.0, 0.20, 1, 80, 2),
-    "cfg4": ("8 x 600 s 48 kHz stereo s16 clips per GPU, ~50% silence: resample + trim + 80-mel", 48000, 2, 600.0, 0.50, 8, 80, 4),
+    "cfg4": ("64 x 600 s 48 kHz stereo s16 clips (~50% silence) sharded by clip over the GPUs: resample + trim + 80-mel", 48000, 2, 600.0, 0.50, 64, 80, 4),
+    "cfg5": ("128 x 1-hour 44.1 kHz stereo s16 clips resident per GPU (1024 over 8 GPUs), sharded by clip: resample + trim + 80-mel", 44100, 2, 3600.0, 0.20, 128, 80, 5),
     "cfg3": ("[4096, 480000] f32 30-s chunks per GPU: 128-mel log-mel only (Whisper large-v3 front-end)", 16000, 1, 30.0, 0.0, 4096, 128, 3),
 }
 
@@ -253,9 +255,26 @@ def run_b200(args):
             os.dup2(saved, 1)
             os.close(saved)
     desc, in_rate, ch, secs, sil, clips, n_mels, seed = WORKLOADS[args.workload]
-    if args.clips:
-        clips = args.clips
+    scaling = "weak"
+    if args.workload == "cfg4":
+        # 64 clips in total, sharded by clip with the duration-balanced packer (strong scaling over 1 / 2 / 4 GPUs)
+        from audio_processor_b200 import sharding as _sh
+        total_clips = args.clips or clips
+        mine = _sh.shard_clips([secs] * total_clips, world)[rank]
+        clip_ids = list(mine)
+        clips = len(clip_ids)
+        scaling = "strong"
+    elif args.workload == "cfg5":
+        from audio_processor_b200 import sharding as _sh
+        per_gpu = args.clips or clips                    # 128 one-hour clips resident per GPU (weak scaling: 1024 on 8 GPUs)
+        clip_ids = list(_sh.shard_clips([secs] * (per_gpu * world), world)[rank])
+        clips = len(clip_ids)
+    else:
+        if args.clips:
+            clips = args.clips
+        clip_ids = [rank * clips + i for i in range(clips)]
     logmel_only = args.workload == "cfg3"
+    batched = (not logmel_only) and clips > 1            # one b2a_pipeline_batch call (one CUDA-graph replay) per pass
     peak, peak_src = measured_peak()
 
     def barrier():
@@ -291,21 +310,26 @@ def run_b200(args):
         def algo_bytes():
             return in_bytes + out_holder["mel"].numel() * 4
     else:
-        inputs = [synth.synth_clip(seed + 100 * rank + i, in_rate, ch, secs, sil, device=dev) for i in range(clips)]
+        inputs = [synth.synth_clip(seed * 1000 + cid, in_rate, ch, secs, sil, device=dev) for cid in clip_ids]
         in_bytes = sum(t.numel() * 2 for t in inputs)
         audio_h = clips * secs / 3600.0
-        # `inflight` independent clip pipelines: consecutive passes alternate between them (own output buffers, own
-        # stream), so the latency-bound tail of one clip (silence ranges, compaction) overlaps the next clip's FIR —
-        # the way a worker pool keeps several clips in flight per GPU.  Every pass still does all of its work.
-        inflight = max(1, args.inflight)
-        use_graphs = not args.no_graphs                  # each clip's 8 launches replayed as one CUDA graph (same b2a_pipeline call)
+        # Single-clip workloads: `inflight` independent clip pipelines, consecutive passes alternate between them (own output
+        # buffers, own stream), so the latency-bound tail of one pass overlaps the next pass's FIR - the way a worker pool
+        # keeps several clips in flight per GPU.  Multi-clip workloads: ONE b2a_pipeline_batch call per pass; the library
+        # forks the clips over its internal streams.  Every pass does all of its work.
+        inflight = 1 if batched else max(1, args.inflight)
+        use_graphs = not args.no_graphs                  # a pass = one CUDA-graph replay of the same C-ABI call
         plan_sets = [[ops.PipelinePlan(int(t.shape[0]), in_rate, ch, t.dtype, n_mels=n_mels, padding=0, device=dev) for t in inputs]
                      for _ in range(inflight)]
         plans = plan_sets[0]
+        batch = ops.PipelineBatch(plans) if batched else None
         side = [torch.cuda.Stream(device=dev) for _ in range(inflight)] if inflight > 1 else []
         state = {"n": 0}
 
         def step():
+            if batched:
+                batch.run(inputs, graph=use_graphs, **SIL)
+                return
             slot = state["n"] % inflight
             state["n"] += 1
             if inflight == 1:
@@ -322,6 +346,9 @@ def run_b200(args):
             for _ in range(2 * inflight):
                 step()
             torch.cuda.synchronize()
+        mem_gb = torch.cuda.max_memory_allocated(dev) / 1e9
+        if mem_gb > 180.0:
+            raise RuntimeError(f"{mem_gb:.1f} GB of device memory: the shard does not fit a B200's 180 GB")
 
         def fork(ev):                                    # side streams start after the start event ...
             for sd in side:
@@ -377,8 +404,7 @@ def run_b200(args):
         for p in plans:
             nk = int(p.info[_abi.INFO_N_KEPT].item())
             tables.append(p.kept[:nk].cpu().tolist())
-        ids = [rank * clips + i for i in range(clips)]
-        allt = sharding.gather_segment_tables(ids, tables, cap=plans[0].cap, device=dev)
+        allt = sharding.gather_segment_tables(clip_ids, tables, cap=plans[0].cap, device=dev)
         gathered = {"clips": len(allt), "segments": int(sum(len(t) for _, t in allt))}
 
     # ---- per-stage device times (same stream, CUDA events) -> the dominant kernel for the roofline ----
@@ -434,7 +460,7 @@ def run_b200(args):
         top = max(stages, key=lambda k: stages[k])
         fir_name = ("fir_tmem_kernel (+ fir_mma_kernel behind the last span)" if ch == 2 else "fir_mma_kernel (+ resample_generic_kernel for the clip edges)")
         kname = {"resample+downmix+energy": fir_name if in_rate in (44100, 48000) else "passthrough_kernel",
-                 "silence ranges": "cover_kernel", "compaction": "compact_kernel", "log-mel": "stft_mel_kernel"}[top]
+                 "silence ranges": "silence_kernel", "compaction": "compact_kernel", "log-mel": "stft_mel_kernel"}[top]
         roof = dict(kernel=kname, stage=top, bytes=stage_bytes[top], ms=stages[top],
                     per_stage={k: dict(algorithmic_bytes=int(stage_bytes[k]), ms=stages[k]) for k in stages})
 
@@ -457,9 +483,12 @@ def run_b200(args):
             e2e_audio_h = rows * 30.0 / 3600.0
         else:
             fe = AudioFrontend(n_mels=n_mels, device=str(dev), **SIL)
-            hin = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in inputs]
-            for h, t in zip(hin, inputs):
+            n_host = min(len(inputs), 2)                 # bounded pinned footprint: at most two distinct host clips, cycled
+            hbuf = [torch.empty(inputs[i].shape, dtype=inputs[i].dtype).pin_memory() for i in range(n_host)]
+            for h, t in zip(hbuf, inputs):
                 h.copy_(t)
+            e2e_clips = min(len(inputs), args.e2e_clips) if args.e2e_clips else len(inputs)
+            hin = [hbuf[i % n_host] for i in range(e2e_clips)]
             # the public pipelined API: ClipStream.submit() uploads + runs, result() downloads trimmed PCM + mel + tables
             # into pinned host buffers; depth 2 keeps the next upload in flight while the previous clip is collected
             cs = fe.stream(int(inputs[0].shape[0]), in_rate, ch, inputs[0].dtype, padding=0, depth=2)
@@ -483,8 +512,8 @@ def run_b200(args):
                     tk = pending.pop(0)
                     cs.result(tk)
                     last["tk"] = tk
-            e2e_audio_h = audio_h
-        for _ in range(3):
+            e2e_audio_h = audio_h * len(hin) / max(len(inputs), 1)
+        for _ in range(3 if not batched else 1):
             bi, bo = e2e_step()
         if not logmel_only:
             e2e_drain()                # the timed region starts with nothing in flight
@@ -499,8 +528,29 @@ def run_b200(args):
         if not logmel_only:
             b1, b2 = cs.bytes_per_clip(last["tk"])
             bi, bo = b1 * len(hin), b2 * len(hin)
+        # the ceiling the host can feed: every rank copies pinned host memory to its GPU at the same time (plain cudaMemcpyAsync
+        # loop, nothing else running); e2e is input-bound, so its H2D rate over this ceiling says how much the API leaves unused
+        hc = torch.empty(512 << 20, dtype=torch.uint8).pin_memory()
+        dc = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+        for _ in range(3):
+            dc.copy_(hc, non_blocking=True)
+        barrier()
+        ce0, ce1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ce0.record()
+        for _ in range(16):
+            dc.copy_(hc, non_blocking=True)
+        ce1.record()
+        torch.cuda.synchronize()
+        h2d_local = 16 * (512 << 20) / (ce0.elapsed_time(ce1) * 1e-3) / 1e9
+        barrier()
+        h2d_sum = sum_over_ranks(h2d_local)
+        del hc, dc
+        e2e_h2d_rate = sum_over_ranks(float(bi)) * e2e_steps / (dt_ms / 1e3) / 1e9
         e2e = {"value": sum_over_ranks(e2e_audio_h) * e2e_steps / (dt_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(bi),
                "d2h_bytes_per_step": int(bo), "ms_per_step": dt_ms / e2e_steps, "steps": e2e_steps,
+               "h2d_ceiling_gbs": round(h2d_sum, 2), "h2d_achieved_gbs": round(e2e_h2d_rate, 2),
+               "frac_of_h2d_ceiling": round(e2e_h2d_rate / h2d_sum, 3) if h2d_sum > 0 else None,
+               "h2d_ceiling_note": "all ranks copying 512 MB pinned buffers to their GPUs concurrently (16 x cudaMemcpyAsync, CUDA events), summed over ranks",
                "api": "whisper_audio.log_mel_spectrogram(host)" if logmel_only else "AudioFrontend.stream(...).submit(host pcm) / result(): 2 clips in flight"}
     t_load1 = time.time()
     clocks = sampler.stop(t_load0, t_load1) if sampler else None
@@ -533,10 +583,12 @@ def run_b200(args):
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "f32 (s16 PCM in/out, exact int64 silence energies)", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "clips_per_gpu": clips, "audio_hours_per_step": total_audio_h,
-                       "clip_pipelines_in_flight": 1 if logmel_only else max(1, args.inflight),
+                       "clip_pipelines_in_flight": 1 if (logmel_only or batched) else max(1, args.inflight),
+                       "batched_call": "b2a_pipeline_batch: all clips of the rank in one call (4 internal stream lanes)" if batched else None,
+                       "device_memory_gb": None if logmel_only else round(mem_gb, 1),
                        "cuda_graphs": False if logmel_only else (not args.no_graphs),
                        "silence": None if logmel_only else SIL, "n_mels": n_mels,
                        "l2": f"inputs larger than L2 ({in_bytes / 1e6:.0f} MB per GPU per step vs 126 MB), no flush needed"
@@ -578,15 +630,19 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="default: cfg2 on one GPU (the configuration the metric is quoted on), cfg5 on several")
     ap.add_argument("--clips", type=int, default=0, help="override clips per GPU")
     ap.add_argument("--no-graphs", action="store_true", help="enqueue every b2a_pipeline call directly instead of replaying its CUDA graph")
     ap.add_argument("--inflight", type=int, default=2, help="clip pipelines in flight per GPU (device-resident timing)")
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-clips", type=int, default=16, help="clips per end-to-end step for multi-clip workloads (0 = all)")
     ap.add_argument("--cpu-sample-s", type=float, default=300.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    if args.workload is None:
+        args.workload = "cfg2" if int(os.environ.get("WORLD_SIZE", str(args.gpus))) <= 1 and args.gpus <= 1 else "cfg5"
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)

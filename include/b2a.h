@@ -185,6 +185,32 @@ int b2a_pipeline(const void* d_in, int fmt, int channels, int in_rate, int64_t n
                  int16_t* d_pcm_out, float* d_mel_out, int32_t* d_nonsilent_ms, int32_t* d_kept_ms,
                  int64_t* d_info, void* d_ws, size_t ws_bytes, b2a_stream_t stream);
 
+/* Many clips in one call (a rank's shard of a corpus: SURVEY.md section 8(b) "batched clip descriptors").  `clips` is a HOST
+ * array; every clip brings its own outputs and workspace (b2a_pipeline_workspace_bytes for its n_in), all clips share
+ * the silence parameters, n_mels, padding and cap.  The clips are independent problems: the library spreads them over
+ * a small pool of internal streams forked from and joined back into `stream` (created once per device on first use,
+ * like the tables), so the latency-bound stages of one clip (silence ranges, the log-mel floor pass) overlap the
+ * bandwidth-bound stages of its neighbours.  Capturable into a CUDA graph on `stream` after one eager call.
+ * Results are identical to n_clips calls of b2a_pipeline. */
+typedef struct b2a_clip_desc {
+    const void* d_in;        /* [n_in, channels] interleaved PCM */
+    int32_t fmt;             /* B2A_FMT_S16 / B2A_FMT_F32 */
+    int32_t channels;
+    int32_t in_rate;
+    int32_t reserved;
+    int64_t n_in;
+    int16_t* d_pcm_out;      /* as b2a_pipeline */
+    float* d_mel_out;
+    int32_t* d_nonsilent_ms;
+    int32_t* d_kept_ms;
+    int64_t* d_info;
+    void* d_ws;
+    size_t ws_bytes;
+} b2a_clip_desc;
+
+int b2a_pipeline_batch(const b2a_clip_desc* clips, int n_clips, const b2a_silence_params* params, int n_mels,
+                       int64_t padding, int32_t cap, b2a_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Timestamps on the silence-stripped timeline -> the original recording: what the speaker-overlap loop of
  * process_audio (/root/reference/app/services/audio_processor.py:1114-1145) needs once preprocess_audio

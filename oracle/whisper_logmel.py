@@ -131,3 +131,31 @@ def log_mel_spectrogram(audio, n_mels: int = 80, padding: int = 0, dtype=torch.f
         log_spec = torch.maximum(log_spec, log_spec.max() - 8.0)
     log_spec = (log_spec + 4.0) / 4.0
     return log_spec
+
+
+def encoder_windows(mel: np.ndarray, n_frames: int = N_FRAMES, *, content_frames=None, seek0: int = 0, stride=None,
+                    n_windows=None, dtype=np.float32) -> np.ndarray:
+    """The windows ``whisper.transcribe`` feeds the encoder, restated in numpy (whisper/transcribe.py main loop):
+
+        content_frames = mel.shape[-1] - N_FRAMES            # the mel was computed with padding = N_SAMPLES
+        while seek < content_frames:
+            segment_size = min(N_FRAMES, content_frames - seek)
+            mel_segment = mel[:, seek : seek + segment_size]
+            mel_segment = pad_or_trim(mel_segment, N_FRAMES).to(device).to(dtype)
+
+    for every window of a uniform grid at once (window w starts at ``seek0 + w * stride``; transcribe without timestamp
+    seeking advances by ``n_frames``).  Frames at or beyond ``content_frames`` read as zero; the cast is numpy's
+    round-to-nearest-even (``astype(np.float16)`` = torch ``.half()``).  Returns [n_windows, n_mels, n_frames]."""
+    mel = np.asarray(mel, dtype=np.float32)
+    T = mel.shape[-1]
+    content = max(T - N_FRAMES, 0) if content_frames is None else int(content_frames)
+    stride = n_frames if stride is None else int(stride)
+    if n_windows is None:
+        n_windows = max((content - seek0 + stride - 1) // stride, 0)
+    out = np.zeros((n_windows, mel.shape[0], n_frames), dtype=dtype)
+    for w in range(n_windows):
+        s = seek0 + w * stride
+        e = min(s + n_frames, content)
+        if e > s:
+            out[w, :, : e - s] = mel[:, s:e].astype(dtype)
+    return out

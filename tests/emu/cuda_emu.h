@@ -79,6 +79,12 @@ static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = aligned_alloc(25
 static inline cudaError_t cudaFree(void* p) { free(p); return 0; }
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+typedef struct CUevent_st* cudaEvent_t;
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return 0; }
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = nullptr; return 0; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return 0; }
 static inline cudaError_t cudaDeviceSynchronize() { return 0; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return 0; }
 

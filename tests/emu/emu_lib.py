@@ -171,3 +171,49 @@ def pipeline(pcm, in_rate, n_mels=80, padding=0, trim=True, min_silence_len=1000
     n_n, n_k = int(info[1]), int(info[2])
     return dict(pcm=pcm_out[:n_keep].copy(), mel=mel[:n_mels * T].reshape(n_mels, T).copy(),
                 nonsilent=ns[:2 * n_n].reshape(-1, 2).tolist(), kept=kp[:2 * n_k].reshape(-1, 2).tolist(), info=info.copy())
+
+
+def pipeline_batch(clips, n_mels=80, padding=0, trim=True, min_silence_len=1000, silence_thresh=-40.0, keep_silence=200, seek_step=1,
+                   cap=4096):
+    """clips: list of (pcm, in_rate); ONE b2a_pipeline_batch call; returns one dict per clip like pipeline()"""
+    L = lib()
+    descs = (_abi.ClipDesc * len(clips))()
+    hold = []
+    for d, (pcm, in_rate) in zip(descs, clips):
+        a = np.ascontiguousarray(pcm)
+        ch = 1 if a.ndim == 1 else a.shape[1]
+        n_in = a.shape[0]
+        src = _aligned(a.size + 64, a.dtype); src[:a.size] = a.reshape(-1)
+        n16 = L.b2a_resample_out_len(n_in, in_rate, 16000)
+        pcm_out = _aligned(n16 + 64, np.int16)
+        mel = _aligned(n_mels * ((n16 + 16 + padding) // 160) + 64, np.float32)
+        ns = _aligned(cap * 2, np.int32); kp = _aligned(cap * 2, np.int32); info = _aligned(_abi.INFO_LEN, np.int64)
+        wsb = L.b2a_pipeline_workspace_bytes(n_in, in_rate, padding, cap)
+        ws = _aligned(wsb + 256, np.uint8)
+        d.d_in, d.fmt, d.channels, d.in_rate, d.n_in = src.ctypes.data, (_abi.FMT_S16 if a.dtype == np.int16 else _abi.FMT_F32), ch, in_rate, n_in
+        d.d_pcm_out, d.d_mel_out, d.d_nonsilent_ms, d.d_kept_ms, d.d_info = pcm_out.ctypes.data, mel.ctypes.data, ns.ctypes.data, kp.ctypes.data, info.ctypes.data
+        d.d_ws, d.ws_bytes = ws.ctypes.data, wsb
+        hold.append((src, pcm_out, mel, ns, kp, info, ws))
+    prm = _abi.SilenceParams(int(min_silence_len), -1 if keep_silence is True else int(keep_silence), int(seek_step), 0, float(silence_thresh))
+    _check(L.b2a_pipeline_batch(descs, len(clips), C.byref(prm) if trim else None, n_mels, padding, cap, None))
+    out = []
+    for (src, pcm_out, mel, ns, kp, info, ws) in hold:
+        n_keep = int(info[_abi.INFO_N_KEEP]); T = int(info[_abi.INFO_N_FRAMES]); n_n, n_k = int(info[1]), int(info[2])
+        out.append(dict(pcm=pcm_out[:n_keep].copy(), mel=mel[:n_mels * T].reshape(n_mels, T).copy(),
+                        nonsilent=ns[:2 * n_n].reshape(-1, 2).tolist(), kept=kp[:2 * n_k].reshape(-1, 2).tolist()))
+    return out
+
+
+def remap_times(times, kept_ms, sr=16000):
+    """b2a_kept_offsets + b2a_remap_times on host buffers"""
+    L = lib()
+    k = np.asarray(kept_ms, dtype=np.int32).reshape(-1, 2)
+    cap = max(len(k), 1)
+    kp = _aligned(cap * 2, np.int32); kp[:k.size] = k.reshape(-1)
+    info = _aligned(_abi.INFO_LEN, np.int64); info[:] = 0; info[_abi.INFO_N_KEPT] = len(k)
+    koff = _aligned(cap + 1, np.int64)
+    _check(L.b2a_kept_offsets(_p(kp), _p(info), sr, cap, _p(koff), None))
+    t = _aligned(max(len(times), 1), np.float64); t[:len(times)] = np.asarray(times, dtype=np.float64)
+    out = _aligned(max(len(times), 1), np.float64)
+    _check(L.b2a_remap_times(_p(t), len(times), _p(kp), _p(koff), _p(info), sr, _p(out), None))
+    return out[:len(times)].copy(), koff[:len(k) + 1].copy()

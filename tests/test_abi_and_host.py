@@ -235,3 +235,33 @@ def test_fir_issue_schedule_is_hazard_free(rate):
         freed += frees
     assert next_s == [ks] * 10 and freed == pieces and ready <= pieces
     assert max_live <= 3                                  # the plane ring has 4 (44.1 kHz) / 5 (48 kHz) pieces
+
+
+# ---------------------------------------------------------------- compressed input (host-side decode)
+def _fixture_signal():
+    t = np.arange(int(22050 * 1.5)) / 22050
+    l = 0.30 * np.sin(2 * np.pi * 440 * t) + 0.10 * np.sin(2 * np.pi * 1330 * t)
+    r = 0.25 * np.sin(2 * np.pi * 660 * t) * (t > 0.4)
+    return np.stack([l, r], axis=1).astype(np.float32)
+
+
+def test_compressed_fixtures_decode_on_the_host():
+    """audio_processor_b200/avdecode.py (ctypes over the bundled libavformat / libavcodec; the reference lets the ffmpeg CLI
+    demux + decode, audio_processor.py:912-920, for the m4a / mp3 inputs README.md:22 names): the committed FLAC fixture
+    decodes bit-exactly to the signal tests/golden/make_compressed_fixtures.py encoded, the AAC-in-MP4 fixture to float32
+    PCM close to it (lossy codec: > 20 dB SNR), and garbage is refused with the decoder's message"""
+    from audio_processor_b200 import avdecode, wavio
+    if not avdecode.available():
+        pytest.skip("bundled FFmpeg libraries not found")
+    here = os.path.join(ROOT, "tests", "golden")
+    x = _fixture_signal()
+    pcm, rate = wavio.read_audio(os.path.join(here, "tone_stereo_22k.flac"))
+    assert rate == 22050 and pcm.dtype == np.int16 and pcm.shape == x.shape
+    assert np.array_equal(pcm, np.clip(np.rint(x * 32768.0), -32768, 32767).astype(np.int16))
+    pcm, rate = wavio.read_audio(os.path.join(here, "tone_stereo_22k.m4a"))
+    assert rate == 22050 and pcm.dtype == np.float32 and pcm.ndim == 2 and pcm.shape[1] == 2 and pcm.shape[0] >= len(x)
+    best = max(10 * np.log10((x[2000:30000] ** 2).sum() / ((pcm[2000 + d:30000 + d] - x[2000:30000]) ** 2).sum()) for d in range(0, 2100))
+    assert best > 20.0, best                      # (96 kbit/s AAC-LC: 22.7 dB on this signal) the encoder's delay is a whole number of samples somewhere in 0 .. 2 frames
+    with pytest.raises(wavio.UnsupportedAudio):
+        bad = os.path.join(here, "golden.json")
+        wavio.read_audio(bad)

@@ -340,3 +340,35 @@ def test_emu_pipeline_tc_fused_compaction(emu, keep, pad, extra, monkeypatch):
     """the probe's gathering fetch + trimmed-PCM write-back on bursts of 120-300 ms (several kept ranges per tile)"""
     monkeypatch.setenv("B2A_LM_IMPL", "tc")
     test_emu_pipeline_fused_compaction_many_short_segments(emu, keep, pad, extra)
+
+
+def test_emu_pipeline_batch_matches_single_calls(emu):
+    """b2a_pipeline_batch: three clips of different length, rate and channel count in ONE call == three b2a_pipeline calls"""
+    rng = np.random.default_rng(31)
+    clips = []
+    for rate, ch, secs in ((44100, 2, 3.1), (16000, 1, 5.0), (48000, 2, 2.3)):
+        n = int(rate * secs) + int(rng.integers(0, 50))
+        t = np.arange(n) / rate
+        env = (np.floor(t / 1.3) % 2 == 0)
+        x = (np.where(env, 5000 * np.sin(2 * np.pi * 330 * t), 0)[:, None] + rng.standard_normal((n, ch)) * 5).astype(np.int16)
+        clips.append((x[:, 0].copy() if ch == 1 else x, rate))
+    kw = dict(min_silence_len=400, silence_thresh=-40, keep_silence=100, seek_step=1)
+    got = emu.pipeline_batch(clips, n_mels=80, padding=0, **kw)
+    for (pcm, rate), g in zip(clips, got):
+        one = emu.pipeline(pcm, rate, n_mels=80, padding=0, **kw)
+        assert g["kept"] == one["kept"] and g["nonsilent"] == one["nonsilent"]
+        assert np.array_equal(g["pcm"], one["pcm"]) and np.array_equal(g["mel"], one["mel"])
+    assert sum(len(g["kept"]) for g in got) >= 5 and all(0 < len(g["pcm"]) for g in got)
+
+
+def test_emu_remap_times_matches_oracle(emu):
+    """b2a_kept_offsets + b2a_remap_times against oracle/remap.py (trimmed-timeline seconds -> original recording)"""
+    from oracle import remap as orm
+    kept = [[0, 3093], [4907, 8000], [9100, 9900], [15000, 15016]]
+    times = [0.0, 0.001, 3.0929, 3.093, 3.0931, 5.0, 6.186, 6.1861, 6.986, 7.0, 7.002, 7.5, 100.0]
+    got, koff = emu.remap_times(times, kept)
+    assert koff.tolist() == [0, 3093 * 16, 6186 * 16, 6986 * 16, 7002 * 16]
+    ref = [orm.remap_time(t, kept) for t in times]
+    assert np.abs(got - np.array(ref)).max() <= 1e-9, (got, ref)
+    got0, _ = emu.remap_times([1.5], [])
+    assert got0.tolist() == [1.5]

@@ -274,26 +274,25 @@ def test_logmel_whisper_api(ops, T, tmp_path):
 
 
 def test_mel_windows_match_transcribe_loop(ops, T):
-    """b2a_mel_windows == whisper.transcribe's slice + pad_or_trim + cast, window by window (bit-exact, f32 and f16)"""
+    """b2a_mel_windows == whisper.transcribe's slice + pad_or_trim + cast, window by window (bit-exact, f32 and f16), against
+    the numpy restatement in oracle/whisper_logmel.py (encoder_windows) — and the package's own window iterator agrees"""
     from audio_processor_b200 import whisper_audio as wa
+    from oracle import whisper_logmel as wl
     g = T.Generator(device="cuda").manual_seed(5)
     audio = (T.randn(16000 * 73, device="cuda", generator=g) * 0.1).clamp(-1, 1)
     mel = wa.log_mel_spectrogram(audio, 80, padding=wa.N_SAMPLES)
-    for dtype in (T.float32, T.float16):
-        ref = list(wa.mel_segments(mel, dtype=dtype))
+    mel_h = mel.cpu().numpy()
+    for dtype, npdt in ((T.float32, np.float32), (T.float16, np.float16)):
+        ref = wl.encoder_windows(mel_h, dtype=npdt)
         got = wa.mel_windows(mel, dtype=dtype)
-        assert got.shape == (len(ref), 80, 3000) and got.dtype == dtype
-        for w, (_, seg) in enumerate(ref):
-            assert T.equal(got[w], seg)
+        assert got.shape == ref.shape == (3, 80, 3000) and got.dtype == dtype
+        assert np.array_equal(got.cpu().numpy(), ref)
+        for w, (_, seg) in enumerate(wa.mel_segments(mel, dtype=dtype)):
+            assert np.array_equal(seg.cpu().numpy(), ref[w])
     # overlapping grid with an odd window length and windows past the content
     got = ops.mel_windows(mel, 301, content_frames=1000, seek0=7, stride=150, n_windows=9, dtype=T.float16)
-    for w in range(9):
-        s = 7 + 150 * w
-        e = min(s + 301, 1000)
-        ref = T.zeros((80, 301), dtype=T.float16, device="cuda")
-        if e > s:
-            ref[:, :e - s] = mel[:, s:e].half()
-        assert T.equal(got[w], ref)
+    ref = wl.encoder_windows(mel_h, 301, content_frames=1000, seek0=7, stride=150, n_windows=9, dtype=np.float16)
+    assert np.array_equal(got.cpu().numpy(), ref)
     with pytest.raises(RuntimeError):
         ops.mel_windows(mel, content_frames=mel.shape[1] + 1)
 
@@ -577,3 +576,146 @@ def test_second_device_in_one_process(ops, T):
         x1 = x0.to("cuda:1")
         r1 = ops.pipeline(x1, 44100, n_mels=80, min_silence_len=1000, silence_thresh=-40, keep_silence=200)
         assert r1.kept == r0.kept and T.equal(r1.pcm.cpu(), r0.pcm.cpu()) and T.equal(r1.mel.cpu(), r0.mel.cpu())
+
+
+# ---------------------------------------------------------------- batches, threads, remap
+def _cfg4_like_clip(T, seed, secs):
+    from audio_processor_b200 import synth
+    return synth.synth_clip(seed, 48000, 2, secs, 0.50, device="cuda")
+
+
+def test_pipeline_batch_cfg4_shape_vs_oracle(ops, T):
+    """BASELINE configs[3] in miniature: 48 kHz stereo clips with ~50 % silence and DIFFERENT lengths through ONE
+    b2a_pipeline_batch call (the library forks them over its internal streams), each checked against the oracle run on the
+    same bytes: ranges and trimmed PCM bit-exact, log-mel <= 1e-4; then the same batch replayed as one CUDA graph"""
+    from oracle import pydub_silence as ps, whisper_logmel as wl
+    clips = [_cfg4_like_clip(T, 40 + i, secs) for i, secs in enumerate((21.0, 9.5, 33.3, 14.2, 6.1))]
+    plans = [ops.PipelinePlan(int(c.shape[0]), 48000, 2, c.dtype, n_mels=80, padding=0) for c in clips]
+    batch = ops.PipelineBatch(plans)
+    kw = dict(min_silence_len=1000, silence_thresh=-40, keep_silence=200, seek_step=1)
+    for rep in range(3):                                     # eager, capture, replay
+        res = batch.run(clips, graph=True, **kw)
+        T.cuda.synchronize()
+        for c, r in zip(clips, res):
+            full = ops.resample(c, 48000)[0].cpu().numpy()
+            assert r.kept == ps.kept_ranges_fast(full, 16000, **kw) and r.nonsilent == ps.detect_nonsilent_fast(full, 16000, 1000, -40, 1)
+            trimmed = ps.strip_silence_fast(full, 16000, **kw)
+            assert np.array_equal(r.pcm.cpu().numpy(), trimmed) and 0.2 * len(full) < len(trimmed) < 0.9 * len(full)
+            ref = wl.log_mel_spectrogram(trimmed.astype(np.float32) / 32768.0, 80).numpy()
+            assert np.abs(r.mel.cpu().numpy() - ref).max() <= MEL_TOL
+
+
+def test_c_abi_from_six_threads(ops, T):
+    """the reference calls the front-end from ThreadPoolExecutor workers (audio_processor.py:56): six Python threads, each
+    with its own stream and its own clips, drive b2a_resample / b2a_detect_silence / b2a_log_mel / b2a_pipeline concurrently
+    (ctypes releases the GIL during the calls); every result is checked against the oracle"""
+    import threading
+    from audio_processor_b200 import synth
+    from audio_processor_b200.service import AudioFrontend
+    from oracle import pydub_silence as ps, resample_oracle as ro, whisper_logmel as wl
+    fe = AudioFrontend(min_silence_len=700, silence_thresh=-40, keep_silence=150)       # ONE shared instance, as in the reference
+    kw = dict(min_silence_len=700, silence_thresh=-40, keep_silence=150, seek_step=1)
+    errors = []
+
+    def worker(tid):
+        try:
+            rate = (44100, 48000, 16000)[tid % 3]
+            ch = 2 if rate != 16000 else 1
+            stream = T.cuda.Stream()
+            with T.cuda.stream(stream):
+                for it in range(4):
+                    x = synth.synth_clip(100 * tid + it, rate, ch, 6.0 + tid + 0.37 * it, 0.35, device="cuda")
+                    y16, _, en = ops.resample(x, rate, want_energy=True)
+                    r = ops.detect(y16, 16000, energy=en, **kw)
+                    mel = ops.log_mel(y16, 80)
+                    pcm_t, mel_t, kept = fe.process_pcm(x, rate)
+                    stream.synchronize()
+                    full = y16.cpu().numpy()
+                    ref16 = ro.convert(x.cpu().numpy(), rate)
+                    assert len(full) == len(ref16) and np.abs(full.astype(int) - ref16.astype(int)).max() <= 1
+                    want = ps.kept_ranges_fast(full, 16000, **kw)
+                    assert r.kept == want and kept == want and fe.last_segments == want
+                    trimmed = ps.strip_silence_fast(full, 16000, **kw)
+                    assert np.array_equal(pcm_t.cpu().numpy(), trimmed)
+                    assert np.abs(mel.cpu().numpy() - wl.log_mel_spectrogram(full.astype(np.float32) / 32768.0, 80).numpy()).max() <= MEL_TOL
+                    assert np.abs(mel_t.cpu().numpy() - wl.log_mel_spectrogram(trimmed.astype(np.float32) / 32768.0, 80).numpy()).max() <= MEL_TOL
+        except Exception as e:                                # noqa: BLE001
+            import traceback
+            errors.append((tid, traceback.format_exc()))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errors, errors[0][1]
+    # results of earlier calls stay valid when the same thread runs the next clip of the same shape (ADVICE round 1)
+    a = synth.synth_clip(900, 44100, 2, 5.0, 0.3, device="cuda")
+    b = synth.synth_clip(901, 44100, 2, 5.0, 0.3, device="cuda")
+    ra, rb = fe.process_pcm(a, 44100), fe.process_pcm(b, 44100)
+    ra2 = fe.process_pcm(a, 44100)
+    assert T.equal(ra[1], ra2[1]) and T.equal(ra[0], ra2[0]) and ra[1].data_ptr() != rb[1].data_ptr() and ra[2] == ra2[2]
+
+
+def test_remap_times_on_device(ops, T):
+    """b2a_remap_times: Whisper-style segment times on the trimmed timeline -> original recording, against oracle/remap.py,
+    with the kept table of a real pipeline run (and the derived offsets against the silence detector's own)"""
+    from audio_processor_b200 import synth
+    from oracle import remap as orm
+    x = synth.synth_clip(77, 44100, 2, 40.0, 0.4, device="cuda")
+    plan = ops.PipelinePlan(int(x.shape[0]), 44100, 2, x.dtype, n_mels=80, padding=0)
+    r = plan.run(x, min_silence_len=1000, silence_thresh=-40, keep_silence=200)
+    kept = r.kept
+    assert len(kept) >= 3
+    rng = np.random.default_rng(5)
+    total_s = sum(e - s for s, e in kept) / 1000.0
+    times = np.concatenate([rng.uniform(0, total_s, 500), [0.0, total_s, total_s + 3.0],
+                            np.cumsum([e - s for s, e in kept]) / 1000.0])            # incl. times exactly on the cuts
+    got = ops.remap_times(times, plan.kept, plan.info).cpu().numpy()
+    ref = np.array([orm.remap_time(t, kept) for t in times])
+    assert np.abs(got - ref).max() <= 1e-9
+    y16, _, en = ops.resample(x, 44100, want_energy=True)
+    d = ops.detect(y16, 16000, 1000, -40, 200, 1, energy=en)
+    got2 = ops.remap_times(times, d.kept_ms, d.info, kept_off=d.kept_off).cpu().numpy()
+    assert np.array_equal(got, got2)
+    from audio_processor_b200 import service
+    segs = [{"start": float(a), "end": float(a) + 0.5, "text": "x"} for a in times[:20]]
+    host = service.remap_segments(segs, kept)
+    assert all(abs(h["start"] - orm.remap_time(s["start"], kept)) <= 1e-9 for h, s in zip(host, segs))
+
+
+def test_convert_to_wav_from_compressed_containers(ops, T, tmp_path):
+    """f4: convert_to_wav("x.m4a") / ("x.flac") — the call process_audio makes for every non-WAV upload
+    (audio_processor.py:1040-1044): host decode (libavcodec) -> b2a_resample on the GPU -> 16 kHz mono s16 WAV, equal to
+    what the real libswresample makes of the same decoded PCM (<= 1 LSB), i.e. to the WAV route on the decoded samples"""
+    import os
+    import shutil
+    from audio_processor_b200 import avdecode, wavio
+    from audio_processor_b200.service import AudioFrontend
+    from oracle import resample_oracle as ro, swr_ref
+    if not avdecode.available():
+        pytest.skip("bundled FFmpeg libraries not found")
+    fe = AudioFrontend()
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    for name in ("tone_stereo_22k.m4a", "tone_stereo_22k.flac"):
+        src = str(tmp_path / name)
+        shutil.copy(os.path.join(here, name), src)
+        out = fe.convert_to_wav(src)
+        assert out == os.path.splitext(src)[0] + ".wav" and os.path.exists(out)
+        y, rate = wavio.read_wav(out)
+        assert rate == 16000 and y.ndim == 1 and y.dtype == np.int16
+        pcm, in_rate = avdecode.decode_audio(src)
+        ref = swr_ref.convert(pcm, in_rate) if swr_ref.available() else ro.convert(pcm, in_rate)
+        assert len(y) == len(ref) and np.abs(y.astype(int) - ref.astype(int)).max() <= 1
+        # the same decoded PCM through the WAV route gives the same file
+        wav_in = str(tmp_path / (name + ".pcm.wav"))
+        if pcm.dtype == np.int16:
+            import wave
+            w = wave.open(wav_in, "wb"); w.setnchannels(2); w.setsampwidth(2); w.setframerate(in_rate); w.writeframes(pcm.tobytes()); w.close()
+            y2, _ = wavio.read_wav(fe.convert_to_wav(wav_in))
+            assert np.array_equal(y2, y)
+    import subprocess
+    bad = str(tmp_path / "noise.m4a")
+    open(bad, "wb").write(b"not audio at all" * 100)
+    with pytest.raises(subprocess.CalledProcessError):
+        fe.convert_to_wav(bad)
