@@ -97,7 +97,10 @@ int pipeline_launch(const void* d_in, int fmt, int channels, int in_rate, i64 n_
 }
 
 // ---- many clips per call: fork / join over a small pool of internal streams --------------------------------------
-constexpr int kBatchLanes = 4;             // clip i runs on lane i % 4; lane 0 is the caller's stream
+#ifndef B2A_BATCH_LANES
+#define B2A_BATCH_LANES 8
+#endif
+constexpr int kBatchLanes = B2A_BATCH_LANES;   // clip i runs on lane i % lanes; lane 0 is the caller's stream
 struct BatchPool {
     cudaStream_t side[kBatchLanes - 1];
     cudaEvent_t fork, join[kBatchLanes - 1];

@@ -191,12 +191,17 @@ __global__ void __launch_bounds__(SIL_THREADS, 1) silence_kernel(const u64* __re
 
     auto energy = [&](i64 t) -> u64 { return (t >= 0 && t < c.len_ms && t < c.n_energy) ? e[t] : 0ull; };
 
-    // ---- 1. 32-ms sums ----
-    for (int j = warp; j < n_S; j += SIL_WARPS) {
-        u64 v = energy(f_lo + 32 * (i64)j + lane);
+    // ---- 1. 32-ms sums (four independent loads in flight per warp) ----
+    for (int j0 = warp; j0 < n_S; j0 += 4 * SIL_WARPS) {
+        u64 v[4];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) s_S[j] = v;
+        for (int u = 0; u < 4; u++) v[u] = j0 + u * SIL_WARPS < n_S ? energy(f_lo + 32 * (i64)(j0 + u * SIL_WARPS) + lane) : 0ull;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[u] += __shfl_xor_sync(0xffffffffu, v[u], o);
+            if (lane == 0 && j0 + u * SIL_WARPS < n_S) s_S[j0 + u * SIL_WARPS] = v[u];
+        }
     }
     __syncthreads();
 
@@ -214,20 +219,31 @@ __global__ void __launch_bounds__(SIL_THREADS, 1) silence_kernel(const u64* __re
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) D += __shfl_xor_sync(0xffffffffu, D, o);
-            for (int fw = w0; fw < w1; fw++) {
-                const i64 i = f_lo + 32 * (i64)fw + lane;                 // this lane's window start
-                const u64 d = energy(i + W) - energy(i);                  // wraps; the running sum is exact mod 2^64
-                u64 inc = d;
+            // four flag words per round: the eight loads go out together, the scans follow (the running sum D is the only
+            // dependency between words, one add each)
+            for (int fw0 = w0; fw0 < w1; fw0 += 4) {
+                u64 d[4];
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const u64 y = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o) inc += y;
+                for (int u = 0; u < 4; u++) {
+                    const i64 i = f_lo + 32 * (i64)(fw0 + u) + lane;       // this lane's window start
+                    d[u] = fw0 + u < w1 ? energy(i + W) - energy(i) : 0ull; // wraps; the running sum is exact mod 2^64
                 }
-                const u64 E = D + inc - d;                                 // sum e[i .. i + W)
-                const bool cand = i >= 0 && i <= c.last && (c.step == 1 || (i % c.step) == 0 || i == c.last);
-                const unsigned word = __ballot_sync(0xffffffffu, cand && E < c.limit);
-                if (lane == 0) s_flag[fw] = word;
-                D += __shfl_sync(0xffffffffu, inc, 31);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (fw0 + u >= w1) break;
+                    const i64 i = f_lo + 32 * (i64)(fw0 + u) + lane;
+                    u64 inc = d[u];
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const u64 y = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= o) inc += y;
+                    }
+                    const u64 E = D + inc - d[u];                           // sum e[i .. i + W)
+                    const bool cand = i >= 0 && i <= c.last && (c.step == 1 || (i % c.step) == 0 || i == c.last);
+                    const unsigned word = __ballot_sync(0xffffffffu, cand && E < c.limit);
+                    if (lane == 0) s_flag[fw0 + u] = word;
+                    D += __shfl_sync(0xffffffffu, inc, 31);
+                }
             }
         }
     }
