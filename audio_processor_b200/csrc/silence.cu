@@ -174,8 +174,11 @@ __global__ void __launch_bounds__(SIL_THREADS, 1) silence_kernel(const u64* __re
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = c.W, Wr = (W + 31) & ~31;
     const int chunk = c.chunk;
-    const i64 c0 = (i64)blockIdx.x * chunk;             // first cover position of this block
-    const i64 f_lo = c0 - Wr;                           // first window start evaluated (32-aligned, <= c0 - W; may be negative)
+    // every position of the clip fits 32 bits (SIL_MAX_BLOCKS x SIL_MAX_CHUNK ms): index arithmetic is int, the energies are uint64
+    const int len_ms = (int)c.len_ms, last = (int)c.last;
+    const int n_valid = (int)(c.n_energy < c.len_ms ? c.n_energy : c.len_ms);
+    const int c0 = (int)blockIdx.x * chunk;             // first cover position of this block
+    const int f_lo = c0 - Wr;                           // first window start evaluated (32-aligned, <= c0 - W; may be negative)
     const int n_fw = (chunk + Wr) / 32;                 // flag words: starts [f_lo, c0 + chunk)
     const int n_cw = chunk / 32;                        // cover words: positions [c0, c0 + chunk)
     const int n_S = (chunk + 2 * Wr) / 32 + 1;          // 32-ms sums over energies [f_lo, c0 + chunk + Wr + 32)
@@ -189,13 +192,13 @@ __global__ void __launch_bounds__(SIL_THREADS, 1) silence_kernel(const u64* __re
     __shared__ i64 s_base;                              // packed run counts of the blocks before this one
     __shared__ int s_is_last;
 
-    auto energy = [&](i64 t) -> u64 { return (t >= 0 && t < c.len_ms && t < c.n_energy) ? e[t] : 0ull; };
+    auto energy = [&](int t) -> u64 { return (unsigned)t < (unsigned)n_valid ? e[t] : 0ull; };
 
     // ---- 1. 32-ms sums (four independent loads in flight per warp) ----
     for (int j0 = warp; j0 < n_S; j0 += 4 * SIL_WARPS) {
         u64 v[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) v[u] = j0 + u * SIL_WARPS < n_S ? energy(f_lo + 32 * (i64)(j0 + u * SIL_WARPS) + lane) : 0ull;
+        for (int u = 0; u < 4; u++) v[u] = j0 + u * SIL_WARPS < n_S ? energy(f_lo + 32 * (j0 + u * SIL_WARPS) + lane) : 0ull;
 #pragma unroll
         for (int u = 0; u < 4; u++) {
 #pragma unroll
@@ -214,7 +217,7 @@ __global__ void __launch_bounds__(SIL_THREADS, 1) silence_kernel(const u64* __re
             u64 D = 0;
             for (int j = lane; j < W / 32; j += 32) D += s_S[w0 + j];
             {
-                const i64 t = f_lo + 32 * (i64)(w0 + W / 32) + lane;
+                const int t = f_lo + 32 * (w0 + W / 32) + lane;
                 if (lane < (W & 31)) D += energy(t);
             }
 #pragma unroll
@@ -225,13 +228,13 @@ __global__ void __launch_bounds__(SIL_THREADS, 1) silence_kernel(const u64* __re
                 u64 d[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    const i64 i = f_lo + 32 * (i64)(fw0 + u) + lane;       // this lane's window start
+                    const int i = f_lo + 32 * (fw0 + u) + lane;            // this lane's window start
                     d[u] = fw0 + u < w1 ? energy(i + W) - energy(i) : 0ull; // wraps; the running sum is exact mod 2^64
                 }
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     if (fw0 + u >= w1) break;
-                    const i64 i = f_lo + 32 * (i64)(fw0 + u) + lane;
+                    const int i = f_lo + 32 * (fw0 + u) + lane;
                     u64 inc = d[u];
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
@@ -239,7 +242,7 @@ __global__ void __launch_bounds__(SIL_THREADS, 1) silence_kernel(const u64* __re
                         if (lane >= o) inc += y;
                     }
                     const u64 E = D + inc - d[u];                           // sum e[i .. i + W)
-                    const bool cand = i >= 0 && i <= c.last && (c.step == 1 || (i % c.step) == 0 || i == c.last);
+                    const bool cand = (unsigned)i <= (unsigned)last && last >= 0 && (c.step == 1 || (i % c.step) == 0 || i == last);
                     const unsigned word = __ballot_sync(0xffffffffu, cand && E < c.limit);
                     if (lane == 0) s_flag[fw0 + u] = word;
                     D += __shfl_sync(0xffffffffu, inc, 31);
@@ -267,7 +270,7 @@ __global__ void __launch_bounds__(SIL_THREADS, 1) silence_kernel(const u64* __re
         }
     }
     __syncthreads();
-    auto window_silent = [&](i64 i) -> bool {            // direct evaluation (only for the seek_step > W continuity rule)
+    auto window_silent = [&](int i) -> bool {            // direct evaluation (only for the seek_step > W continuity rule)
         u64 E = 0;
         for (int k = 0; k < W; k++) E += energy(i + k);
         return E < c.limit;
@@ -282,18 +285,18 @@ __global__ void __launch_bounds__(SIL_THREADS, 1) silence_kernel(const u64* __re
         } else {
             for (int k = 0; k < W; k++) cov |= f << k;
         }
-        const i64 t0 = c0 + 32 * (i64)cw;
+        const int t0 = c0 + 32 * cw;
         if (c.step > W && cov != 0xffffffffu) {
             // pydub merges consecutive candidates p, p + step that are both silent even though no window covers the gap
             for (int b = 0; b < 32; b++) {
-                const i64 t = t0 + b;
-                if (((cov >> b) & 1u) || t >= c.len_ms || t < 0) continue;
-                const i64 pc = (t / c.step) * c.step, nc = pc + c.step;
-                if (nc <= c.last && window_silent(pc) && window_silent(nc)) cov |= 1u << b;
+                const int t = t0 + b;
+                if (((cov >> b) & 1u) || t >= len_ms || t < 0) continue;
+                const i64 pc = ((i64)t / c.step) * c.step, nc = pc + c.step;
+                if (nc <= c.last && window_silent((int)pc) && window_silent((int)nc)) cov |= 1u << b;
             }
         }
-        const i64 left = c.len_ms - t0;                   // positions of this word inside the clip
-        if (left < 32) cov &= left <= 0 ? 0u : ((1u << (int)left) - 1u);
+        const int left = len_ms - t0;                     // positions of this word inside the clip
+        if (left < 32) cov &= left <= 0 ? 0u : ((1u << left) - 1u);
         return cov;
     };
     for (int cw = tid; cw < n_cw; cw += SIL_THREADS) s_cov[cw] = cover_word(cw);
@@ -307,9 +310,9 @@ __global__ void __launch_bounds__(SIL_THREADS, 1) silence_kernel(const u64* __re
     const int lo_c = min(tid * per_c, n_cw), hi_c = min(lo_c + per_c, n_cw);
     auto start_masks = [&](int cw, unsigned& ns, unsigned& ss) {
         const unsigned cov = s_cov[cw];
-        const i64 t0 = c0 + 32 * (i64)cw;
-        const i64 left = c.len_ms - t0;
-        const unsigned valid = left >= 32 ? 0xffffffffu : left <= 0 ? 0u : ((1u << (int)left) - 1u);
+        const int t0 = c0 + 32 * cw;
+        const int left = len_ms - t0;
+        const unsigned valid = left >= 32 ? 0xffffffffu : left <= 0 ? 0u : ((1u << left) - 1u);
         unsigned pbit;                                     // cover(t0 - 1)
         if (cw > 0) pbit = s_cov[cw - 1] >> 31;
         else pbit = prev_block_cov ? 1u : 0u;
@@ -353,7 +356,7 @@ __global__ void __launch_bounds__(SIL_THREADS, 1) silence_kernel(const u64* __re
         for (int cw = lo_c; cw < hi_c; cw++) {
             unsigned ns, ss;
             start_masks(cw, ns, ss);
-            const i64 t0 = c0 + 32 * (i64)cw;
+            const int t0 = c0 + 32 * cw;
             unsigned both = ns | ss;                                   // never both at one position
             while (both) {
                 const int b = __ffs((int)both) - 1;
@@ -375,7 +378,7 @@ __global__ void __launch_bounds__(SIL_THREADS, 1) silence_kernel(const u64* __re
         // totals, and the end of the run that is open at the end of the clip
         const i64 all = s_base + tot;
         const int g0 = (int)(all >> 32), g1 = (int)(all & 0xffffffffLL);
-        const i64 tl = c.len_ms - 1 - c0;                              // last position of the clip, relative to this block
+        const int tl = len_ms - 1 - c0;                                // last position of the clip, relative to this block
         const bool last_cov = tl >= 0 && ((s_cov[tl / 32] >> (tl % 32)) & 1u);
         if (last_cov) { if (g1 >= 1 && g1 - 1 < c.cap && silent_ms) silent_ms[2 * (g1 - 1) + 1] = (int32_t)c.len_ms; }
         else { if (g0 >= 1 && g0 - 1 < c.cap && nonsilent_ms) nonsilent_ms[2 * (g0 - 1) + 1] = (int32_t)c.len_ms; }

@@ -265,3 +265,36 @@ def test_compressed_fixtures_decode_on_the_host():
     with pytest.raises(wavio.UnsupportedAudio):
         bad = os.path.join(here, "golden.json")
         wavio.read_audio(bad)
+
+
+def test_patch_whisper_rebinds_what_transcribe_calls(tmp_path, monkeypatch):
+    """round-1 ADVICE: `import whisper.transcribe as wt` binds the FUNCTION (whisper/__init__ does `from .transcribe import
+    transcribe`), so the old patch never reached transcribe.py's own from-imported names.  With a stub package laid out like
+    openai-whisper, patch_whisper() must make whisper.transcribe(...) call this package's log_mel_spectrogram."""
+    import importlib
+    pkg = tmp_path / "whisper"
+    pkg.mkdir()
+    (pkg / "audio.py").write_text(
+        "def load_audio(file, sr=16000):\n    return 'orig-load'\n"
+        "def pad_or_trim(array, length=480000, *, axis=-1):\n    return 'orig-pad'\n"
+        "def log_mel_spectrogram(audio, n_mels=80, padding=0, device=None):\n    return 'orig-mel'\n")
+    (pkg / "transcribe.py").write_text(
+        "from .audio import log_mel_spectrogram, pad_or_trim\n"
+        "def transcribe(model, audio, **kw):\n    return log_mel_spectrogram(audio, 80, padding=480000), pad_or_trim(audio, 3000)\n")
+    (pkg / "__init__.py").write_text(
+        "from .audio import load_audio, log_mel_spectrogram, pad_or_trim\nfrom .transcribe import transcribe\n")
+    monkeypatch.syspath_prepend(str(tmp_path))
+    for m in [k for k in sys.modules if k == "whisper" or k.startswith("whisper.")]:
+        monkeypatch.delitem(sys.modules, m)
+    import whisper  # the stub
+    assert whisper.transcribe(None, "a.wav") == ("orig-mel", "orig-pad") and callable(whisper.transcribe)
+    from audio_processor_b200 import whisper_audio
+    monkeypatch.setattr(whisper_audio, "log_mel_spectrogram", lambda audio, n_mels=80, padding=0, device=None: ("b2a-mel", n_mels, padding))
+    monkeypatch.setattr(whisper_audio, "pad_or_trim", lambda array, length=480000, *, axis=-1: ("b2a-pad", length))
+    whisper_audio.patch_whisper()
+    wt = importlib.import_module("whisper.transcribe")
+    assert wt.log_mel_spectrogram is whisper_audio.log_mel_spectrogram and sys.modules["whisper.audio"].load_audio is whisper_audio.load_audio
+    assert whisper.transcribe(None, "a.wav") == (("b2a-mel", 80, 480000), ("b2a-pad", 3000))
+    assert whisper.log_mel_spectrogram is whisper_audio.log_mel_spectrogram
+    for m in [k for k in sys.modules if k == "whisper" or k.startswith("whisper.")]:
+        monkeypatch.delitem(sys.modules, m)
