@@ -24,8 +24,9 @@ namespace b2a {
 constexpr int SIL_THREADS = 1024;           // one block per SM
 constexpr int SIL_WARPS = SIL_THREADS / 32;
 constexpr int SIL_MIN_CHUNK = 4096;         // milliseconds per block, at least (short clips use fewer blocks)
-constexpr int SIL_MAX_CHUNK = 1 << 18;      // shared-memory bound: 148 blocks x 262 144 ms = 10.7 hours per clip
 constexpr int SIL_MAX_BLOCKS = 148;         // every block resident at once (the run-count exchange spins on its predecessors)
+constexpr int SIL_MAX_CHUNKS = 8192;        // status words in the workspace (148 chunks of 24 576 ms cover an hour)
+constexpr int SIL_SMEM_BUDGET = 231000;     // dynamic shared memory per block (227 KB less the static part)
 
 struct SilenceCfg {
     i64 n_samples;      // F
@@ -38,8 +39,9 @@ struct SilenceCfg {
     i64 last;           // len_ms - W  (< 0: clip shorter than the window -> nothing is silent)
     u64 limit;          // n_win * (floor(thr)+1)^2
     int cap;
-    int chunk;          // cover positions per block (multiple of 32)
-    int n_blocks;
+    int chunk;          // cover positions per chunk (multiple of 32)
+    int n_chunks;
+    int n_blocks;       // grid: min(n_chunks, SIL_MAX_BLOCKS)
 };
 
 // ---- per-ms energy of an existing s16 mono buffer ------------------------------------------
@@ -70,14 +72,17 @@ __device__ __forceinline__ T block_exclusive_scan(T v, T* s_warp /*[SIL_WARPS]*/
     __syncthreads();             // s_warp may still be read from a previous call
     if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
-    T wpre = 0, tot = 0;
+    // the 32 warp totals are scanned by every warp with shuffles (one shared-memory load per thread)
+    T winc = s_warp[lane];
 #pragma unroll
-    for (int w = 0; w < SIL_WARPS; w++) {
-        T x = s_warp[w];
-        if (w < warp) wpre += x;
-        tot += x;
+    for (int o = 1; o < 32; o <<= 1) {
+        T y = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += y;
     }
-    *total = tot;
+    static_assert(SIL_WARPS == 32, "one warp total per lane");
+    const T wprev = __shfl_sync(0xffffffffu, winc, (warp + 31) & 31);
+    const T wpre = warp ? wprev : (T)0;
+    *total = __shfl_sync(0xffffffffu, winc, 31);
     return wpre + inc - v;
 }
 // the same with max (values >= -2^30)
@@ -93,9 +98,14 @@ __device__ __forceinline__ int block_exclusive_max(int v, int* s_warp /*[SIL_WAR
     __syncthreads();
     if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
-    int wpre = kNone;
+    int winc = s_warp[lane];
 #pragma unroll
-    for (int w = 0; w < SIL_WARPS; w++) if (w < warp) wpre = max(wpre, s_warp[w]);
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc = max(winc, y);
+    }
+    const int wprev = __shfl_sync(0xffffffffu, winc, (warp + 31) & 31);
+    const int wpre = warp ? wprev : kNone;
     int ex = __shfl_up_sync(0xffffffffu, inc, 1);
     if (lane == 0) ex = kNone;
     return max(wpre, ex);
@@ -147,24 +157,27 @@ __device__ void silence_kept_pass(const int32_t* __restrict__ nonsilent_ms, cons
 }
 
 // ---- the whole of pydub's detect_silence / detect_nonsilent / split_on_silence range logic in ONE launch -----------------
-// Block b owns the cover positions [c0, c0 + chunk) (chunk = len_ms / blocks, a multiple of 32) and evaluates the
-// window starts i in [c0 - W, c0 + chunk) it needs for them:
-//   1. S[j] = sum of 32 consecutive energies (one warp-reduce per 32 ms) over the block's range + halos, in shared memory;
-//   2. every warp streams a contiguous span of starts: E(i) = sum e[i .. i+W) follows from E of the span's first start
-//      (a few S values + a partial block) by ONE warp scan per 32 starts of d[l] = e[i+W+l] - e[i+l]; the silent-start flags
-//      of 32 starts are one ballot word in shared memory;
+// The clip is cut into chunks of `chunk` cover positions (a multiple of 32 ms; one chunk per block for clips up to about
+// an hour, otherwise block b takes chunks b, b + grid, ...).  For the chunk [c0, c0 + chunk) a block evaluates the window
+// starts i in [c0 - W, c0 + chunk) it needs:
+//   1. the energies e[c0 - Wr .. c0 + chunk + W) are staged in shared memory (coalesced 16-byte loads) and turned, in place,
+//      into their exclusive prefix sums P (every thread owns an odd number of consecutive entries: conflict-free; one
+//      block-wide scan of the per-thread totals);
+//   2. E(i) = sum e[i .. i+W) = P[i + W] - P[i]: two shared-memory loads, a subtraction and a compare per start; the
+//      silent-start flags of 32 starts are one ballot word in shared memory;
 //   3. a start covers the W ms behind it: cover(t) <=> t - (last flagged start <= t) < W, i.e. a block-wide prefix MAXIMUM of
 //      flag positions and a few bit operations per word of 32 ms;
-//   4. run starts (covered <-> uncovered transitions) are counted per word; the blocks exchange their counts through a status
-//      word each (every block is resident: a block waits only for blocks of lower index) and scatter their run boundaries
-//      into the ordered range tables: a silent run's start is the end of the nonsilent run before it, and vice versa;
+//   4. run starts (covered <-> uncovered transitions) are counted per word; the chunks exchange their counts through a status
+//      word each (blocks take chunks in increasing order and wait only for chunks of lower index, which are resident or done)
+//      and scatter their run boundaries into the ordered range tables: a silent run's start is the end of the nonsilent
+//      run before it, and vice versa;
 //   5. the block that finishes last (ticket counter) does split_on_silence's keep_silence / midpoint / clamp arithmetic and
 //      the exclusive scan of the kept lengths.
-// Exact-integer throughout (uint64 energies; differences wrap consistently).
+// Exact-integer throughout (uint64 energies; prefix sums wrap consistently mod 2^64).
 struct SilenceWs {            // global workspace, zeroed on the stream before the launch
-    unsigned long long status[SIL_MAX_BLOCKS];    // bit 63 valid | nonsilent starts << 31 | silent starts
     unsigned int ticket;
     unsigned int pad;
+    unsigned long long status[1];    // [n_chunks]: bit 63 valid | nonsilent starts << 31 | silent starts
 };
 
 __global__ void __launch_bounds__(SIL_THREADS, 1) silence_kernel(const u64* __restrict__ e, SilenceCfg c, int32_t* __restrict__ silent_ms,
@@ -174,80 +187,80 @@ __global__ void __launch_bounds__(SIL_THREADS, 1) silence_kernel(const u64* __re
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = c.W, Wr = (W + 31) & ~31;
     const int chunk = c.chunk;
-    // every position of the clip fits 32 bits (SIL_MAX_BLOCKS x SIL_MAX_CHUNK ms): index arithmetic is int, the energies are uint64
+    // every position of the clip fits 32 bits: index arithmetic is int, the energies are uint64
     const int len_ms = (int)c.len_ms, last = (int)c.last;
     const int n_valid = (int)(c.n_energy < c.len_ms ? c.n_energy : c.len_ms);
-    const int c0 = (int)blockIdx.x * chunk;             // first cover position of this block
-    const int f_lo = c0 - Wr;                           // first window start evaluated (32-aligned, <= c0 - W; may be negative)
     const int n_fw = (chunk + Wr) / 32;                 // flag words: starts [f_lo, c0 + chunk)
     const int n_cw = chunk / 32;                        // cover words: positions [c0, c0 + chunk)
-    const int n_S = (chunk + 2 * Wr) / 32 + 1;          // 32-ms sums over energies [f_lo, c0 + chunk + Wr + 32)
-    u64* s_S = (u64*)smem_raw;                          // [n_S]
-    unsigned* s_flag = (unsigned*)(s_S + n_S);          // [n_fw]
+    const int n_P = chunk + Wr + W;                     // prefix sums over energies [f_lo, c0 + chunk + W): P[k] = sum of the first k
+    u64* s_P = (u64*)smem_raw;                          // [n_P] (16-byte aligned)
+    unsigned* s_flag = (unsigned*)(s_P + ((n_P + 1) & ~1));   // [n_fw]
     unsigned* s_cov = s_flag + n_fw;                    // [n_cw]
     int* s_last = (int*)(s_cov + n_cw);                 // [n_fw]: last flagged start (relative to f_lo) before word fw
     __shared__ i64 s_w64[SIL_WARPS];
     __shared__ int s_w32[SIL_WARPS];
     __shared__ i64 s_carry;
-    __shared__ i64 s_base;                              // packed run counts of the blocks before this one
+    __shared__ unsigned long long s_acc;                // packed run counts of the chunks this block had to wait for
     __shared__ int s_is_last;
+    __shared__ unsigned s_prev_cov;                     // cover(c0 - 1), by the same rule (the word before the chunk)
 
     auto energy = [&](int t) -> u64 { return (unsigned)t < (unsigned)n_valid ? e[t] : 0ull; };
+    const bool e_vec = (((uintptr_t)e) & 15) == 0;      // 16-byte loads of energy pairs
 
-    // ---- 1. 32-ms sums (four independent loads in flight per warp) ----
-    for (int j0 = warp; j0 < n_S; j0 += 4 * SIL_WARPS) {
-        u64 v[4];
+    i64 base_run = 0;                                   // packed run counts (nonsilent << 32 | silent) of all chunks before the current one
+  for (int ck = blockIdx.x; ck < c.n_chunks; ck += gridDim.x) {
+    if (tid == 0) s_acc = 0ull;                         // read after several barriers
+    const int c0 = ck * chunk;                          // first cover position of this chunk
+    const int f_lo = c0 - Wr;                           // first window start evaluated (32-aligned, <= c0 - W; may be negative)
+
+    // ---- 1. energies -> shared memory -> exclusive prefix sums, in place ----
+    for (int k0 = 2 * tid; k0 < n_P; k0 += 16 * SIL_THREADS) {
+        ulonglong2 v[8];
 #pragma unroll
-        for (int u = 0; u < 4; u++) v[u] = j0 + u * SIL_WARPS < n_S ? energy(f_lo + 32 * (j0 + u * SIL_WARPS) + lane) : 0ull;
+        for (int u = 0; u < 8; u++) {
+            const int k = k0 + 2 * u * SIL_THREADS, t = f_lo + k;
+            if (k < n_P && t >= 0 && t + 1 < n_valid && e_vec) v[u] = *(const ulonglong2*)(e + t);     // f_lo and k are even
+            else { v[u].x = energy(t); v[u].y = energy(t + 1); }
+        }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v[u] += __shfl_xor_sync(0xffffffffu, v[u], o);
-            if (lane == 0 && j0 + u * SIL_WARPS < n_S) s_S[j0 + u * SIL_WARPS] = v[u];
+        for (int u = 0; u < 8; u++) {
+            const int k = k0 + 2 * u * SIL_THREADS;
+            if (k < n_P) *(ulonglong2*)(s_P + k) = v[u];               // the array is padded to an even length
+        }
+    }
+    __syncthreads();
+    {
+        const int per = ((n_P + SIL_THREADS - 1) / SIL_THREADS) | 1;   // odd: the 64-bit accesses of a half-warp hit distinct banks
+        const int lo = min(tid * per, n_P), hi = min(lo + per, n_P);
+        u64 sum = 0;
+        for (int k = lo; k < hi; k++) sum += s_P[k];
+        u64 tot;
+        u64 run = block_exclusive_scan<u64>(sum, (u64*)s_w64, &tot);
+        for (int k = lo; k < hi; k++) {
+            const u64 x = s_P[k];
+            s_P[k] = run;
+            run += x;
         }
     }
     __syncthreads();
 
-    // ---- 2. silent-start flags, one warp per contiguous span of flag words ----
-    {
-        const int span = (n_fw + SIL_WARPS - 1) / SIL_WARPS;
-        const int w0 = warp * span, w1 = min(n_fw, w0 + span);
-        if (w0 < w1) {
-            // E of the span's first start: W / 32 whole 32-ms sums + W % 32 energies
-            u64 D = 0;
-            for (int j = lane; j < W / 32; j += 32) D += s_S[w0 + j];
-            {
-                const int t = f_lo + 32 * (w0 + W / 32) + lane;
-                if (lane < (W & 31)) D += energy(t);
-            }
+    // ---- 2. silent-start flags: E(i) = P[i + W] - P[i] ----
+    for (int fw0 = warp; fw0 < n_fw; fw0 += 4 * SIL_WARPS) {
+        u64 E[4];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) D += __shfl_xor_sync(0xffffffffu, D, o);
-            // four flag words per round: the eight loads go out together, the scans follow (the running sum D is the only
-            // dependency between words, one add each)
-            for (int fw0 = w0; fw0 < w1; fw0 += 4) {
-                u64 d[4];
+        for (int u = 0; u < 4; u++) {
+            const int fw = fw0 + u * SIL_WARPS;
+            const int k = 32 * (fw < n_fw ? fw : fw0) + lane;
+            E[u] = s_P[k + W] - s_P[k];
+        }
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int i = f_lo + 32 * (fw0 + u) + lane;            // this lane's window start
-                    d[u] = fw0 + u < w1 ? energy(i + W) - energy(i) : 0ull; // wraps; the running sum is exact mod 2^64
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    if (fw0 + u >= w1) break;
-                    const int i = f_lo + 32 * (fw0 + u) + lane;
-                    u64 inc = d[u];
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const u64 y = __shfl_up_sync(0xffffffffu, inc, o);
-                        if (lane >= o) inc += y;
-                    }
-                    const u64 E = D + inc - d[u];                           // sum e[i .. i + W)
-                    const bool cand = (unsigned)i <= (unsigned)last && last >= 0 && (c.step == 1 || (i % c.step) == 0 || i == last);
-                    const unsigned word = __ballot_sync(0xffffffffu, cand && E < c.limit);
-                    if (lane == 0) s_flag[fw0 + u] = word;
-                    D += __shfl_sync(0xffffffffu, inc, 31);
-                }
-            }
+        for (int u = 0; u < 4; u++) {
+            const int fw = fw0 + u * SIL_WARPS;
+            if (fw >= n_fw) break;
+            const int i = f_lo + 32 * fw + lane;                       // this lane's window start
+            const bool cand = last >= 0 && (unsigned)i <= (unsigned)last && (c.step == 1 || (i % c.step) == 0 || i == last);
+            const unsigned word = __ballot_sync(0xffffffffu, cand && E[u] < c.limit);
+            if (lane == 0) s_flag[fw] = word;
         }
     }
     __syncthreads();
@@ -300,7 +313,6 @@ __global__ void __launch_bounds__(SIL_THREADS, 1) silence_kernel(const u64* __re
         return cov;
     };
     for (int cw = tid; cw < n_cw; cw += SIL_THREADS) s_cov[cw] = cover_word(cw);
-    __shared__ unsigned s_prev_cov;                       // cover(c0 - 1), by the same rule (the word before the chunk)
     if (tid == 0) s_prev_cov = c0 > 0 ? (cover_word(-1) >> 31) : 0u;
     __syncthreads();
 
@@ -329,29 +341,33 @@ __global__ void __launch_bounds__(SIL_THREADS, 1) silence_kernel(const u64* __re
     }
     i64 tot;
     const i64 pre = block_exclusive_scan<i64>(cnt, s_w64, &tot);
-    if (warp == 0) {
-        if (lane == 0) {
+    {
+        if (tid == 0) {
             const unsigned long long st = (1ull << 63) | ((unsigned long long)(tot >> 32) << 31) | (unsigned long long)(tot & 0x7fffffffLL);
-            atomicExch(&ws->status[blockIdx.x], st);
+            atomicExch(&ws->status[ck], st);
         }
-        i64 base = 0;
-        for (int p0 = 0; p0 < (int)blockIdx.x; p0 += 32) {
-            const int pidx = p0 + lane;
-            unsigned long long st = 0;
-            if (pidx < (int)blockIdx.x) {
-                do { st = *(volatile unsigned long long*)&ws->status[pidx]; } while (!(st >> 63));
-                base += (i64)(((st >> 31) & 0xffffffffull) << 32) | (i64)(st & 0x7fffffffull);
-            }
+        // counts of the earlier chunks, one per thread: on the block's first chunk every one of them (< SIL_MAX_BLOCKS),
+        // afterwards the chunks since its previous one (gridDim.x of them)
+        const bool first = ck == (int)blockIdx.x;
+        const int p_lo = first ? 0 : ck - (int)gridDim.x;
+        i64 part = 0;
+        if (p_lo + tid < ck) {
+            unsigned long long st;
+            do { st = *(volatile unsigned long long*)&ws->status[p_lo + tid]; } while (!(st >> 63));
+            part = (i64)(((st >> 31) & 0xffffffffull) << 32) | (i64)(st & 0x7fffffffull);
         }
+        if (warp * 32 < ck - p_lo) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) base += __shfl_xor_sync(0xffffffffu, base, o);
-        if (lane == 0) s_base = base;
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if (lane == 0 && part) atomicAdd(&s_acc, (unsigned long long)part);
+        }
+        __syncthreads();
+        base_run = (first ? 0 : base_run) + (i64)s_acc;
     }
-    __syncthreads();
 
     // ---- 5. scatter: every run start is also the end of the run of the other kind before it ----
     {
-        i64 at = s_base + pre;
+        i64 at = base_run + pre;
         int i0 = (int)(at >> 32), i1 = (int)(at & 0xffffffffLL);     // nonsilent / silent starts before this thread's first word
         for (int cw = lo_c; cw < hi_c; cw++) {
             unsigned ns, ss;
@@ -374,9 +390,9 @@ __global__ void __launch_bounds__(SIL_THREADS, 1) silence_kernel(const u64* __re
             }
         }
     }
-    if (blockIdx.x == gridDim.x - 1 && tid == 0) {
+    if (ck == c.n_chunks - 1 && tid == 0) {
         // totals, and the end of the run that is open at the end of the clip
-        const i64 all = s_base + tot;
+        const i64 all = base_run + tot;
         const int g0 = (int)(all >> 32), g1 = (int)(all & 0xffffffffLL);
         const int tl = len_ms - 1 - c0;                                // last position of the clip, relative to this block
         const bool last_cov = tl >= 0 && ((s_cov[tl / 32] >> (tl % 32)) & 1u);
@@ -387,6 +403,9 @@ __global__ void __launch_bounds__(SIL_THREADS, 1) silence_kernel(const u64* __re
         info[B2A_INFO_OVERFLOW] = (g0 > c.cap || g1 > c.cap) ? 1 : 0;
         info[B2A_INFO_LEN_MS] = c.len_ms;
     }
+
+    __syncthreads();                                    // shared memory is reused by the block's next chunk
+  }
 
     // ---- 6. the block that finishes last derives the kept ranges ----
     __threadfence();
@@ -451,8 +470,15 @@ static i64 pydub_len_ms(i64 n_frames, int sample_rate) {
     return (i64)std::nearbyint(v);
 }
 
-// workspace: the blocks' status words and the ticket counter
-static size_t silence_ws_bytes(i64, int) { return align_up(sizeof(SilenceWs), 256) + 256; }
+// workspace: the ticket counter and the chunks' status words
+static size_t silence_ws_bytes(i64, int) { return align_up(sizeof(SilenceWs) + 8 * (size_t)SIL_MAX_CHUNKS, 256) + 256; }
+
+// dynamic shared memory of silence_kernel: prefix sums (padded to an even count) + flag, cover and last-start words
+static size_t silence_smem_bytes(int chunk, int W) {
+    const int Wr = (W + 31) & ~31;
+    const size_t n_P = (size_t)chunk + Wr + W;
+    return ((n_P + 1) & ~(size_t)1) * 8 + (size_t)((chunk + Wr) / 32) * 8 + (size_t)(chunk / 32) * 4 + 64;
+}
 
 int silence_build_cfg(i64 n_samples, int sample_rate, const b2a_silence_params* prm, int cap, SilenceCfg* c) {
     if (!prm) { set_error("silence: null params"); return B2A_EINVAL; }
@@ -480,16 +506,29 @@ int silence_build_cfg(i64 n_samples, int sample_rate, const b2a_silence_params* 
     u64 k = (u64)kf;
     c->limit = (u64)c->W * (u64)c->spm * k * k;
     c->cap = cap;
-    // one chunk of cover positions per block: at most one block per SM, at least SIL_MIN_CHUNK ms each
+    // chunks: as many as there are SMs when the clip is long enough (at least SIL_MIN_CHUNK ms each); the chunk's energies
+    // and their prefix sums must fit in shared memory, so very long clips take several rounds of SIL_MAX_BLOCKS chunks
+    const i64 Wr = (c->W + 31) / 32 * 32;
+    i64 cap_chunk = (SIL_SMEM_BUDGET - 64 - 8 * (Wr + c->W + 2)) / 9 / 32 * 32;
+    while (cap_chunk >= 0 && (i64)silence_smem_bytes((int)cap_chunk + 32, c->W) <= SIL_SMEM_BUDGET) cap_chunk += 32;
+    if (cap_chunk < 32) { set_error("silence: min_silence_len %d does not fit the shared-memory window", c->W); return B2A_EUNSUPPORTED; }
     i64 blocks = (c->len_ms + SIL_MIN_CHUNK - 1) / SIL_MIN_CHUNK;
     if (blocks > SIL_MAX_BLOCKS) blocks = SIL_MAX_BLOCKS;
     if (blocks < 1) blocks = 1;
-    i64 chunk = ((c->len_ms + blocks - 1) / blocks + 31) / 32 * 32;
+    i64 rounds = (c->len_ms + blocks * cap_chunk - 1) / (blocks * cap_chunk);
+    if (rounds < 1) rounds = 1;
+    i64 chunk = ((c->len_ms + blocks * rounds - 1) / (blocks * rounds) + 31) / 32 * 32;
     if (chunk < 32) chunk = 32;
-    if (chunk > SIL_MAX_CHUNK) { set_error("silence: clips longer than %d x %d ms are unsupported", SIL_MAX_BLOCKS, SIL_MAX_CHUNK); return B2A_EUNSUPPORTED; }
+    if (chunk > cap_chunk) chunk = cap_chunk;
+    i64 n_chunks = (c->len_ms + chunk - 1) / chunk;
+    if (n_chunks < 1) n_chunks = 1;
+    if (n_chunks > SIL_MAX_CHUNKS || c->len_ms + chunk + 2 * Wr >= (i64)1 << 31) {
+        set_error("silence: clip of %lld ms is too long (at most %d chunks of %lld ms)", (long long)c->len_ms, SIL_MAX_CHUNKS, (long long)chunk);
+        return B2A_EUNSUPPORTED;
+    }
     c->chunk = (int)chunk;
-    c->n_blocks = (int)((c->len_ms + chunk - 1) / chunk);
-    if (c->n_blocks < 1) c->n_blocks = 1;
+    c->n_chunks = (int)n_chunks;
+    c->n_blocks = (int)(n_chunks < SIL_MAX_BLOCKS ? n_chunks : SIL_MAX_BLOCKS);
     return B2A_OK;
 }
 
@@ -510,11 +549,10 @@ int silence_launch(const u64* d_energy, i64 n_samples, int sample_rate, const b2
     }
     if (((uintptr_t)d_ws) & 7) { set_error("silence: workspace must be 8-byte aligned"); return B2A_EINVAL; }
     SilenceWs* wsp = (SilenceWs*)d_ws;
-    cudaError_t e = cudaMemsetAsync(wsp, 0, sizeof(SilenceWs), stream);
+    cudaError_t e = cudaMemsetAsync(wsp, 0, sizeof(SilenceWs) + 8 * (size_t)c.n_chunks, stream);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(silence workspace)");
-    const int Wr = (c.W + 31) & ~31;
-    const size_t smem = (size_t)((c.chunk + 2 * Wr) / 32 + 1) * 8 + (size_t)((c.chunk + Wr) / 32) * 8 + (size_t)(c.chunk / 32) * 4 + 64;
-    static const size_t kSmemMax = (size_t)((SIL_MAX_CHUNK + 2 * 10016) / 32 + 1) * 8 + (size_t)((SIL_MAX_CHUNK + 10016) / 32) * 8 + (size_t)(SIL_MAX_CHUNK / 32) * 4 + 64;
+    const size_t smem = silence_smem_bytes(c.chunk, c.W);
+    static const size_t kSmemMax = SIL_SMEM_BUDGET;
     auto k1 = silence_kernel;
     {
         // the opt-in to large dynamic shared memory is set ONCE per device to the largest size any call can need

@@ -205,6 +205,21 @@ def test_silence_edges_and_api(ops, T):
         ops.detect(x, 44100)                       # 44.1 samples per ms: unsupported, loudly
 
 
+def test_silence_long_clip_several_rounds_of_chunks(ops, T):
+    """clips beyond about an hour take several rounds of chunks per block (the prefix sums of a chunk live in shared memory):
+    2.6 h of 16 kHz audio against the vectorised oracle, plus a 10-second window (the largest supported, smallest chunks)"""
+    from oracle import pydub_silence as ps
+    rng = np.random.default_rng(77)
+    n = int(2.6 * 3600 * 16000) + 5
+    x = H.random_speechlike(rng, n, min_span=8000, max_span=400000)
+    d = T.from_numpy(x).cuda()
+    for W, th, keep, step in [(1000, -40.0, 200, 1), (10000, -35.0, 700, 1), (700, -40.0, 100, 7)]:
+        r = ops.detect(d, 16000, W, th, keep, step)
+        assert r.silent == ps.detect_silence_fast(x, 16000, W, th, step), (W, th, step)
+        assert r.nonsilent == ps.detect_nonsilent_fast(x, 16000, W, th, step), (W, th, step)
+        assert r.kept == ps.kept_ranges_fast(x, 16000, W, th, keep, step), (W, th, keep, step)
+
+
 def test_silence_idempotent_full_hour(ops, T):
     """size-independent properties at the cfg2 size (1 h @ 16 kHz): sorted, disjoint, inside the clip, and
     trimming the trimmed audio with keep_silence >= min_silence_len/2 removes (almost) nothing more."""
