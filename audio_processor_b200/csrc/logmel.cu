@@ -17,13 +17,13 @@
 //    transposes through shared memory (pitch 201 complex per frame: conflict free), then the radix-20 butterflies
 //    (4x5 prime-factor) of output residues {u, 10-u} mod 10 — so the real-FFT unpack pairs (k, 200-k) stay inside
 //    one thread.  The unpack produces 4|X|^2 (16 flops per conjugate pair); the 1/4 lives in the mel weights.
-//  * mel projection: warp g owns a contiguous group of mels (balanced by cost), lane = frame.  The sparse filterbank
-//    (mel_tables_gen.inc) is staged in shared memory as packed descriptors + zero-padded weight quads and walked by a
-//    small loop shared by all warps (16-byte broadcast loads of weights, conflict-free loads of the power bins at
-//    pitch 203) — the fully unrolled immediate-weight form was 24-48 % slower on instruction fetch.  log10, running
-//    max/min and the [n_mels][T] store follow; a warp stores 32 consecutive frames of one mel = one 128-byte line.
+//  * mel projection: warp u owns mels u, u + 5, u + 10, ... (lane = frame), so all five warps run the same fully unrolled
+//    code over the sparse filterbank (mel_tables_gen.inc: weights as 16-byte shared-memory broadcasts at compile-time
+//    offsets, conflict-free loads of the power bins at pitch 203).  log10, running max/min and the [n_mels][T] store
+//    follow; a warp stores 32 consecutive frames of one mel = one 128-byte line.
 //  * K5 applies Whisper's global floor in place and skips tiles whose minimum is already above it.
 #include <cstdlib>
+#include <utility>
 
 #include "b2a_tables.cuh"
 #include "f16_bits.h"
@@ -52,14 +52,6 @@ constexpr int LM_PP = 203;                          // power-spectrum pitch per 
 #define B2A_MEL_TABLES_INCLUDED
 #include "mel_tables_gen.inc"
 #endif
-// compile-time access to MelC<NM>::seg[G][q] from device code (the constexpr arrays themselves have no device storage)
-template <int NM, int G> struct MelSeg {
-    __host__ __device__ static constexpr int v(int q) {
-        constexpr int s0 = MelC<NM>::seg[G][0], s1 = MelC<NM>::seg[G][1], s2 = MelC<NM>::seg[G][2], s3 = MelC<NM>::seg[G][3], s4 = MelC<NM>::seg[G][4];
-        return q == 0 ? s0 : q == 1 ? s1 : q == 2 ? s2 : q == 3 ? s3 : s4;
-    }
-};
-
 struct cpx { float r, i; };
 __device__ __forceinline__ cpx cadd(cpx a, cpx b) { return {a.r + b.r, a.i + b.i}; }
 __device__ __forceinline__ cpx csub(cpx a, cpx b) { return {a.r - b.r, a.i - b.i}; }
@@ -175,46 +167,56 @@ __device__ __forceinline__ float load_sample(const void* audio, int fmt, i64 idx
     return ((const float*)audio)[idx];
 }
 
-// ---- mel projection of one frame for a warp's group of mels, table driven ----
-// The sparse filterbank sits in shared memory: desc[m] = {byte offset of the first power bin, byte offset of the first
-// weight quad}, weights padded with zeros to whole quads (one 16-byte broadcast load per 4 taps) and the quad count made
-// non-decreasing in m, so a group is at most four runs of constant quad count: loops without a per-mel branch.  The code
-// is the same few dozen instructions for every warp: the fully unrolled immediate-weight form measured 24 % (80 mels) to
-// 48 % (128 mels) slower because five warps x 5 different 4-6 KB bodies overflow the instruction cache
-// (profiles/r01_logmel_icache.md).  lmax / lmin track log2(mel) over the group (converted once per tile by the caller);
-// only the store is predicated.
-template <int NQ>
-__device__ __forceinline__ void mel_run(const uint2* __restrict__ s_desc, const char* __restrict__ s_flat, int m0, int m1,
-                                        const char* __restrict__ Pf, float*& ocol, size_t Tstride, bool valid, float& lmax, float& lmin) {
-#pragma unroll 1
-    for (int m = m0; m < m1; m++, ocol += Tstride) {
-        const uint2 d = s_desc[m];
-        const float* pf = (const float*)(Pf + d.x);
-        const float4* w4 = (const float4*)(s_flat + d.y);
-        float a0 = 0.0f, a1 = 0.0f;
+// ---- mel projection of one frame: warp u owns mels u, u + 5, u + 10, ... (slot i = mel 5 i + u), lane = frame ----
+// Every warp runs the same fully unrolled code (mel_tables_gen.inc): slot i takes nt[i] taps (the widest of its five
+// filters, the others zero padded), its weights are 16-byte broadcast loads at a compile-time offset of the warp's block,
+// and only the first power bin differs between warps (one broadcast load per slot).  History: unrolled per-warp bodies with
+// immediate weights overflowed the instruction cache (profiles/r01_logmel_icache.md); a table-driven loop over each warp's
+// contiguous group of mels then spent 22 instructions per mel on descriptors, pointers and loop control for 4-16 FFMAs and
+// serialised every mel behind its descriptor load (20 % of the kernel's instructions for 5 % of its flops).
+// lmax / lmin track log2(mel) (converted once per tile by the caller); only the store is predicated.
+__device__ __forceinline__ float lg2_fast(float x) {          // x >= 1e-10: never denormal, one MUFU
+#ifndef B2A_EMU
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return __log2f(x);
+#endif
+}
+template <int NM, int I>
+__device__ __forceinline__ void mel_slot(const float4* __restrict__ wq, const unsigned* __restrict__ so, const char* __restrict__ Pf,
+                                         float*& ocol, size_t step, bool valid, int u, float& lmax, float& lmin) {
+    constexpr int NT = MelC<NM>::nt[I], Q0 = MelC<NM>::qoff[I], NQ = (NT + 3) / 4;
+    constexpr bool TAIL = 5 * I + 4 >= NM;                    // the last slot of 128 mels: warps 3 and 4 have no mel
+    const float* pf = (const float*)(Pf + so[I]);
+    float a0 = 0.0f, a1 = 0.0f;
 #pragma unroll
-        for (int q = 0; q < NQ; q++) {
-            const float4 w = w4[q];
+    for (int q = 0; q < NQ; q++) {
+        const float4 w = wq[Q0 + q];
+        if (q == 0) {
+            a0 = w.x * pf[0];
+            if (NT > 1) a1 = w.y * pf[1];
+        } else {
             a0 = fmaf(w.x, pf[4 * q], a0);
-            a1 = fmaf(w.y, pf[4 * q + 1], a1);
-            a0 = fmaf(w.z, pf[4 * q + 2], a0);
-            a1 = fmaf(w.w, pf[4 * q + 3], a1);
+            if (4 * q + 1 < NT) a1 = fmaf(w.y, pf[4 * q + 1], a1);
         }
-        const float l2 = __log2f(fmaxf(a0 + a1, 1e-10f));
+        if (4 * q + 2 < NT) a0 = fmaf(w.z, pf[4 * q + 2], a0);
+        if (4 * q + 3 < NT) a1 = fmaf(w.w, pf[4 * q + 3], a1);
+    }
+    const float l2 = lg2_fast(fmaxf(a0 + a1, 1e-10f));
+    const bool real = !TAIL || 5 * I + u < NM;
+    if (real) {
         lmax = fmaxf(lmax, l2);
         lmin = fminf(lmin, l2);
-        if (valid) *ocol = fmaf(l2 * 0.30102999566398120f, 0.25f, 1.0f);      // (log10 + 4) / 4, same roundings as Whisper's two steps
     }
+    if (valid && real) *ocol = fmaf(l2 * 0.30102999566398120f, 0.25f, 1.0f);      // (log10 + 4) / 4, same roundings as Whisper's two steps
+    ocol += step;
 }
-// seg[q]: first mel of the group with more than q quads (seg[0] = group start, seg[4] = group end)
-__device__ __forceinline__ void mel_group(const uint2* __restrict__ s_desc, const char* __restrict__ s_flat, const int (&seg)[5],
-                                          const float* __restrict__ Pf, float* ocol, size_t Tstride, bool valid,
-                                          float& lmax, float& lmin) {
-    ocol += (size_t)seg[0] * Tstride;
-    mel_run<1>(s_desc, s_flat, seg[0], seg[1], (const char*)Pf, ocol, Tstride, valid, lmax, lmin);
-    mel_run<2>(s_desc, s_flat, seg[1], seg[2], (const char*)Pf, ocol, Tstride, valid, lmax, lmin);
-    mel_run<3>(s_desc, s_flat, seg[2], seg[3], (const char*)Pf, ocol, Tstride, valid, lmax, lmin);
-    mel_run<4>(s_desc, s_flat, seg[3], seg[4], (const char*)Pf, ocol, Tstride, valid, lmax, lmin);
+template <int NM, int... Is>
+__device__ __forceinline__ void mel_slots(std::integer_sequence<int, Is...>, const float4* __restrict__ wq, const unsigned* __restrict__ so,
+                                          const float* __restrict__ Pf, float* ocol, size_t step, bool valid, int u, float& lmax, float& lmin) {
+    (mel_slot<NM, Is>(wq, so, (const char*)Pf, ocol, step, valid, u, lmax, lmin), ...);
 }
 
 #ifndef B2A_EMU
@@ -248,12 +250,16 @@ constexpr int LM_CHUNKS = LM_TILE / 8;                                  // s16 i
 constexpr int LM_PRE4 = (LM_CHUNKS + LM_THREADS - 1) / LM_THREADS;      // 5 chunks per thread
 static_assert(LM_TILE % 8 == 0 && (kHop / 2) % 4 == 0, "a 16-byte chunk never straddles a hop (the skew changes between hops)");
 
+constexpr int LM_MELW_WORDS = LM_ROLES * MelC<128>::QUADS * 4;            // mel weights, one block of QUADS quads per warp (128 mels: the larger)
+constexpr int LM_MELOFF_WORDS = (LM_ROLES * MelC<128>::SLOTS + 3) / 4 * 4;  // first power bin (byte offset) of every (warp, slot)
+static_assert(MelC<80>::QUADS <= MelC<128>::QUADS && MelC<80>::SLOTS <= MelC<128>::SLOTS, "shared-memory mel tables are sized for 128 mels");
+
 // shared-memory footprint: the s16 variant keeps the tile as raw sample pairs (half the bytes) and both variants put the
 // power spectra into the exchange buffer once it has been consumed => 67 KB (s16: 3 CTAs per SM) / 78 KB (f32: 2)
 template <int FMT> struct LmSmem {
     static constexpr int TILE_WORDS = ((FMT == B2A_FMT_S16 ? (LM_TILE / 2 + (LM_TILE / kHop + 2)) : LM_TILE_WORDS) + 3) / 4 * 4;   // keeps the buffers behind it 16-byte aligned
     static constexpr int HOPW = FMT == B2A_FMT_S16 ? (kHop / 2 + 1) : LM_HOPW;      // words between frames (81: odd, conflict free)
-    static constexpr int WORDS = TILE_WORDS + 2 * LM_FRAMES * LM_EXP + kNFFT + 2 * 200 + 2 * 202 + 8 + kMelFlatN128 + 2 * kMelMaxMels + 12 * LM_GBATCH;   // + LM_GBATCH x 6 int64 gather descriptors
+    static constexpr int WORDS = TILE_WORDS + 2 * LM_FRAMES * LM_EXP + kNFFT + 2 * 200 + 2 * 202 + 8 + LM_MELW_WORDS + LM_MELOFF_WORDS + 12 * LM_GBATCH;   // + LM_GBATCH x 6 int64 gather descriptors
     static constexpr int CTAS = FMT == B2A_FMT_S16 ? LM_S16_CTAS : 2;
 };
 
@@ -270,17 +276,17 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
     float2* s_tw200 = (float2*)(s_win + kNFFT);                         // 200
     float2* s_tw400 = s_tw200 + 200;                                    // 201 (+1 pad)
     float* s_red = (float*)(s_tw400 + 202);                             // 8
-    float4* s_flat4 = (float4*)(s_red + 8);                             // padded mel weights (<= kMelFlatN128 floats, 16-byte aligned)
-    uint2* s_desc = (uint2*)(s_flat4 + kMelFlatN128 / 4);                // n_mels filter descriptors
-    i64* s_g = (i64*)(s_desc + kMelMaxMels);                            // [LM_GBATCH][6]: lo0, add0, bound1, add1, bound2, mode of the CTA's next gathered tiles
+    float4* s_flat4 = (float4*)(s_red + 8);                             // mel weights: [warp][QUADS] quads (16-byte aligned)
+    unsigned* s_moff = (unsigned*)(s_flat4 + LM_MELW_WORDS / 4);         // [warp][SLOTS] byte offset of the slot's first power bin
+    i64* s_g = (i64*)(s_moff + LM_MELOFF_WORDS);                          // [LM_GBATCH][6]: lo0, add0, bound1, add1, bound2, mode of the CTA's next gathered tiles
 
     const int tid = threadIdx.x;
     const LogMelTables* tab = p.tab;
     for (int i = tid; i < kNFFT; i += LM_THREADS) s_win[i] = tab->win[i] * (S16 ? (1.0f / 32768.0f) : 1.0f);   // s16 tile holds raw integers
     for (int i = tid; i < 200; i += LM_THREADS) s_tw200[i] = tab->tw200[i];
     for (int i = tid; i < kNBins; i += LM_THREADS) s_tw400[i] = tab->tw400[i];
-    for (int i = tid; i < (NM == 80 ? kMelFlatN80 : kMelFlatN128); i += LM_THREADS) ((float*)s_flat4)[i] = NM == 80 ? kMelFlat80[i] : kMelFlat128[i];
-    for (int i = tid; i < 2 * NM; i += LM_THREADS) ((unsigned*)s_desc)[i] = NM == 80 ? kMelDesc80[i] : kMelDesc128[i];
+    for (int i = tid; i < LM_ROLES * MelC<NM>::QUADS * 4; i += LM_THREADS) ((float*)s_flat4)[i] = NM == 80 ? kMelUW80[i] : kMelUW128[i];
+    for (int i = tid; i < LM_ROLES * MelC<NM>::SLOTS; i += LM_THREADS) s_moff[i] = NM == 80 ? kMelUOff80[i] : kMelUOff128[i];
     for (int i = tid; i < LM_FRAMES * LM_EXP; i += LM_THREADS) s_ex[i] = make_float2(0.0f, 0.0f);   // padded taps may read slots no stage writes
 
     i64 n_act = p.n;
@@ -305,12 +311,8 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
     const float2* pex_b = s_ex + LM_EXP * f + 20 * k1b;
     float* pP = s_P + LM_PP * f;
     const int elem = S16 ? 2 : 4;
-    // this warp's group of mels (balanced by cost at table-generation time)
-    int mseg[5];
-#pragma unroll
-    for (int q = 0; q < 5; q++) {
-            mseg[q] = u == 0 ? MelSeg<NM, 0>::v(q) : u == 1 ? MelSeg<NM, 1>::v(q) : u == 2 ? MelSeg<NM, 2>::v(q) : u == 3 ? MelSeg<NM, 3>::v(q) : MelSeg<NM, 4>::v(q);
-    }
+    const float4* mel_wq = s_flat4 + u * MelC<NM>::QUADS;    // this warp's mels: u, u + 5, u + 10, ...
+    const unsigned* mel_so = s_moff + u * MelC<NM>::SLOTS;
 
     float run_max = -3.0e38f;
     i64 prev_slot = -1;                          // tile_min slot of the previous work item (written one barrier later)
@@ -586,13 +588,13 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
         }
         __syncthreads();   // power spectra complete
 
-        // ---- mel projection + log10 + store: warp u = mel group, lane = frame ----
+        // ---- mel projection + log10 + store: warp u = mels u, u + 5, ..., lane = frame ----
         {
             const i64 t = t0 + f;
             const bool valid = t < T;
-            float* ocol = p.out + (size_t)b * (size_t)NM * (size_t)T + (valid ? t : 0);
+            float* ocol = p.out + ((size_t)b * (size_t)NM + (size_t)u) * (size_t)T + (valid ? t : 0);
             float lmax = -3.0e38f, lmin = 3.0e38f;
-            mel_group(s_desc, (const char*)s_flat4, mseg, pP, ocol, (size_t)T, valid, lmax, lmin);
+            mel_slots<NM>(std::make_integer_sequence<int, MelC<NM>::SLOTS>{}, mel_wq, mel_so, pP, ocol, (size_t)LM_ROLES * (size_t)T, valid, u, lmax, lmin);
             if (valid) run_max = fmaxf(run_max, lmax * 0.30102999566398120f);
             // per-tile minimum (lets mel_floor skip tiles that need no clamping): published after the next barrier
             lmin = warp_reduce_min_f(valid ? lmin : 3.0e38f);
