@@ -244,6 +244,32 @@ static inline void cp_async8(void* smem_dst, const void* gsrc) { memcpy(smem_dst
 static inline void cp_async_drain() {}
 #endif
 
+// Split barriers: two of the four block-wide barriers of a tile are arrive / wait pairs on shared-memory mbarriers (one
+// arrival per warp): a warp ARRIVES as soon as it is done with the contested buffer, keeps working on registers, and WAITS
+// only where it needs the others.  (bar.arrive + bar.sync on a named barrier cannot do this when every thread does both:
+// the sync counts as an arrival too.)  The emulation build turns the pair into one full barrier at the wait.
+#ifndef B2A_EMU
+__device__ __forceinline__ void lm_bar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void lm_arrive(unsigned long long* bar, int lane) {
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void lm_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    } while (!done);
+}
+#else
+static inline void lm_bar_init(unsigned long long*, unsigned) {}
+static inline void lm_arrive(unsigned long long*, int) {}
+static inline void lm_wait(unsigned long long*, unsigned) { __syncthreads(); }
+#endif
+
 constexpr int LM_PAIRS = LM_TILE / 2;                                   // 2680 sample pairs per tile
 constexpr int LM_PRE = (LM_PAIRS + LM_THREADS - 1) / LM_THREADS;        // 17 pairs per thread (f32 input: cp.async of pairs)
 constexpr int LM_CHUNKS = LM_TILE / 8;                                  // s16 input: 670 chunks of 8 samples (16 bytes) per tile
@@ -259,7 +285,7 @@ static_assert(MelC<80>::QUADS <= MelC<128>::QUADS && MelC<80>::SLOTS <= MelC<128
 template <int FMT> struct LmSmem {
     static constexpr int TILE_WORDS = ((FMT == B2A_FMT_S16 ? (LM_TILE / 2 + (LM_TILE / kHop + 2)) : LM_TILE_WORDS) + 3) / 4 * 4;   // keeps the buffers behind it 16-byte aligned
     static constexpr int HOPW = FMT == B2A_FMT_S16 ? (kHop / 2 + 1) : LM_HOPW;      // words between frames (81: odd, conflict free)
-    static constexpr int WORDS = TILE_WORDS + 2 * LM_FRAMES * LM_EXP + kNFFT + 2 * 200 + 2 * 202 + 8 + LM_MELW_WORDS + LM_MELOFF_WORDS + 12 * LM_GBATCH;   // + LM_GBATCH x 6 int64 gather descriptors
+    static constexpr int WORDS = TILE_WORDS + 2 * LM_FRAMES * LM_EXP + kNFFT + 2 * 200 + 2 * 202 + 12 + LM_MELW_WORDS + LM_MELOFF_WORDS + 12 * LM_GBATCH;   // + LM_GBATCH x 6 int64 gather descriptors
     static constexpr int CTAS = FMT == B2A_FMT_S16 ? LM_S16_CTAS : 2;
 };
 
@@ -276,7 +302,8 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
     float2* s_tw200 = (float2*)(s_win + kNFFT);                         // 200
     float2* s_tw400 = s_tw200 + 200;                                    // 201 (+1 pad)
     float* s_red = (float*)(s_tw400 + 202);                             // 8
-    float4* s_flat4 = (float4*)(s_red + 8);                             // mel weights: [warp][QUADS] quads (16-byte aligned)
+    unsigned long long* s_bar = (unsigned long long*)(s_red + 8);       // 2 mbarriers: [0] tile done (power spectra consumed, next samples in place), [1] exchange consumed
+    float4* s_flat4 = (float4*)(s_red + 12);                            // mel weights: [warp][QUADS] quads (16-byte aligned)
     unsigned* s_moff = (unsigned*)(s_flat4 + LM_MELW_WORDS / 4);         // [warp][SLOTS] byte offset of the slot's first power bin
     i64* s_g = (i64*)(s_moff + LM_MELOFF_WORDS);                          // [LM_GBATCH][6]: lo0, add0, bound1, add1, bound2, mode of the CTA's next gathered tiles
 
@@ -288,6 +315,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
     for (int i = tid; i < LM_ROLES * MelC<NM>::QUADS * 4; i += LM_THREADS) ((float*)s_flat4)[i] = NM == 80 ? kMelUW80[i] : kMelUW128[i];
     for (int i = tid; i < LM_ROLES * MelC<NM>::SLOTS; i += LM_THREADS) s_moff[i] = NM == 80 ? kMelUOff80[i] : kMelUOff128[i];
     for (int i = tid; i < LM_FRAMES * LM_EXP; i += LM_THREADS) s_ex[i] = make_float2(0.0f, 0.0f);   // padded taps may read slots no stage writes
+    if (tid == 0) { lm_bar_init(s_bar, LM_ROLES); lm_bar_init(s_bar + 1, LM_ROLES); }                // visible to all after the first block-wide barrier
 
     i64 n_act = p.n;
     if (p.d_n) { n_act = *p.d_n; if (n_act > p.n) n_act = p.n; if (n_act < 0) n_act = 0; }
@@ -477,7 +505,8 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
         else load_generic(sc);
     }
 
-    for (i64 work = blockIdx.x; work < n_work; work += gridDim.x) {
+    unsigned it = 0;                                  // this CTA's iteration count: mbarrier phase parities
+    for (i64 work = blockIdx.x; work < n_work; work += gridDim.x, it++) {
         int b;
         i64 tile;
         split_work(work, b, tile);
@@ -494,7 +523,8 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
         }
         if (nwork < n_work) nsc = locate(nwork, nit % LM_GBATCH);
 
-        __syncthreads();   // s_tile (and, first time, the tables) visible; previous tile's s_red written
+        // s_tile (and, first time, the tables) visible; previous tile's s_red written and its power spectra consumed
+        if (it == 0) __syncthreads(); else lm_wait(s_bar, (it - 1) & 1);
         if (tid == 0 && prev_slot >= 0) {
             const float l2 = fminf(fminf(fminf(s_red[0], s_red[1]), fminf(s_red[2], s_red[3])), s_red[4]);
             p.tile_min[prev_slot] = float_to_key(fmaf(l2 * 0.30102999566398120f, 0.25f, 1.0f));
@@ -535,7 +565,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
         }
         __syncthreads();   // exchange complete; every stage-1 read of s_tile is done
 
-        // ---- next tile -> s_tile (overlaps stage 2 + mel projection) ----
+        // ---- next tile -> s_tile (its registers are free again before stage 2 needs them) ----
         if (nsc.mode == 1) {
             if constexpr (GATHER) store_s16_chunks(nsc, pre4);
             else store_s16_pairs(pre);
@@ -552,9 +582,10 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
                 for (int n2 = 0; n2 < 20; n2++) { const float2 v = pex_a[n2]; xa[n2] = {v.x, v.y}; }
 #pragma unroll
                 for (int n2 = 0; n2 < 20; n2++) { const float2 v = pex_b[n2]; xb[n2] = {v.x, v.y}; }
-                __syncthreads();   // the exchange buffer is consumed: the power spectra may overwrite it
+                lm_arrive(s_bar + 1, f);       // this warp has consumed its part of the exchange buffer ...
                 dft20(xa, za);
                 dft20(xb, zb);
+                lm_wait(s_bar + 1, it & 1);    // ... and the power spectra may overwrite it once every warp has
             }
             if (u != 0) {
                 // Z[k] = za[j] (k = u+10j),  Z[200-k] = zb[19-j]
@@ -607,6 +638,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
             run_max = -3.0e38f;
         }
         if (nsc.mode == 2) cp_async_drain();
+        if (nwork < n_work) lm_arrive(s_bar, f);   // done with this tile's power spectra; the next tile's samples are in place
     }
     __syncthreads();
     if (tid == 0 && prev_slot >= 0) {
