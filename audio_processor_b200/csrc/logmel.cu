@@ -45,6 +45,13 @@ constexpr int LM_EXP = 201;                         // exchange pitch per frame,
 #ifndef LM_S16_CTAS
 #define LM_S16_CTAS 3
 #endif
+#ifndef LM_S1_UNROLL
+#define LM_S1_UNROLL 1                              // stage-1 column loop (4 iterations)
+#endif
+constexpr int kS1Unroll = LM_S1_UNROLL;
+#ifndef LM_S1_PREFETCH
+#define LM_S1_PREFETCH 0                            // s16: load the next column's raw words before this column's butterflies
+#endif
 constexpr int LM_GBATCH = 32;                       // gathered tiles whose segment descriptors are looked up together
 constexpr int LM_PP = 203;                          // power-spectrum pitch per frame, in floats (odd)
 
@@ -211,7 +218,7 @@ __device__ __forceinline__ void mel_slot(const float4* __restrict__ wq, const un
         lmin = fminf(lmin, l2);
     }
     if (valid && real) *ocol = fmaf(l2 * 0.30102999566398120f, 0.25f, 1.0f);      // (log10 + 4) / 4, same roundings as Whisper's two steps
-    ocol += step;
+    ocol += step;      // (a byte pointer with a byte step measured 4 % slower: the compiler then keeps every slot's address live)
 }
 template <int NM, int... Is>
 __device__ __forceinline__ void mel_slots(std::integer_sequence<int, Is...>, const float4* __restrict__ wq, const unsigned* __restrict__ so,
@@ -538,14 +545,25 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
         }
 
         // ---- stage 1: radix-10 butterflies over n1 for n2 = u + 5j, twiddle, transpose into s_ex ----
-#pragma unroll 1
+#if LM_S1_PREFETCH
+        unsigned raw[10];
+        if (S16) {
+#pragma unroll
+            for (int n1 = 0; n1 < 10; n1++) raw[n1] = ps16[20 * n1 + n1 / 4];
+        }
+#endif
+#pragma unroll kS1Unroll
         for (int j = 0; j < 4; j++) {
             cpx x[10], y[10];
 #pragma unroll
             for (int n1 = 0; n1 < 10; n1++) {
                 float2 xv;
                 if (S16) {
+#if LM_S1_PREFETCH
+                    const unsigned w = raw[n1];
+#else
                     const unsigned w = ps16[5 * j + 20 * n1 + n1 / 4];
+#endif
                     xv = make_float2((float)(short)(w & 0xffff), (float)(short)(w >> 16));
                 } else {
                     xv = *(const float2*)(ps + 10 * j + 40 * n1 + LM_SKEW * (n1 / 4));
@@ -554,6 +572,12 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
                 x[n1].r = xv.x * wv.x;
                 x[n1].i = xv.y * wv.y;
             }
+#if LM_S1_PREFETCH
+            if (S16 && j < 3) {                 // the next column's raw words travel under this column's butterflies
+#pragma unroll
+                for (int n1 = 0; n1 < 10; n1++) raw[n1] = ps16[5 * (j + 1) + 20 * n1 + n1 / 4];
+            }
+#endif
             dft10(x, y);
 #pragma unroll
             for (int k1 = 0; k1 < 10; k1++) {
@@ -652,51 +676,51 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
 }
 
 // K5: out = max(out, ((gmax - 8) + 4) / 4) in place; tiles whose minimum already clears the floor are skipped.
-// One warp per 32-frame tile (lane = frame): the skip test is a single broadcast load per warp.
+// A block screens `tpc` consecutive 32-frame tiles (one thread each: one load of the tile's minimum), collects the tiles below
+// the floor in shared memory, and then all its warps walk that list in items of (tile, 16 rows): lane = frame, 16 loads in
+// flight per lane.  The grid is a single wave (tpc = tiles / 296 for one clip), so the kernel is about four dependent memory
+// latencies long.  (Round 1: one warp per tile walked its 80 rows alone while the warps of clean tiles exited: 16 us at cfg2
+// in almost three waves of blocks.)
+constexpr int LM_FLOOR_THREADS = 512;
 template <int NM>
-__global__ void __launch_bounds__(256, 3) mel_floor_kernel(LogMelParams p, int chunk) {
+__global__ void __launch_bounds__(LM_FLOOR_THREADS, 2) mel_floor_kernel(LogMelParams p, int tpc) {
+    constexpr int R = 16, GROUPS = NM / R;
+    static_assert(NM % R == 0, "row groups of 16");
+    __shared__ int s_count;
+    __shared__ int s_b[LM_FLOOR_THREADS], s_tile[LM_FLOOR_THREADS];
+    __shared__ float s_floor[LM_FLOOR_THREADS];
     i64 n_act = p.n;
     if (p.d_n) { n_act = *p.d_n; if (n_act > p.n) n_act = p.n; if (n_act < 0) n_act = 0; }
     const i64 T = (n_act + p.padding) / kHop;
     const i64 tiles = (T + LM_FRAMES - 1) / LM_FRAMES;
     const i64 total = tiles * p.batch;
-    const int lane = threadIdx.x & 31;
-    // A warp checks `chunk` (1..32) consecutive tiles with one load per lane, then walks only the tiles below the floor,
-    // 16 rows in flight per round.  The host picks chunk = 1 for a few thousand tiles (one clip: the
-    // kernel is three dependent memory latencies long) and 32 for hundreds of thousands (chunk batches: the tile_min latency
-    // and the work -> (clip, tile) division are paid once per 32 tiles).
-    constexpr int R = 16;                      // 16 values + 16 addresses: 80 registers per thread, 3 CTAs per SM
-    const i64 stride = (i64)gridDim.x * (blockDim.x >> 5) * chunk;
-    for (i64 w0 = ((i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * chunk; w0 < total; w0 += stride) {
-        const i64 work = w0 + lane;
-        int b = 0, tile = 0;
-        float floor_l = 0.0f;
-        bool need = false;
-        if (lane < chunk && work < total) {
-            b = (int)(work / tiles);
-            tile = (int)(work - (i64)b * tiles);
-            floor_l = ((key_to_float(p.gmax_key[p.per_clip ? b : 0]) - 8.0f) + 4.0f) * 0.25f;
-            need = key_to_float(p.tile_min[(size_t)b * (size_t)p.tiles_cap + (size_t)tile]) < floor_l;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    const i64 work = (i64)blockIdx.x * tpc + tid;
+    if (tid < tpc && work < total) {
+        const int b = (int)(work / tiles);
+        const int tile = (int)(work - (i64)b * tiles);
+        const float floor_l = ((key_to_float(p.gmax_key[p.per_clip ? b : 0]) - 8.0f) + 4.0f) * 0.25f;
+        if (key_to_float(p.tile_min[(size_t)b * (size_t)p.tiles_cap + (size_t)tile]) < floor_l) {
+            const int slot = atomicAdd(&s_count, 1);
+            s_b[slot] = b; s_tile[slot] = tile; s_floor[slot] = floor_l;
         }
-        unsigned m = __ballot_sync(0xFFFFFFFFu, need);
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const float floor_v = __shfl_sync(0xFFFFFFFFu, floor_l, src);
-            const int bb = __shfl_sync(0xFFFFFFFFu, b, src);
-            const i64 t = (i64)__shfl_sync(0xFFFFFFFFu, tile, src) * LM_FRAMES + lane;
-            if (t >= T) continue;
-            float* q = p.out + (size_t)bb * (size_t)NM * (size_t)T + t;
-#pragma unroll 1
-            for (int m0 = 0; m0 < NM; m0 += R, q += (size_t)R * (size_t)T) {
-                float v[R];
+    }
+    __syncthreads();
+    const int items = s_count * GROUPS;
+    for (int it = warp; it < items; it += LM_FLOOR_THREADS / 32) {
+        const int e = it / GROUPS, g = it - e * GROUPS;
+        const i64 t = (i64)s_tile[e] * LM_FRAMES + lane;
+        if (t >= T) continue;
+        const float floor_v = s_floor[e];
+        float* q = p.out + ((size_t)s_b[e] * (size_t)NM + (size_t)g * R) * (size_t)T + t;
+        float v[R];
 #pragma unroll
-                for (int e = 0; e < R; e++) v[e] = q[(size_t)e * (size_t)T];
+        for (int r = 0; r < R; r++) v[r] = q[(size_t)r * (size_t)T];
 #pragma unroll
-                for (int e = 0; e < R; e++)
-                    if (v[e] < floor_v) q[(size_t)e * (size_t)T] = floor_v;
-            }
-        }
+        for (int r = 0; r < R; r++)
+            if (v[r] < floor_v) q[(size_t)r * (size_t)T] = floor_v;
     }
 }
 
@@ -818,16 +842,15 @@ int logmel_launch(const void* d_audio, int fmt, i64 batch, i64 n, i64 row_stride
     B2A_LAUNCH(k4, (unsigned)grid, LM_THREADS, smem, stream, p);
     B2A_CHECK_LAUNCH("stft_mel_kernel");
     }
-    i64 chunk5 = work / (148 * 8 * 8);                                     // tiles per warp and round: fill the machine first
-    chunk5 = chunk5 < 1 ? 1 : chunk5 > 32 ? 32 : chunk5;
-    const i64 warps5 = (work + chunk5 - 1) / chunk5;
-    const i64 grid5 = (warps5 + 7) / 8 < 148 * 8 ? (warps5 + 7) / 8 : 148 * 8;
+    i64 tpc = (work + 148 * 2 - 1) / (148 * 2);                            // tiles per block: one wave of two blocks per SM ...
+    tpc = tpc < 32 ? 32 : tpc > LM_FLOOR_THREADS ? LM_FLOOR_THREADS : tpc;    // ... of at least a warp's worth, at most a thread each
+    const i64 grid5 = (work + tpc - 1) / tpc;
     if (n_mels == 80) {
         auto k5 = mel_floor_kernel<80>;
-        B2A_LAUNCH(k5, (unsigned)grid5, 256, 0, stream, p, (int)chunk5);
+        B2A_LAUNCH(k5, (unsigned)grid5, LM_FLOOR_THREADS, 0, stream, p, (int)tpc);
     } else {
         auto k5 = mel_floor_kernel<128>;
-        B2A_LAUNCH(k5, (unsigned)grid5, 256, 0, stream, p, (int)chunk5);
+        B2A_LAUNCH(k5, (unsigned)grid5, LM_FLOOR_THREADS, 0, stream, p, (int)tpc);
     }
     B2A_CHECK_LAUNCH("mel_floor_kernel");
     return B2A_OK;

@@ -42,4 +42,15 @@ for path in libs:
                               C.c_void_p(ns.data_ptr()), C.c_void_p(kp.data_ptr()), C.c_void_p(info.data_ptr()), pptr, pwsb, None)
         assert rc == 0, lib.b2a_last_error()
     t_p = timeit(pipe)
-    print("%-40s log_mel(288k frames) %7.1f us   pipeline(1 h clip) %7.1f us" % (os.path.basename(path), t_lm, t_p), flush=True)
+    # cfg3-shaped: 512 x 30 s of f32, 128 mels (an eighth of cfg3)
+    B3, n3 = 512, 480000
+    if "x3" not in globals():
+        globals()["x3"] = torch.randn((B3, n3), generator=g, device="cuda") * 0.1
+    out3 = torch.empty((B3, 128, n3 // 160), dtype=torch.float32, device="cuda")
+    wsb3 = lib.b2a_log_mel_workspace_bytes(B3, n3, 0)
+    ws3 = torch.empty(wsb3 + 256, dtype=torch.uint8, device="cuda")
+    def lm3():
+        rc = lib.b2a_log_mel(C.c_void_p(x3.data_ptr()), 1, B3, n3, n3, None, 0, 128, 0, C.c_void_p(out3.data_ptr()), None, C.c_void_p(ws3.data_ptr()), wsb3, None)
+        assert rc == 0, lib.b2a_last_error()
+    t_3 = timeit(lm3, 10)
+    print("%-28s log_mel(288k frames s16, 80) %7.1f us   pipeline(1 h clip) %7.1f us   log_mel(512 x 30 s f32, 128) %7.1f us" % (os.path.basename(path), t_lm, t_p, t_3), flush=True)
