@@ -191,9 +191,24 @@ __device__ __forceinline__ float lg2_fast(float x) {          // x >= 1e-10: nev
     return __log2f(x);
 #endif
 }
+// (log10(x) + 4) / 4 from log2(x), with the same roundings as Whisper's two steps (silence comes out as exactly -1.5)
+__device__ __forceinline__ float mel_out_value(float l2) { return fmaf(l2 * 0.30102999566398120f, 0.25f, 1.0f); }
+
+// predicated global store: the address is formed unconditionally and the store stays one predicated STG (written as
+// `if (ok) *p = v` with a 64-bit address the compiler branches around every store: 16 BSSY / BRA / BSYNC blocks per tile)
+__device__ __forceinline__ void st_f32_if(float* p, float v, bool ok) {
+#ifndef B2A_EMU
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.f32 [%0], %1;\n\t}" ::"l"(p), "f"(v), "r"((unsigned)ok));
+#else
+    if (ok) *p = v;
+#endif
+}
+
+// one slot: returns log2(mel), or NaN for a slot without a mel (fmaxf / fminf skip NaN).  Store addresses are a 64-bit base
+// plus a 32-bit offset (one IMAD.WIDE each): a clip's [n_mels][T] block stays below 2^31 floats (checked at launch)
 template <int NM, int I>
-__device__ __forceinline__ void mel_slot(const float4* __restrict__ wq, const unsigned* __restrict__ so, const char* __restrict__ Pf,
-                                         float*& ocol, size_t step, bool valid, int u, float& lmax, float& lmin) {
+__device__ __forceinline__ float mel_slot(const float4* __restrict__ wq, const unsigned* __restrict__ so, const char* __restrict__ Pf,
+                                          float* __restrict__ obase, unsigned o0, unsigned ostep, bool valid, int u) {
     constexpr int NT = MelC<NM>::nt[I], Q0 = MelC<NM>::qoff[I], NQ = (NT + 3) / 4;
     constexpr bool TAIL = 5 * I + 4 >= NM;                    // the last slot of 128 mels: warps 3 and 4 have no mel
     const float* pf = (const float*)(Pf + so[I]);
@@ -213,17 +228,24 @@ __device__ __forceinline__ void mel_slot(const float4* __restrict__ wq, const un
     }
     const float l2 = lg2_fast(fmaxf(a0 + a1, 1e-10f));
     const bool real = !TAIL || 5 * I + u < NM;
-    if (real) {
-        lmax = fmaxf(lmax, l2);
-        lmin = fminf(lmin, l2);
-    }
-    if (valid && real) *ocol = fmaf(l2 * 0.30102999566398120f, 0.25f, 1.0f);      // (log10 + 4) / 4, same roundings as Whisper's two steps
-    ocol += step;      // (a byte pointer with a byte step measured 4 % slower: the compiler then keeps every slot's address live)
+    st_f32_if(obase + (o0 + (unsigned)I * ostep), mel_out_value(l2), valid && real);
+    return real ? l2 : __int_as_float(0x7fffffff);
+}
+// two slots and one three-input FMNMX3 each for the running maximum and minimum
+template <int NM, int I2>
+__device__ __forceinline__ void mel_pair(const float4* __restrict__ wq, const unsigned* __restrict__ so, const char* __restrict__ Pf,
+                                         float* __restrict__ obase, unsigned o0, unsigned ostep, bool valid, int u, float& lmax, float& lmin) {
+    const float x = mel_slot<NM, 2 * I2>(wq, so, Pf, obase, o0, ostep, valid, u);
+    const float y = mel_slot<NM, 2 * I2 + 1>(wq, so, Pf, obase, o0, ostep, valid, u);
+    lmax = fmaxf(fmaxf(lmax, x), y);
+    lmin = fminf(fminf(lmin, x), y);
 }
 template <int NM, int... Is>
 __device__ __forceinline__ void mel_slots(std::integer_sequence<int, Is...>, const float4* __restrict__ wq, const unsigned* __restrict__ so,
-                                          const float* __restrict__ Pf, float* ocol, size_t step, bool valid, int u, float& lmax, float& lmin) {
-    (mel_slot<NM, Is>(wq, so, (const char*)Pf, ocol, step, valid, u, lmax, lmin), ...);
+                                          const float* __restrict__ Pf, float* __restrict__ obase, unsigned o0, unsigned ostep, bool valid, int u,
+                                          float& lmax, float& lmin) {
+    static_assert(MelC<NM>::SLOTS == 2 * sizeof...(Is), "slots are walked in pairs");
+    (mel_pair<NM, Is>(wq, so, (const char*)Pf, obase, o0, ostep, valid, u, lmax, lmin), ...);
 }
 
 #ifndef B2A_EMU
@@ -522,7 +544,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
         Src nsc;
         nsc.mode = -1;
         nsc.g = s_g;
-        const int nit = (int)((work - blockIdx.x) / gridDim.x) + 1;              // iteration index of the next tile
+        const int nit = (int)it + 1;                                             // iteration index of the next tile
         if (gather && nit % LM_GBATCH == 0) {
             __syncthreads();                                                       // every reader of the old batch is done
             lookup_batch(nwork);
@@ -534,7 +556,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
         if (it == 0) __syncthreads(); else lm_wait(s_bar, (it - 1) & 1);
         if (tid == 0 && prev_slot >= 0) {
             const float l2 = fminf(fminf(fminf(s_red[0], s_red[1]), fminf(s_red[2], s_red[3])), s_red[4]);
-            p.tile_min[prev_slot] = float_to_key(fmaf(l2 * 0.30102999566398120f, 0.25f, 1.0f));
+            p.tile_min[prev_slot] = float_to_key(mel_out_value(l2));
         }
         // next tile's s16 samples travel global -> registers while stage 1 runs
         uint4 pre4[GATHER ? LM_PRE4 : 1];
@@ -647,9 +669,9 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
         {
             const i64 t = t0 + f;
             const bool valid = t < T;
-            float* ocol = p.out + ((size_t)b * (size_t)NM + (size_t)u) * (size_t)T + (valid ? t : 0);
+            float* obase = p.out + (size_t)b * (size_t)NM * (size_t)T + (valid ? t : 0);
             float lmax = -3.0e38f, lmin = 3.0e38f;
-            mel_slots<NM>(std::make_integer_sequence<int, MelC<NM>::SLOTS>{}, mel_wq, mel_so, pP, ocol, (size_t)LM_ROLES * (size_t)T, valid, u, lmax, lmin);
+            mel_slots<NM>(std::make_integer_sequence<int, MelC<NM>::SLOTS / 2>{}, mel_wq, mel_so, pP, obase, (unsigned)u * (unsigned)T, (unsigned)LM_ROLES * (unsigned)T, valid, u, lmax, lmin);
             if (valid) run_max = fmaxf(run_max, lmax * 0.30102999566398120f);
             // per-tile minimum (lets mel_floor skip tiles that need no clamping): published after the next barrier
             lmin = warp_reduce_min_f(valid ? lmin : 3.0e38f);
@@ -667,7 +689,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
     __syncthreads();
     if (tid == 0 && prev_slot >= 0) {
         const float l2 = fminf(fminf(fminf(s_red[0], s_red[1]), fminf(s_red[2], s_red[3])), s_red[4]);
-        p.tile_min[prev_slot] = float_to_key(fmaf(l2 * 0.30102999566398120f, 0.25f, 1.0f));
+        p.tile_min[prev_slot] = float_to_key(mel_out_value(l2));
     }
     if (!p.per_clip) {
         const float bm = warp_reduce_max_f(run_max);
@@ -754,6 +776,10 @@ int logmel_launch(const void* d_audio, int fmt, i64 batch, i64 n, i64 row_stride
     if (d_n && batch != 1) { set_error("log_mel: device-side length needs batch == 1"); return B2A_EINVAL; }
     if (!d_n && n + padding <= 200) { set_error("log_mel: need more than 200 samples (reflect pad), got %lld", (long long)(n + padding)); return B2A_EINVAL; }
     if (norm_mode != B2A_NORM_WHISPER && norm_mode != B2A_NORM_PER_CLIP) { set_error("log_mel: bad norm_mode"); return B2A_EINVAL; }
+    if ((n + padding) / kHop * (i64)n_mels >= ((i64)1 << 31)) {           // 46 hours at 128 mels: the kernel addresses a clip's block with 32-bit offsets
+        set_error("log_mel: a clip's [n_mels][T] block must stay below 2^31 values (n + padding = %lld)", (long long)(n + padding));
+        return B2A_EUNSUPPORTED;
+    }
     if (ws_bytes < logmel_workspace_bytes(batch, n, padding)) { set_error("log_mel: workspace too small"); return B2A_EWORKSPACE; }
     const LogMelTables* tab = get_logmel_tables(n_mels);
     if (!tab) return B2A_EINVAL;
