@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
     const bool one_clip = p.batch == 1;
     const bool small_work = tiles * p.batch < ((i64)1 << 31);
     auto split_work = [&](i64 work, int& b, i64& tile) {
-        if (one_clip) { b = 0; tile = work; }
+        if (GATHER || one_clip) { b = 0; tile = work; }                      // (the gathering instantiation is always one clip)
         else if (small_work) { b = (int)((unsigned)work / (unsigned)tiles); tile = (i64)((unsigned)work - (unsigned)b * (unsigned)tiles); }
         else { b = (int)(work / tiles); tile = work - (i64)b * tiles; }
     };
@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
         int b;
         i64 tile;
         split_work(work, b, tile);
-        r.row = (const char*)p.audio + (size_t)b * (size_t)p.row_stride * elem;
+        r.row = GATHER ? (const char*)p.audio : (const char*)p.audio + (size_t)b * (size_t)p.row_stride * elem;
         r.q0 = tile * (LM_FRAMES * kHop) - 200;
         r.g = s_g + 6 * slot;
         if (gather) {
