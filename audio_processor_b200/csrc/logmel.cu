@@ -468,17 +468,24 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
     // segment bounds are multiples of 16 samples in both domains, so chunk k of a tile is aligned in the source, in the trimmed
     // output and against the segment split whenever the buffers themselves are (checked where the mode is chosen).
     // chunk k (pairs 4k .. 4k+3) lives at words 4k + k / 20 .. + 3 of the skewed tile (one word of skew per hop of 80 pairs)
+    // k = tid + 160 i, so k / 20 = tid / 20 + 8 i: every address below is one per-thread base plus a compile-time offset
+    static_assert(LM_THREADS % 20 == 0, "the chunk skew advances by whole words per round");
+    unsigned* const st_chunk0 = s_tile16 + 4 * tid + tid / 20;
     auto store_s16_chunks = [&](const Src& sc, const uint4 (&pre)[LM_PRE4]) {
+        uint4* const t16 = (uint4*)p.trim_out + ((sc.q0 >> 3) + tid);             // (used when trim_vec)
+        unsigned* const t4 = (unsigned*)p.trim_out + ((sc.q0 >> 1) + 4 * tid);
 #pragma unroll
         for (int i = 0; i < LM_PRE4; i++) {
-            const int k = tid + LM_THREADS * i;
-            if (k < LM_CHUNKS) {
-                unsigned* d = s_tile16 + 4 * k + k / 20;                           // raw pairs, converted where they are used
+            const int k0 = LM_THREADS * i;                                         // k = k0 + tid
+            if (k0 + LM_THREADS <= LM_CHUNKS || tid < LM_CHUNKS - k0) {
+                unsigned* d = st_chunk0 + (4 * k0 + k0 / 20);                      // raw pairs, converted where they are used
                 d[0] = pre[i].x; d[1] = pre[i].y; d[2] = pre[i].z; d[3] = pre[i].w;
-                if (k >= 25 && k < 25 + LM_FRAMES * kHop / 8) {                    // the tile's own 5120 samples
-                    if (trim_vec) ((uint4*)p.trim_out)[(sc.q0 >> 3) + k] = pre[i];
+                // the tile's own 5120 samples: chunks 25 .. 664
+                const bool own = (k0 >= 25 || tid >= 25 - k0) && (k0 + LM_THREADS <= 25 + LM_FRAMES * kHop / 8 || tid < 25 + LM_FRAMES * kHop / 8 - k0);
+                if (own) {
+                    if (trim_vec) t16[k0] = pre[i];
                     else {
-                        unsigned* o = (unsigned*)p.trim_out + (sc.q0 >> 1) + 4 * k;
+                        unsigned* o = t4 + 4 * k0;
                         o[0] = pre[i].x; o[1] = pre[i].y; o[2] = pre[i].z; o[3] = pre[i].w;
                     }
                 }
@@ -498,7 +505,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
     };
     // plain (not gathered) s16 tiles keep the 4-byte form: pair pr (samples 2pr, 2pr+1) lives at word pr + pr / 80 of the skewed
     // tile; 17 loads per thread in flight measured 2 % faster than 5 wide ones there, and rows need only 4-byte alignment
-    auto store_s16_pairs = [&](const unsigned (&pre)[LM_PRE]) {
+    auto store_s16_pairs = [&](const unsigned (&pre)[LM_PRE]) {         // (per-thread base + compile-time offsets measured 2 % slower here: spills)
 #pragma unroll
         for (int i = 0; i < LM_PRE; i++) {
             const int pr = tid + LM_THREADS * i;
@@ -530,7 +537,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
             if constexpr (GATHER) { uint4 pre[LM_PRE4]; fetch_s16_chunks(sc, pre); store_s16_chunks(sc, pre); }
             else { unsigned pre[LM_PRE]; fetch_s16_pairs(sc, pre); store_s16_pairs(pre); }
         }
-        else if (sc.mode == 2) { copy_f32_pairs(sc); cp_async_drain(); }
+        else if (!S16 && sc.mode == 2) { copy_f32_pairs(sc); cp_async_drain(); }
         else load_generic(sc);
     }
 
@@ -616,7 +623,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
             if constexpr (GATHER) store_s16_chunks(nsc, pre4);
             else store_s16_pairs(pre);
         }
-        else if (nsc.mode == 2) copy_f32_pairs(nsc);
+        else if (!S16 && nsc.mode == 2) copy_f32_pairs(nsc);
         else if (nsc.mode == 0) load_generic(nsc);
 
         // ---- stage 2: radix-20 butterflies over n2 for residues k1a, k1b; unpack conjugate pairs in registers ----
@@ -683,7 +690,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
             if (f == 0 && bm > -1.0e38f) atomicMax(p.gmax_key + b, float_to_key(bm));
             run_max = -3.0e38f;
         }
-        if (nsc.mode == 2) cp_async_drain();
+        if (!S16 && nsc.mode == 2) cp_async_drain();
         if (nwork < n_work) lm_arrive(s_bar, f);   // done with this tile's power spectra; the next tile's samples are in place
     }
     __syncthreads();
