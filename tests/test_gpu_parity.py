@@ -63,12 +63,13 @@ def test_resample_vs_oracles(ops, T, rate, ch, secs):
 
 
 
-@pytest.mark.parametrize("rate,spans", [(44100, 3), (48000, 5), (44100, 85), (48000, 120)])
+@pytest.mark.parametrize("rate,spans", [(44100, 3), (48000, 5), (44100, 85), (48000, 120), (44100, 301), (48000, 300)])
 def test_resample_tcgen05_tiles(ops, T, rate, spans):
     """the tcgen05 FIR (fir_tmem.cuh): 512-run spans = 4 class tiles of 128 rows; 85 / 120 spans over 37 span lanes give
     3-4 tiles per persistent CTA (column ring wrap, mbarrier phases, accumulator ring) + the mma.sync kernel behind the
-    last span, against the float64 restatement (<= 1 LSB), the real libswresample (>= 99.8 % identical, SAME length) and
-    the exact per-millisecond energies"""
+    last span — from 300 spans on (25 minutes) those 200 runs are computed by the FIR kernel's spare warps instead
+    (fir_dispatch.cu) — against the float64 restatement (<= 1 LSB), the real libswresample (>= 99.8 % identical, SAME
+    length) and the exact per-millisecond energies"""
     from oracle import resample_oracle as ro, swr_ref
     S = 441 if rate == 44100 else 480
     rng = np.random.default_rng(rate + spans)
@@ -471,7 +472,7 @@ def test_pipeline_graph_replay_matches_direct_calls(ops, T):
         T.cuda.synchronize()
         n = ops.launch_count() - n0
         per_call = n if per_call is None else per_call
-        assert n == per_call and n >= 6
+        assert n == per_call and n >= 5
         assert r.kept == kept0 and T.equal(r.pcm, pcm0) and T.equal(r.mel, mel0)
     assert len(plan._graphs) == 1
 
