@@ -67,6 +67,21 @@ __device__ __forceinline__ void resample_generic_output(const GenericParams& p, 
             float b0 = 0.f, b1 = 0.f;
             if (p.fmt == B2A_FMT_S16 && p.channels == 2 && (((uintptr_t)p.in) & 3) == 0) {
                 const int* s = (const int*)p.in + base;            // one 32-bit word per stereo frame
+                // 16 taps per round with all 32 loads issued up front (same accumulator order as the 4-tap loop below): the
+                // FIR's spare warps run this while the kernel saturates HBM, where a dependent round trip costs microseconds
+                for (; i + 15 < p.taps; i += 16) {
+                    int sv[16];
+                    float hv[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) { sv[j] = s[i + j]; hv[j] = h[i + j]; }
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        a0 = fmaf((float)__dp2a_lo(sv[j], 0x0101, 0), hv[j], a0);
+                        a1 = fmaf((float)__dp2a_lo(sv[j + 1], 0x0101, 0), hv[j + 1], a1);
+                        b0 = fmaf((float)__dp2a_lo(sv[j + 2], 0x0101, 0), hv[j + 2], b0);
+                        b1 = fmaf((float)__dp2a_lo(sv[j + 3], 0x0101, 0), hv[j + 3], b1);
+                    }
+                }
                 for (; i + 3 < p.taps; i += 4) {
                     a0 = fmaf((float)__dp2a_lo(s[i], 0x0101, 0), h[i], a0);
                     a1 = fmaf((float)__dp2a_lo(s[i + 1], 0x0101, 0), h[i + 1], a1);
