@@ -151,7 +151,9 @@ size_t b2a_log_mel_workspace_bytes(int64_t batch, int64_t n, int64_t padding);
  *   N_KEEP slot of a d_info block, so trimming and log-mel chain without a host round trip.
  * d_out: float32 [batch][n_mels][T], T = (n_actual + padding)/160, T contiguous (whisper layout).
  * d_frames_out (optional): device int64 receiving T.
- * n_mels: 80 or 128. */
+ * n_mels: 80 or 128.
+ * Limit: one clip's [n_mels][T] block must stay below 2^31 values (46 hours of audio at 128 mels);
+ *   longer rows return B2A_EUNSUPPORTED (split them: the floor couples only what one call sees). */
 int b2a_log_mel(const void* d_audio, int fmt, int64_t batch, int64_t n, int64_t row_stride,
                 const int64_t* d_n, int64_t padding, int n_mels, int norm_mode, float* d_out,
                 int64_t* d_frames_out, void* d_ws, size_t ws_bytes, b2a_stream_t stream);

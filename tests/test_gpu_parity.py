@@ -735,3 +735,21 @@ def test_convert_to_wav_from_compressed_containers(ops, T, tmp_path):
     open(bad, "wb").write(b"not audio at all" * 100)
     with pytest.raises(subprocess.CalledProcessError):
         fe.convert_to_wav(bad)
+
+
+def test_logmel_row_limit_is_reported(ops, T):
+    """a clip whose [n_mels][T] block would reach 2^31 values is refused with B2A_EUNSUPPORTED before anything is launched
+    (the kernel addresses a clip's block with 32-bit offsets; include/b2a.h)"""
+    import ctypes as C
+    from audio_processor_b200 import _lib
+    lib = _lib.lib()
+    x = T.zeros(1024, dtype=T.int16, device="cuda")
+    out = T.zeros(1024, dtype=T.float32, device="cuda")
+    n = 160 * ((1 << 31) // 128)                      # T * 128 == 2^31
+    n0 = ops.launch_count()
+    rc = lib.b2a_log_mel(C.c_void_p(x.data_ptr()), 0, 1, n, n, None, 0, 128, 0, C.c_void_p(out.data_ptr()), None,
+                         C.c_void_p(out.data_ptr()), 1 << 40, None)
+    assert rc == -2 and b"2^31" in lib.b2a_last_error()
+    assert ops.launch_count() == n0
+    assert lib.b2a_log_mel(C.c_void_p(x.data_ptr()), 0, 1, n - 160, n - 160, None, 0, 128, 0, C.c_void_p(out.data_ptr()), None,
+                           C.c_void_p(out.data_ptr()), 16, None) == -3      # one frame fewer passes the limit (and then fails on the workspace size)
