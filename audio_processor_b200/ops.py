@@ -281,7 +281,7 @@ class PipelinePlan:
             self.ws = torch.empty(self.ws_bytes + 512, dtype=torch.uint8, device=self.device)
             off = (-self.ws.data_ptr()) % 256
             self._ws_ptr = C.c_void_p(self.ws.data_ptr() + off)
-        self._graphs = {}        # (input pointer, silence parameters) -> captured CUDA graph of the 8 launches (run(graph=True))
+        self._graphs = {}        # (input pointer, silence parameters) -> captured CUDA graph of the clip's launches (run(graph=True))
         self._warm = set()
 
     def run(self, pcm, *, trim: bool = True, min_silence_len: int = 1000, silence_thresh: float = -40,
