@@ -27,7 +27,7 @@
 //   warps 6-7   the clip's edge outputs (reflect / symmetric extension at the head, the tail behind the last span),
 //               table-driven, one thread per output, spread over all CTAs: no separate edge kernel on the stream;
 //   warps 8-15  converters: warp w converts lane quadrant w % 4 (rows 32 (w % 4) + lane), frames 32 h .. 32 h + 31 of the
-//               piece with h = (w - 8) / 4: eight swizzle-aware LDS.128, 16 + 16 packed words, two tcgen05.st.
+//               piece with h = (w - 8) / 4: eight swizzle-aware LDS.128, 16 + 16 packed words (dp2a + PRMT), two tcgen05.st.
 //
 // Measured (profiles/r01_ncu_fir_tmem.txt, one-hour 44.1 kHz stereo clip): 147-153 us, DRAM 636 MB read + 127 MB written =
 // the algorithmic bytes, 5.1-5.3 TB/s = 78-81 % of the measured HBM copy peak (the mma.sync kernel: 236 us).
@@ -322,7 +322,11 @@ __global__ void __launch_bounds__(kFtThreads, 1) fir_tmem_kernel(const __grid_co
         for (i64 g = (i64)blockIdx.x * 2 + (warp - 6); g < groups; g += (i64)gridDim.x * 2) resample_generic_output(a.edge, g * 32 + lane);
     } else {
         // ===================================== converters: thread = row =====================================
-        constexpr unsigned KHV = 65536u + (0x6400u << 7);         // dp2a bias: (u >> 7) = f16 bits of 1024 + (hv + 512), u & 127 = lo
+        // dp2a bias.  u = 2 (L + R) + KHV2 puts the f16 bits of 1024 + (hv + 512) into bytes 1-2 (hv = (L + R) >> 7), 2 lo into
+        // byte 0 (lo = (L + R) & 127) and 0x64 into byte 3, so one PRMT per plane packs two frames: bytes (1, 2) of both words
+        // are the hv pair, bytes (0, 3) are the f16 pair 1024 + 2 lo.  (With the fields at bit 7 the packing took shifts and
+        // masks: 11 instead of 6 instructions per pair of frames, and the converters are 55 % of the kernel's instructions.)
+        constexpr unsigned KHV2 = 0x64000000u + 2u * (65536u + (0x6400u << 7));
         const int cw = warp - kFtCvtWarp0, q = cw & 3, h = cw >> 2;
         const int row = 32 * q + lane;
         const unsigned t_lane = (unsigned)(32 * q) << 16;
@@ -349,12 +353,12 @@ __global__ void __launch_bounds__(kFtThreads, 1) fir_tmem_kernel(const __grid_co
             unsigned hv[16], lo[16];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const unsigned u0 = (unsigned)__dp2a_lo((int)v[j].x, 0x0101, (int)KHV), u1 = (unsigned)__dp2a_lo((int)v[j].y, 0x0101, (int)KHV);
-                const unsigned u2 = (unsigned)__dp2a_lo((int)v[j].z, 0x0101, (int)KHV), u3 = (unsigned)__dp2a_lo((int)v[j].w, 0x0101, (int)KHV);
-                hv[2 * j] = hsub2_bits(((u1 >> 7) << 16) + (u0 >> 7), 0x66006600u);           // (1024 + hv + 512) - 1536
-                hv[2 * j + 1] = hsub2_bits(((u3 >> 7) << 16) + (u2 >> 7), 0x66006600u);
-                lo[2 * j] = hfma2_bits((((u1 & 127u) << 16) | (u0 & 127u)) | 0x64006400u, 0x20002000u, 0xC800C800u);   // (1024 + lo) / 128 - 8
-                lo[2 * j + 1] = hfma2_bits((((u3 & 127u) << 16) | (u2 & 127u)) | 0x64006400u, 0x20002000u, 0xC800C800u);
+                const unsigned u0 = (unsigned)__dp2a_lo((int)v[j].x, 0x0202, (int)KHV2), u1 = (unsigned)__dp2a_lo((int)v[j].y, 0x0202, (int)KHV2);
+                const unsigned u2 = (unsigned)__dp2a_lo((int)v[j].z, 0x0202, (int)KHV2), u3 = (unsigned)__dp2a_lo((int)v[j].w, 0x0202, (int)KHV2);
+                hv[2 * j] = hsub2_bits(__byte_perm(u0, u1, 0x6521), 0x66006600u);             // (1024 + hv + 512) - 1536
+                hv[2 * j + 1] = hsub2_bits(__byte_perm(u2, u3, 0x6521), 0x66006600u);
+                lo[2 * j] = hfma2_bits(__byte_perm(u0, u1, 0x7430), 0x1C001C00u, 0xC400C400u);   // (1024 + 2 lo) / 256 - 4 = lo / 128
+                lo[2 * j + 1] = hfma2_bits(__byte_perm(u2, u3, 0x7430), 0x1C001C00u, 0xC400C400u);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(RE(rslot));                // the raw slot may be refilled (its frames are in registers)

@@ -301,6 +301,17 @@ static inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x)
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline unsigned __brev(unsigned x) { unsigned r = 0; for (int i = 0; i < 32; i++) if (x & (1u << i)) r |= 1u << (31 - i); return r; }
 template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
+    const unsigned long long v = ((unsigned long long)y << 32) | x;
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) {
+        const unsigned sel = (s >> (4 * i)) & 0xFu;
+        unsigned b = (unsigned)(v >> (8 * (sel & 7u))) & 0xFFu;
+        if (sel & 8u) b = (b & 0x80u) ? 0xFFu : 0u;
+        r |= b << (8 * i);
+    }
+    return r;
+}
 static inline int __dp2a_lo(int a, int b, int c) {
     short a0 = (short)(a & 0xffff), a1 = (short)((unsigned)a >> 16);
     signed char b0 = (signed char)(b & 0xff), b1 = (signed char)((b >> 8) & 0xff);
