@@ -314,7 +314,7 @@ static_assert(MelC<80>::QUADS <= MelC<128>::QUADS && MelC<80>::SLOTS <= MelC<128
 template <int FMT> struct LmSmem {
     static constexpr int TILE_WORDS = ((FMT == B2A_FMT_S16 ? (LM_TILE / 2 + (LM_TILE / kHop + 2)) : LM_TILE_WORDS) + 3) / 4 * 4;   // keeps the buffers behind it 16-byte aligned
     static constexpr int HOPW = FMT == B2A_FMT_S16 ? (kHop / 2 + 1) : LM_HOPW;      // words between frames (81: odd, conflict free)
-    static constexpr int WORDS = TILE_WORDS + 2 * LM_FRAMES * LM_EXP + kNFFT + 2 * 200 + 2 * 202 + 12 + LM_MELW_WORDS + LM_MELOFF_WORDS + 12 * LM_GBATCH;   // + LM_GBATCH x 6 int64 gather descriptors
+    static constexpr int WORDS = TILE_WORDS + 2 * LM_FRAMES * LM_EXP + kNFFT + 2 * 200 + 2 * 202 + 12 + LM_MELW_WORDS + LM_MELOFF_WORDS + 12 * LM_GBATCH + 4 * LM_GBATCH;   // + LM_GBATCH x 6 int64 gather descriptors
     static constexpr int CTAS = FMT == B2A_FMT_S16 ? LM_S16_CTAS : 2;
 };
 
@@ -334,7 +334,8 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
     unsigned long long* s_bar = (unsigned long long*)(s_red + 8);       // 2 mbarriers: [0] tile done (power spectra consumed, next samples in place), [1] exchange consumed
     float4* s_flat4 = (float4*)(s_red + 12);                            // mel weights: [warp][QUADS] quads (16-byte aligned)
     unsigned* s_moff = (unsigned*)(s_flat4 + LM_MELW_WORDS / 4);         // [warp][SLOTS] byte offset of the slot's first power bin
-    i64* s_g = (i64*)(s_moff + LM_MELOFF_WORDS);                          // [LM_GBATCH][6]: lo0, add0, bound1, add1, bound2, mode of the CTA's next gathered tiles
+    int4* s_gi = (int4*)(s_moff + LM_MELOFF_WORDS);                       // [LM_GBATCH] interior gathered tiles in 32 bits: {first source chunk, split chunk, delta chunks, mode}
+    i64* s_g = (i64*)(s_gi + LM_GBATCH);                          // [LM_GBATCH][6]: lo0, add0, bound1, add1, bound2, mode of the CTA's next gathered tiles
 
     const int tid = threadIdx.x;
     const LogMelTables* tab = p.tab;
@@ -387,7 +388,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
     };
     const bool src_vec = (((uintptr_t)p.audio) & 15) == 0;                 // gathered tiles: 16-byte loads from the untrimmed PCM
     const bool trim_vec = gather && (((uintptr_t)p.trim_out) & 15) == 0;   // ... and 16-byte stores of the trimmed PCM
-    struct Src { const char* row; i64 q0; int mode; const i64* g; };   // mode 0: generic (reflect / zero pad), 1: interior s16, 2: interior f32; g: gather descriptor (shared memory)
+    struct Src { const char* row; i64 q0; int mode; const i64* g; const int4* gi; };   // mode 0: generic (reflect / zero pad), 1: interior s16, 2: interior f32; g: gather descriptor (shared memory)
     // gather: source sample of trimmed index q (segment search; the two segments cached per tile cover an interior tile)
     auto seg_of = [&](i64 q) -> int {
         int lo = 0, hi = n_seg - 1;
@@ -418,6 +419,11 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
                                       (bound1 >= q0 + LM_TILE || add1 + q0 + LM_TILE <= p.n_src);
                 i64* g = s_g + 6 * tid;
                 g[0] = lo0; g[1] = add0; g[2] = bound1; g[3] = add1; g[4] = bound2; g[5] = interior ? 1 : 0;
+                // what the interior loader needs, in chunks of 8 samples and 32 bits (a clip's source offsets fit: n_src < 2^34):
+                // chunk k of the tile is source chunk first + k (+ delta from the split on, where the second segment starts)
+                const i64 split = (bound1 - q0) >> 3;
+                s_gi[tid] = make_int4((int)((add0 + q0) >> 3), (int)(split < LM_CHUNKS ? split : LM_CHUNKS), (int)((add1 - add0) >> 3),
+                                      interior && p.n_src < ((i64)1 << 34) ? 1 : 0);
             }
         }
     };
@@ -429,8 +435,9 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
         r.row = GATHER ? (const char*)p.audio : (const char*)p.audio + (size_t)b * (size_t)p.row_stride * elem;
         r.q0 = tile * (LM_FRAMES * kHop) - 200;
         r.g = s_g + 6 * slot;
+        r.gi = s_gi + slot;
         if (gather) {
-            r.mode = (int)r.g[5];
+            r.mode = r.gi->w;
         } else {
             const bool interior = r.q0 >= 0 && r.q0 + LM_TILE <= n_act && ((((uintptr_t)(r.row + r.q0 * elem)) & 7) == 0);
             r.mode = interior ? (S16 ? 1 : 2) : 0;
@@ -493,14 +500,12 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
         }
     };
     auto fetch_s16_chunks = [&](const Src& sc, uint4 (&pre)[LM_PRE4]) {
-        // the second segment's chunks sit `delta` chunks further on (a clip's source offsets fit 32 bits in chunks)
-        const uint4* g0 = (const uint4*)((const short*)p.audio + sc.g[1] + sc.q0);
-        const int split = (int)min((sc.g[2] - sc.q0) >> 3, (i64)LM_CHUNKS);         // first chunk of the second segment
-        const int delta = (int)((sc.g[3] - sc.g[1]) >> 3);
+        const int4 d = *sc.gi;                                                  // {first source chunk, split, delta, mode}
+        const uint4* g0 = (const uint4*)p.audio + ((unsigned)d.x + (unsigned)tid);
 #pragma unroll
         for (int i = 0; i < LM_PRE4; i++) {
-            const int k = tid + LM_THREADS * i;
-            if (k < LM_CHUNKS) pre[i] = ldg_pinned16(g0 + (k + (k >= split ? delta : 0)));
+            const int k0 = LM_THREADS * i;                                         // k = k0 + tid
+            if (k0 + LM_THREADS <= LM_CHUNKS || tid < LM_CHUNKS - k0) pre[i] = ldg_pinned16(g0 + (k0 + (k0 + tid >= d.y ? d.z : 0)));
         }
     };
     // plain (not gathered) s16 tiles keep the 4-byte form: pair pr (samples 2pr, 2pr+1) lives at word pr + pr / 80 of the skewed
@@ -551,6 +556,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
         Src nsc;
         nsc.mode = -1;
         nsc.g = s_g;
+        nsc.gi = s_gi;
         const int nit = (int)it + 1;                                             // iteration index of the next tile
         if (gather && nit % LM_GBATCH == 0) {
             __syncthreads();                                                       // every reader of the old batch is done
