@@ -129,6 +129,34 @@ class AudioFrontend:
             return r.pcm.clone(), r.mel.clone(), kept
         return r.pcm, r.mel, kept
 
+    # -- process_audio's front half on a file (audio_processor.py:1039-1080) in ONE device pass ------------------------
+    def process_audio_file(self, input_path: str, padding: int = whisper_audio.N_SAMPLES) -> Tuple[str, "object", List[List[int]]]:
+        """convert_to_wav + preprocess_audio + the log-mel of ``model.transcribe`` for one upload, fused: the file is read
+        (WAV parsed, anything else decoded on the host) once, ``b2a_pipeline`` runs once, the trimmed 16 kHz mono WAV is
+        written once.  Returns (wav path for the diarizer, log-mel [n_mels, T] on the device, kept [start_ms, end_ms]).
+
+        The WAV lands where the two helpers would have left it: ``<stem>.wav`` for a non-WAV upload (convert_to_wav's name,
+        :904-906), ``<stem>.trimmed.wav`` for a WAV input that had to change (rate, channels, sample format or removed
+        silence), the input path itself for a 16 kHz mono s16 WAV from which nothing was removed.  Errors surface as
+        ``subprocess.CalledProcessError`` like convert_to_wav's (:928-930)."""
+        logging.info(f"🔄 預處理音頻: {os.path.basename(input_path)}")
+        try:
+            pcm, rate = wavio.read_audio(input_path)
+        except (wavio.UnsupportedAudio, OSError, RuntimeError) as e:
+            logging.error(f"❌ 檔案轉換失敗: {e}")
+            raise subprocess.CalledProcessError(1, ["b2a_pipeline", input_path], stderr=str(e).encode()) from e
+        out_pcm, mel, kept = self.process_pcm(pcm, rate, padding=padding, copy=False)
+        is_wav = input_path.lower().endswith(".wav")
+        canonical = is_wav and rate == ops.SAMPLE_RATE and pcm.ndim == 1 and pcm.dtype == np.int16
+        if canonical and int(out_pcm.shape[0]) == len(pcm):
+            out_path = input_path                                       # nothing to rewrite
+        else:
+            stem = os.path.splitext(input_path)[0]
+            out_path = stem + (".trimmed.wav" if is_wav else ".wav")
+            wavio.write_wav_s16(out_path, out_pcm.cpu().numpy(), ops.SAMPLE_RATE)
+        logging.info("✅ 音頻預處理完成")
+        return out_path, mel.clone(), kept
+
     def stream(self, n_in: int, in_rate: int, channels: int = 2, dtype=None, padding: int = 0, depth: int = 2) -> "ClipStream":
         """pipelined submit()/result() front-end for many same-shaped clips (uploads overlap kernels and downloads)"""
         return ClipStream(self, n_in, in_rate, channels, dtype, padding, depth)

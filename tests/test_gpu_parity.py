@@ -753,3 +753,38 @@ def test_logmel_row_limit_is_reported(ops, T):
     assert ops.launch_count() == n0
     assert lib.b2a_log_mel(C.c_void_p(x.data_ptr()), 0, 1, n - 160, n - 160, None, 0, 128, 0, C.c_void_p(out.data_ptr()), None,
                            C.c_void_p(out.data_ptr()), 16, None) == -3      # one frame fewer passes the limit (and then fails on the workspace size)
+
+
+def test_process_audio_file_equals_the_two_helpers(ops, T, tmp_path):
+    """AudioFrontend.process_audio_file: process_audio's front half (audio_processor.py:1039-1080) as ONE read, one
+    b2a_pipeline call and one write — same WAV bytes as convert_to_wav followed by preprocess_audio, same kept table, and
+    the log-mel Whisper would compute from that WAV (padding = N_SAMPLES as transcribe passes it)"""
+    import shutil
+    from audio_processor_b200 import synth, wavio, whisper_audio
+    from audio_processor_b200.service import AudioFrontend
+    from oracle import whisper_logmel as wl
+    x = synth.synth_clip(9, 44100, 2, 11.0, 0.35, device="cuda").cpu().numpy()
+    a_dir, b_dir = tmp_path / "a", tmp_path / "b"
+    a_dir.mkdir(); b_dir.mkdir()
+    src_a, src_b = str(a_dir / "upload.wav"), str(b_dir / "upload.wav")
+    wavio.write_wav_s16(src_a, x, 44100)
+    shutil.copy(src_a, src_b)
+    fe = AudioFrontend()
+    two_step, kept2 = fe.preprocess_audio_segments(fe.convert_to_wav(src_a))
+    path, mel, kept = fe.process_audio_file(src_b)
+    assert kept == kept2 and path.endswith(".trimmed.wav")
+    y2, _ = wavio.read_wav(two_step)
+    y, sr = wavio.read_wav(path)
+    assert sr == 16000 and np.array_equal(y, y2)
+    ref = wl.log_mel_spectrogram(y.astype(np.float32) / 32768.0, 80, padding=whisper_audio.N_SAMPLES).numpy()
+    assert mel.shape == ref.shape and np.abs(mel.cpu().numpy() - ref).max() <= MEL_TOL
+    # a canonical WAV without silence comes back under its own name
+    tone = (np.sin(np.arange(16000 * 3) * 0.05) * 8000).astype(np.int16)
+    src_c = str(tmp_path / "tone.wav")
+    wavio.write_wav_s16(src_c, tone, 16000)
+    path_c, mel_c, kept_c = fe.process_audio_file(src_c)
+    assert path_c == src_c and kept_c == [[0, 3000]] and mel_c.shape == (80, (len(tone) + whisper_audio.N_SAMPLES) // 160)
+    import subprocess
+    bad = tmp_path / "x.m4a"; bad.write_bytes(b"not audio")
+    with pytest.raises(subprocess.CalledProcessError):
+        fe.process_audio_file(str(bad))
