@@ -41,16 +41,14 @@ constexpr int LM_TILE = LM_FRAMES * kHop + 240;     // 5360 samples
 constexpr int LM_SKEW = 2;                          // extra words per hop (bank de-phasing, keeps 8-byte alignment)
 constexpr int LM_HOPW = kHop + LM_SKEW;             // words between consecutive frames in the skewed tile
 constexpr int LM_TILE_WORDS = LM_TILE + LM_SKEW * (LM_TILE / kHop + 1);
-constexpr int LM_EXP = 201;                         // exchange pitch per frame, in complex values (odd: conflict free)
+#ifndef LM_EX128
+#define LM_EX128 1                                  // exchange buffer moved as 16-byte pairs of neighbouring columns
+#endif
+// exchange pitch per frame, in complex values.  16-byte accesses (two neighbouring columns): rows 1616 bytes apart keep every
+// access aligned and the 8 lanes of a quarter warp on distinct 16-byte bank groups (101 f mod 8).  (8-byte accesses: 201, odd.)
+constexpr int LM_EXP = LM_EX128 ? 202 : 201;
 #ifndef LM_S16_CTAS
 #define LM_S16_CTAS 3
-#endif
-#ifndef LM_S1_UNROLL
-#define LM_S1_UNROLL 1                              // stage-1 column loop (4 iterations)
-#endif
-constexpr int kS1Unroll = LM_S1_UNROLL;
-#ifndef LM_S1_PREFETCH
-#define LM_S1_PREFETCH 0                            // s16: load the next column's raw words before this column's butterflies
 #endif
 constexpr int LM_GBATCH = 32;                       // gathered tiles whose segment descriptors are looked up together
 constexpr int LM_PP = 203;                          // power-spectrum pitch per frame, in floats (odd)
@@ -360,11 +358,22 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
 
     const int u = tid >> 5, f = tid & 31;        // role (warp-uniform), frame within the tile
     const int k1a = u, k1b = (u == 0) ? 5 : 10 - u;
+#if LM_EX128
+    // role u owns the columns n2 = 4u .. 4u + 3 (neighbours in the exchange buffer: one 16-byte store per pair)
+    const float* ps = s_tile + LM_HOPW * f + 8 * u;          // f32 tile: + 40 n1 + 2 j + 2 (n1 / 4)
+    const unsigned* ps16 = s_tile16 + SM::HOPW * f + 4 * u;   // s16 tile (words = sample pairs): + 20 n1 + j + (n1 / 4)
+    const float* pw = s_win + 8 * u;                         // + 40 n1 + 2 j
+    const float2* pt = s_tw200 + 40 * u;                     // + 10 j + k1
+    float2* pex_w = s_ex + LM_EXP * f + 4 * u;               // + 20 k1 + j
+    constexpr int JS = 1, JP = 2, JT = 10;                   // per-column steps of the tile (pairs), the f32 tile / window (floats), the twiddles
+#else
     const float* ps = s_tile + LM_HOPW * f + 2 * u;          // f32 tile: + 40 n1 + 10 j + 2 (n1 / 4)
     const unsigned* ps16 = s_tile16 + SM::HOPW * f + u;       // s16 tile (words = sample pairs): + 20 n1 + 5 j + (n1 / 4)
     const float* pw = s_win + 2 * u;                         // + 40 n1 + 10 j
     const float2* pt = s_tw200 + 10 * u;                     // + 50 j + k1
     float2* pex_w = s_ex + LM_EXP * f + u;                   // + 20 k1 + 5 j
+    constexpr int JS = 5, JP = 10, JT = 50;
+#endif
     const float2* pex_a = s_ex + LM_EXP * f + 20 * k1a;      // + n2
     const float2* pex_b = s_ex + LM_EXP * f + 20 * k1b;
     float* pP = s_P + LM_PP * f;
@@ -580,48 +589,48 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
         }
 
         // ---- stage 1: radix-10 butterflies over n1 for n2 = u + 5j, twiddle, transpose into s_ex ----
-#if LM_S1_PREFETCH
-        unsigned raw[10];
-        if (S16) {
-#pragma unroll
-            for (int n1 = 0; n1 < 10; n1++) raw[n1] = ps16[20 * n1 + n1 / 4];
-        }
-#endif
-#pragma unroll kS1Unroll
-        for (int j = 0; j < 4; j++) {
+        // one column: window, radix-10 butterflies, stage twiddles -> v[k1]
+        auto column = [&](int j, cpx (&v)[10]) {
             cpx x[10], y[10];
 #pragma unroll
             for (int n1 = 0; n1 < 10; n1++) {
                 float2 xv;
                 if (S16) {
-#if LM_S1_PREFETCH
-                    const unsigned w = raw[n1];
-#else
-                    const unsigned w = ps16[5 * j + 20 * n1 + n1 / 4];
-#endif
+                    const unsigned w = ps16[JS * j + 20 * n1 + n1 / 4];
                     xv = make_float2((float)(short)(w & 0xffff), (float)(short)(w >> 16));
                 } else {
-                    xv = *(const float2*)(ps + 10 * j + 40 * n1 + LM_SKEW * (n1 / 4));
+                    xv = *(const float2*)(ps + JP * j + 40 * n1 + LM_SKEW * (n1 / 4));
                 }
-                const float2 wv = *(const float2*)(pw + 10 * j + 40 * n1);
+                const float2 wv = *(const float2*)(pw + JP * j + 40 * n1);
                 x[n1].r = xv.x * wv.x;
                 x[n1].i = xv.y * wv.y;
             }
-#if LM_S1_PREFETCH
-            if (S16 && j < 3) {                 // the next column's raw words travel under this column's butterflies
-#pragma unroll
-                for (int n1 = 0; n1 < 10; n1++) raw[n1] = ps16[5 * (j + 1) + 20 * n1 + n1 / 4];
-            }
-#endif
             dft10(x, y);
 #pragma unroll
             for (int k1 = 0; k1 < 10; k1++) {
-                const float2 tw = pt[50 * j + k1];
+                const float2 tw = pt[JT * j + k1];
                 const cpx w = {tw.x, tw.y};
-                const cpx v = (k1 == 0) ? y[0] : cmul(y[k1], w);
-                pex_w[5 * j + 20 * k1] = make_float2(v.r, v.i);
+                v[k1] = (k1 == 0) ? y[0] : cmul(y[k1], w);
             }
+        };
+#if LM_EX128
+#pragma unroll 1
+        for (int j = 0; j < 4; j += 2) {
+            cpx va[10], vb[10];
+            column(j, va);
+            column(j + 1, vb);
+#pragma unroll
+            for (int k1 = 0; k1 < 10; k1++) *(float4*)(pex_w + j + 20 * k1) = make_float4(va[k1].r, va[k1].i, vb[k1].r, vb[k1].i);
         }
+#else
+#pragma unroll 1
+        for (int j = 0; j < 4; j++) {
+            cpx v[10];
+            column(j, v);
+#pragma unroll
+            for (int k1 = 0; k1 < 10; k1++) pex_w[JS * j + 20 * k1] = make_float2(v[k1].r, v[k1].i);
+        }
+#endif
         __syncthreads();   // exchange complete; every stage-1 read of s_tile is done
 
         // ---- next tile -> s_tile (its registers are free again before stage 2 needs them) ----
@@ -637,10 +646,17 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
             cpx za[20], zb[20];
             {
                 cpx xa[20], xb[20];
+#if LM_EX128
+#pragma unroll
+                for (int n2 = 0; n2 < 20; n2 += 2) { const float4 v = *(const float4*)(pex_a + n2); xa[n2] = {v.x, v.y}; xa[n2 + 1] = {v.z, v.w}; }
+#pragma unroll
+                for (int n2 = 0; n2 < 20; n2 += 2) { const float4 v = *(const float4*)(pex_b + n2); xb[n2] = {v.x, v.y}; xb[n2 + 1] = {v.z, v.w}; }
+#else
 #pragma unroll
                 for (int n2 = 0; n2 < 20; n2++) { const float2 v = pex_a[n2]; xa[n2] = {v.x, v.y}; }
 #pragma unroll
                 for (int n2 = 0; n2 < 20; n2++) { const float2 v = pex_b[n2]; xb[n2] = {v.x, v.y}; }
+#endif
                 lm_arrive(s_bar + 1, f);       // this warp has consumed its part of the exchange buffer ...
                 dft20(xa, za);
                 dft20(xb, zb);
