@@ -13,10 +13,10 @@
 //    16-byte vector loads on the interior path), skewed by 2 words per hop so that the 32 lanes of a warp,
 //    whose frames start 160 samples apart, hit distinct banks.
 //  * one real 400-point FFT per frame = one complex 200-point FFT of (even, odd) samples, split over the 5 roles:
-//    role u does the radix-10 butterflies (2x5 prime-factor) of columns n2 = u + 5j, applies the stage twiddles,
-//    transposes through shared memory (pitch 201 complex per frame: conflict free), then the radix-20 butterflies
-//    (4x5 prime-factor) of output residues {u, 10-u} mod 10 — so the real-FFT unpack pairs (k, 200-k) stay inside
-//    one thread.  The unpack produces 4|X|^2 (16 flops per conjugate pair); the 1/4 lives in the mel weights.
+//    role u does the radix-10 butterflies (2x5 prime-factor) of columns n2 = 4u .. 4u + 3, applies the stage twiddles,
+//    transposes through shared memory (pitch 202 complex per frame; two neighbouring columns per 16-byte access), then the
+//    radix-20 butterflies (4x5 prime-factor) of output residues {u, 10-u} mod 10 — so the real-FFT unpack pairs (k, 200-k)
+//    stay inside one thread.  The unpack produces 4|X|^2 (16 flops per conjugate pair); the 1/4 lives in the mel weights.
 //  * mel projection: warp u owns mels u, u + 5, u + 10, ... (lane = frame), so all five warps run the same fully unrolled
 //    code over the sparse filterbank (mel_tables_gen.inc: weights as 16-byte shared-memory broadcasts at compile-time
 //    offsets, conflict-free loads of the power bins at pitch 203).  log10, running max/min and the [n_mels][T] store
@@ -41,12 +41,9 @@ constexpr int LM_TILE = LM_FRAMES * kHop + 240;     // 5360 samples
 constexpr int LM_SKEW = 2;                          // extra words per hop (bank de-phasing, keeps 8-byte alignment)
 constexpr int LM_HOPW = kHop + LM_SKEW;             // words between consecutive frames in the skewed tile
 constexpr int LM_TILE_WORDS = LM_TILE + LM_SKEW * (LM_TILE / kHop + 1);
-#ifndef LM_EX128
-#define LM_EX128 1                                  // exchange buffer moved as 16-byte pairs of neighbouring columns
-#endif
-// exchange pitch per frame, in complex values.  16-byte accesses (two neighbouring columns): rows 1616 bytes apart keep every
-// access aligned and the 8 lanes of a quarter warp on distinct 16-byte bank groups (101 f mod 8).  (8-byte accesses: 201, odd.)
-constexpr int LM_EXP = LM_EX128 ? 202 : 201;
+// exchange pitch per frame, in complex values.  The buffer is accessed as 16-byte pairs of neighbouring columns: rows 1616 bytes
+// apart keep every access aligned and the 8 lanes of a quarter warp on distinct 16-byte bank groups (101 f mod 8)
+constexpr int LM_EXP = 202;
 #ifndef LM_S16_CTAS
 #define LM_S16_CTAS 3
 #endif
@@ -358,7 +355,6 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
 
     const int u = tid >> 5, f = tid & 31;        // role (warp-uniform), frame within the tile
     const int k1a = u, k1b = (u == 0) ? 5 : 10 - u;
-#if LM_EX128
     // role u owns the columns n2 = 4u .. 4u + 3 (neighbours in the exchange buffer: one 16-byte store per pair)
     const float* ps = s_tile + LM_HOPW * f + 8 * u;          // f32 tile: + 40 n1 + 2 j + 2 (n1 / 4)
     const unsigned* ps16 = s_tile16 + SM::HOPW * f + 4 * u;   // s16 tile (words = sample pairs): + 20 n1 + j + (n1 / 4)
@@ -366,14 +362,6 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
     const float2* pt = s_tw200 + 40 * u;                     // + 10 j + k1
     float2* pex_w = s_ex + LM_EXP * f + 4 * u;               // + 20 k1 + j
     constexpr int JS = 1, JP = 2, JT = 10;                   // per-column steps of the tile (pairs), the f32 tile / window (floats), the twiddles
-#else
-    const float* ps = s_tile + LM_HOPW * f + 2 * u;          // f32 tile: + 40 n1 + 10 j + 2 (n1 / 4)
-    const unsigned* ps16 = s_tile16 + SM::HOPW * f + u;       // s16 tile (words = sample pairs): + 20 n1 + 5 j + (n1 / 4)
-    const float* pw = s_win + 2 * u;                         // + 40 n1 + 10 j
-    const float2* pt = s_tw200 + 10 * u;                     // + 50 j + k1
-    float2* pex_w = s_ex + LM_EXP * f + u;                   // + 20 k1 + 5 j
-    constexpr int JS = 5, JP = 10, JT = 50;
-#endif
     const float2* pex_a = s_ex + LM_EXP * f + 20 * k1a;      // + n2
     const float2* pex_b = s_ex + LM_EXP * f + 20 * k1b;
     float* pP = s_P + LM_PP * f;
@@ -613,7 +601,6 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
                 v[k1] = (k1 == 0) ? y[0] : cmul(y[k1], w);
             }
         };
-#if LM_EX128
 #pragma unroll 1
         for (int j = 0; j < 4; j += 2) {
             cpx va[10], vb[10];
@@ -622,15 +609,6 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
 #pragma unroll
             for (int k1 = 0; k1 < 10; k1++) *(float4*)(pex_w + j + 20 * k1) = make_float4(va[k1].r, va[k1].i, vb[k1].r, vb[k1].i);
         }
-#else
-#pragma unroll 1
-        for (int j = 0; j < 4; j++) {
-            cpx v[10];
-            column(j, v);
-#pragma unroll
-            for (int k1 = 0; k1 < 10; k1++) pex_w[JS * j + 20 * k1] = make_float2(v[k1].r, v[k1].i);
-        }
-#endif
         __syncthreads();   // exchange complete; every stage-1 read of s_tile is done
 
         // ---- next tile -> s_tile (its registers are free again before stage 2 needs them) ----
@@ -646,17 +624,10 @@ __global__ void __launch_bounds__(LM_THREADS, LmSmem<FMT>::CTAS) stft_mel_kernel
             cpx za[20], zb[20];
             {
                 cpx xa[20], xb[20];
-#if LM_EX128
 #pragma unroll
                 for (int n2 = 0; n2 < 20; n2 += 2) { const float4 v = *(const float4*)(pex_a + n2); xa[n2] = {v.x, v.y}; xa[n2 + 1] = {v.z, v.w}; }
 #pragma unroll
                 for (int n2 = 0; n2 < 20; n2 += 2) { const float4 v = *(const float4*)(pex_b + n2); xb[n2] = {v.x, v.y}; xb[n2 + 1] = {v.z, v.w}; }
-#else
-#pragma unroll
-                for (int n2 = 0; n2 < 20; n2++) { const float2 v = pex_a[n2]; xa[n2] = {v.x, v.y}; }
-#pragma unroll
-                for (int n2 = 0; n2 < 20; n2++) { const float2 v = pex_b[n2]; xb[n2] = {v.x, v.y}; }
-#endif
                 lm_arrive(s_bar + 1, f);       // this warp has consumed its part of the exchange buffer ...
                 dft20(xa, za);
                 dft20(xb, zb);
