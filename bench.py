@@ -21,6 +21,8 @@ Keys beyond the base contract:
   value      device-resident throughput (inputs in HBM when the timed region starts)
   e2e        same metric through the public host API (AudioFrontend.process_pcm) with pinned HOST buffers:
              H2D of the input and D2H of trimmed PCM + log-mel + segment table inside the timed region
+             (e2e.h2d_ceiling_gbs = the box's upload-only ceiling measured in the same run, e2e.duplex_h2d_ceiling_gbs = the
+             upload rate plain copies reach with this step's downloads flowing against them; frac_of_* = the e2e run's upload rate over each)
   roofline   dominant kernel: its own algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json hbm_gbs;
              `pipeline_*` = whole-step algorithmic bytes / step time
   cpu_baseline  the oracle stages (libswresample .so, literal pydub loop on audioop, torch.stft f32) on one
@@ -564,13 +566,40 @@ def run_b200(args):
         h2d_local = 16 * (512 << 20) / (ce0.elapsed_time(ce1) * 1e-3) / 1e9
         barrier()
         h2d_sum = sum_over_ranks(h2d_local)
-        del hc, dc
+        # ... and the same with the downloads flowing against it, in this workload's own proportions (bi up : bo down per step):
+        # on this pool the host moves less in both directions at once than the upload-only figure suggests (profiles/r02_pcie_duplex.txt)
+        frac_dn = min(float(bo) / float(bi), 1.0) if bi > 0 else 0.0
+        n_dn = max(int((512 << 20) * frac_dn) // 4096 * 4096, 4096)
+        hd = torch.empty(n_dn, dtype=torch.uint8).pin_memory()
+        dd = torch.empty(n_dn, dtype=torch.uint8, device=dev)
+        s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        torch.cuda.synchronize()
+
+        def duplex_round():
+            with torch.cuda.stream(s_up):
+                dc.copy_(hc, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                hd.copy_(dd, non_blocking=True)
+        for _ in range(2):
+            duplex_round()
+        torch.cuda.synchronize()
+        barrier()
+        td0 = time.perf_counter()
+        for _ in range(12):
+            duplex_round()
+        s_up.synchronize(); s_dn.synchronize()
+        duplex_s = max_over_ranks((time.perf_counter() - td0) * 1e3) / 1e3
+        duplex_h2d = world * 12 * (512 << 20) / duplex_s / 1e9
+        barrier()
+        del hc, dc, hd, dd
         e2e_h2d_rate = sum_over_ranks(float(bi)) * e2e_steps / (dt_ms / 1e3) / 1e9
         e2e = {"value": sum_over_ranks(e2e_audio_h) * e2e_steps / (dt_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(bi),
                "d2h_bytes_per_step": int(bo), "ms_per_step": dt_ms / e2e_steps, "steps": e2e_steps,
                "h2d_ceiling_gbs": round(h2d_sum, 2), "h2d_achieved_gbs": round(e2e_h2d_rate, 2),
                "frac_of_h2d_ceiling": round(e2e_h2d_rate / h2d_sum, 3) if h2d_sum > 0 else None,
                "h2d_ceiling_note": "all ranks copying 512 MB pinned buffers to their GPUs concurrently (16 x cudaMemcpyAsync, CUDA events), summed over ranks",
+               "duplex_h2d_ceiling_gbs": round(duplex_h2d, 2), "frac_of_duplex_ceiling": round(e2e_h2d_rate / duplex_h2d, 3) if duplex_h2d > 0 else None,
+               "duplex_ceiling_note": "the same upload loop with downloads in this step's d2h : h2d proportion on a second stream (12 rounds, all ranks at once, slowest rank): the H2D rate copies alone reach when both directions are busy",
                "api": "whisper_audio.log_mel_spectrogram(host)" if logmel_only else "AudioFrontend.stream(...).submit(host pcm) / result(): 2 clips in flight"}
     t_load1 = time.time()
     clocks = sampler.stop(t_load0, t_load1) if sampler else None
